@@ -1,0 +1,394 @@
+"""ctypes front-ends for the CPU oracle (oracle/_build/librns_oracle.so) and, when built, the
+unmodified reference behind oracle/_ref/libref_shim.so.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs — never by the product package (troy-nova_b200/).
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "_build", "librns_oracle.so")
+REF_SHIM_SO = os.path.join(HERE, "_ref", "libref_shim.so")
+
+BFV, CKKS, BGV = 1, 2, 3
+ASSIGN_OVERWRITE, ASSIGN_ADD_INPLACE, ASSIGN_OVERWRITE_EXCEPT_FIRST = 0, 1, 2
+TABLES_COMPONENTWISE, TABLES_KS_SET_PRODUCTS, TABLES_KS_SKIP_FINALS = 0, 1, 2
+
+u64p = C.POINTER(C.c_uint64)
+
+
+def _p(a):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(u64p)
+
+
+def build_oracle():
+    """Compile the C restatement (gcc, seconds)."""
+    subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
+
+
+def build_ref():
+    """Compile the unmodified reference + shim; needs /root/reference (this container only)."""
+    subprocess.check_call(["make", "-s", "-j8", "-C", HERE, "ref"])
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(ORACLE_SO):
+            build_oracle()
+        L = C.CDLL(ORACLE_SO)
+        L.ro_ctx_create.restype = C.c_void_p
+        L.ro_ctx_create.argtypes = [C.c_uint, u64p, C.c_size_t, C.c_uint64, C.c_int]
+        L.ro_ctx_destroy.argtypes = [C.c_void_p]
+        for f in ("ro_ctx_modulus", "ro_ctx_root"):
+            getattr(L, f).restype = C.c_uint64
+            getattr(L, f).argtypes = [C.c_void_p, C.c_size_t]
+        for f in ("ro_ctx_root_powers", "ro_ctx_inv_root_powers"):
+            getattr(L, f).restype = u64p
+            getattr(L, f).argtypes = [C.c_void_p, C.c_size_t]
+        L.ro_min_primitive_root.restype = C.c_uint64
+        L.ro_min_primitive_root.argtypes = [C.c_uint64, C.c_uint64]
+        L.ro_plain_modulus_batching.restype = C.c_uint64
+        L.ro_plain_modulus_batching.argtypes = [C.c_size_t, C.c_uint]
+        L.ro_coeff_modulus_create.argtypes = [C.c_size_t, C.POINTER(C.c_uint), C.c_size_t, u64p]
+        L.ro_get_primes.argtypes = [C.c_uint64, C.c_uint, C.c_size_t, u64p]
+        for f in ("ro_mulmod", "ro_powmod"):
+            getattr(L, f).restype = C.c_uint64
+            getattr(L, f).argtypes = [C.c_uint64] * 3
+        L.ro_invmod.restype = C.c_uint64
+        L.ro_invmod.argtypes = [C.c_uint64] * 2
+        L.ro_barrett_reduce64.restype = C.c_uint64
+        L.ro_barrett_reduce64.argtypes = [C.c_uint64] * 2
+        L.ro_barrett_reduce128.restype = C.c_uint64
+        L.ro_barrett_reduce128.argtypes = [C.c_uint64] * 3
+        L.ro_shoup_quotient.restype = C.c_uint64
+        L.ro_shoup_quotient.argtypes = [C.c_uint64] * 2
+        L.ro_shoup_mul_lazy.restype = C.c_uint64
+        L.ro_shoup_mul_lazy.argtypes = [C.c_uint64] * 4
+        L.ro_is_prime.argtypes = [C.c_uint64]
+        ntt_args = [C.c_void_p, u64p, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t]
+        L.ro_ntt_fwd.argtypes = ntt_args
+        L.ro_ntt_inv.argtypes = ntt_args
+        L.ro_add.argtypes = [C.c_void_p, u64p, u64p, u64p, C.c_size_t, C.c_size_t]
+        L.ro_sub.argtypes = [C.c_void_p, u64p, u64p, u64p, C.c_size_t, C.c_size_t]
+        L.ro_negate.argtypes = [C.c_void_p, u64p, u64p, C.c_size_t, C.c_size_t]
+        L.ro_dyadic_convolute.argtypes = [C.c_void_p, u64p, C.c_size_t, u64p, C.c_size_t, u64p, C.c_size_t]
+        L.ro_dyadic_square.argtypes = [C.c_void_p, u64p, u64p, C.c_size_t]
+        L.ro_dyadic_broadcast.argtypes = [C.c_void_p, u64p, u64p, u64p, C.c_size_t, C.c_size_t, C.c_int]
+        L.ro_negacyclic_shift.argtypes = [C.c_void_p, u64p, C.c_size_t, u64p, C.c_size_t, C.c_size_t]
+        L.ro_galois_element_from_step.restype = C.c_uint64
+        L.ro_galois_element_from_step.argtypes = [C.c_size_t, C.c_int]
+        L.ro_galois_ntt_table.argtypes = [C.c_uint, C.c_uint64, C.POINTER(C.c_uint32)]
+        L.ro_galois_coeff.argtypes = [C.c_void_p, u64p, C.c_uint64, u64p, C.c_size_t, C.c_size_t]
+        L.ro_galois_ntt.argtypes = [C.c_void_p, u64p, C.c_uint64, u64p, C.c_size_t, C.c_size_t]
+        L.ro_keyswitch.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_int, C.POINTER(u64p), u64p, C.c_int]
+        for f in ("ro_divide_round_q_last", "ro_divide_round_q_last_ntt", "ro_mod_t_divide_q_last_ntt", "ro_drop_last_limb"):
+            getattr(L, f).argtypes = [C.c_void_p, u64p, u64p, C.c_size_t, C.c_size_t]
+        L.ro_bfv_multiply.argtypes = [C.c_void_p, u64p, u64p, u64p, C.c_size_t]
+        L.ro_behz_bases.argtypes = [C.c_void_p, C.c_size_t, u64p, C.POINTER(C.c_size_t), u64p]
+        L.ro_keygen_secret.argtypes = [C.c_void_p, C.c_uint64, u64p]
+        L.ro_keygen_kswitch.argtypes = [C.c_void_p, u64p, u64p, C.c_uint64, u64p]
+        L.ro_encrypt_zero_sym.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_int, C.c_uint64, u64p]
+        L.ro_phase.argtypes = [C.c_void_p, u64p, u64p, C.c_size_t, C.c_size_t, C.c_int, u64p]
+        L.ro_fnv1a64.restype = C.c_uint64
+        L.ro_fnv1a64.argtypes = [u64p, C.c_size_t]
+        _lib = L
+    return _lib
+
+
+def coeff_modulus_create(n, bits):
+    out = np.zeros(len(bits), dtype=np.uint64)
+    arr = (C.c_uint * len(bits))(*bits)
+    if lib().ro_coeff_modulus_create(n, arr, len(bits), _p(out)):
+        raise ValueError("ro_coeff_modulus_create failed")
+    return out
+
+
+def plain_modulus_batching(n, bits):
+    return int(lib().ro_plain_modulus_batching(n, bits))
+
+
+def fnv1a64(a):
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1)
+    return int(lib().ro_fnv1a64(_p(a), a.size))
+
+
+class Oracle:
+    """CPU oracle context: key-level moduli (special prime last), plain modulus, scheme."""
+
+    def __init__(self, log_n, moduli, plain_modulus=0, scheme=CKKS):
+        self.L = lib()
+        self.log_n, self.n = log_n, 1 << log_n
+        self.moduli = np.ascontiguousarray(moduli, dtype=np.uint64)
+        self.nm = len(self.moduli)
+        self.t, self.scheme = int(plain_modulus), scheme
+        self.h = self.L.ro_ctx_create(log_n, _p(self.moduli), self.nm, self.t, scheme)
+        if not self.h:
+            raise ValueError("ro_ctx_create failed (moduli must be primes = 1 mod 2N)")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ro_ctx_destroy(self.h)
+            self.h = None
+
+    def root(self, i):
+        return int(self.L.ro_ctx_root(self.h, i))
+
+    def root_powers(self, i, inverse=False):
+        f = self.L.ro_ctx_inv_root_powers if inverse else self.L.ro_ctx_root_powers
+        return np.ctypeslib.as_array(f(self.h, i), shape=(self.n, 2)).copy()
+
+    def _ntt(self, fn, data, pcount, ncomp, mode, base, decomp):
+        d = np.ascontiguousarray(data, dtype=np.uint64).copy()
+        assert d.size == pcount * ncomp * self.n
+        fn(self.h, _p(d), pcount, ncomp, mode, base, decomp)
+        return d
+
+    def ntt_fwd(self, data, pcount, ncomp, mode=TABLES_COMPONENTWISE, base=0, decomp=0):
+        return self._ntt(self.L.ro_ntt_fwd, data, pcount, ncomp, mode, base, decomp)
+
+    def ntt_inv(self, data, pcount, ncomp, mode=TABLES_COMPONENTWISE, base=0, decomp=0):
+        return self._ntt(self.L.ro_ntt_inv, data, pcount, ncomp, mode, base, decomp)
+
+    def add(self, a, b, pc, nc):
+        o = np.empty_like(a); self.L.ro_add(self.h, _p(a), _p(b), _p(o), pc, nc); return o
+
+    def sub(self, a, b, pc, nc):
+        o = np.empty_like(a); self.L.ro_sub(self.h, _p(a), _p(b), _p(o), pc, nc); return o
+
+    def negate(self, a, pc, nc):
+        o = np.empty_like(a); self.L.ro_negate(self.h, _p(a), _p(o), pc, nc); return o
+
+    def dyadic_convolute(self, a, na, b, nb, nc):
+        o = np.zeros((na + nb - 1) * nc * self.n, dtype=np.uint64)
+        self.L.ro_dyadic_convolute(self.h, _p(a), na, _p(b), nb, _p(o), nc); return o
+
+    def dyadic_square(self, a, nc):
+        o = np.zeros(3 * nc * self.n, dtype=np.uint64)
+        self.L.ro_dyadic_square(self.h, _p(a), _p(o), nc); return o
+
+    def dyadic_broadcast(self, a, plain, pc, nc, acc_into=None):
+        o = np.zeros(pc * nc * self.n, dtype=np.uint64) if acc_into is None else acc_into.copy()
+        self.L.ro_dyadic_broadcast(self.h, _p(a), _p(plain), _p(o), pc, nc, 0 if acc_into is None else 1); return o
+
+    def negacyclic_shift(self, a, shift, pc, nc):
+        o = np.empty_like(a); self.L.ro_negacyclic_shift(self.h, _p(a), shift, _p(o), pc, nc); return o
+
+    def galois_element_from_step(self, step):
+        return int(self.L.ro_galois_element_from_step(self.n, step))
+
+    def galois_ntt_table(self, g):
+        t = np.zeros(self.n, dtype=np.uint32)
+        self.L.ro_galois_ntt_table(self.log_n, g, t.ctypes.data_as(C.POINTER(C.c_uint32))); return t
+
+    def galois(self, a, g, pc, nc, ntt_form):
+        o = np.empty_like(a)
+        (self.L.ro_galois_ntt if ntt_form else self.L.ro_galois_coeff)(self.h, _p(a), g, _p(o), pc, nc); return o
+
+    def keyswitch(self, target, decomp, is_ntt, key, dest=None, assign=ASSIGN_OVERWRITE):
+        """key: array [decomp_first][2][K][N]; dest [2][decomp][N] (copied) -> result."""
+        key = np.ascontiguousarray(key, dtype=np.uint64).reshape(-1)
+        per = 2 * self.nm * self.n
+        ptrs = (u64p * decomp)(*[C.cast(key.ctypes.data + j * per * 8, u64p) for j in range(decomp)])
+        d = np.zeros(2 * decomp * self.n, dtype=np.uint64) if dest is None else np.ascontiguousarray(dest, dtype=np.uint64).copy()
+        t = np.ascontiguousarray(target, dtype=np.uint64)
+        self.L.ro_keyswitch(self.h, _p(t), decomp, int(is_ntt), ptrs, _p(d), assign)
+        return d
+
+    def _modswitch(self, fn, a, pc, nl):
+        o = np.zeros(pc * (nl - 1) * self.n, dtype=np.uint64)
+        fn(self.h, _p(np.ascontiguousarray(a, dtype=np.uint64)), _p(o), pc, nl); return o
+
+    def divide_round_q_last(self, a, pc, nl): return self._modswitch(self.L.ro_divide_round_q_last, a, pc, nl)
+    def divide_round_q_last_ntt(self, a, pc, nl): return self._modswitch(self.L.ro_divide_round_q_last_ntt, a, pc, nl)
+    def mod_t_divide_q_last_ntt(self, a, pc, nl): return self._modswitch(self.L.ro_mod_t_divide_q_last_ntt, a, pc, nl)
+    def drop_last_limb(self, a, pc, nl): return self._modswitch(self.L.ro_drop_last_limb, a, pc, nl)
+
+    def bfv_multiply(self, a, b, nl):
+        o = np.zeros(3 * nl * self.n, dtype=np.uint64)
+        if self.L.ro_bfv_multiply(self.h, _p(a), _p(b), _p(o), nl):
+            raise NotImplementedError("ro_bfv_multiply")
+        return o
+
+    # toy RLWE -----------------------------------------------------------
+    def keygen_secret(self, seed):
+        sk = np.zeros(self.nm * self.n, dtype=np.uint64); self.L.ro_keygen_secret(self.h, seed, _p(sk)); return sk
+
+    def keygen_kswitch(self, sk, new_key, seed):
+        o = np.zeros((self.nm - 1) * 2 * self.nm * self.n, dtype=np.uint64)
+        self.L.ro_keygen_kswitch(self.h, _p(sk), _p(new_key), seed, _p(o)); return o
+
+    def encrypt_zero_sym(self, sk, nl, is_ntt, seed):
+        ct = np.zeros(2 * nl * self.n, dtype=np.uint64)
+        self.L.ro_encrypt_zero_sym(self.h, _p(sk), nl, int(is_ntt), seed, _p(ct)); return ct
+
+    def phase(self, sk, ct, pc, nl, is_ntt):
+        o = np.zeros(nl * self.n, dtype=np.uint64)
+        self.L.ro_phase(self.h, _p(sk), _p(np.ascontiguousarray(ct, dtype=np.uint64)), pc, nl, int(is_ntt), _p(o)); return o
+
+    def random_poly(self, rng, pc, nl, base=0):
+        """uniform residues, [pc][nl][N], limb j reduced mod moduli[base+j]"""
+        out = np.empty((pc, nl, self.n), dtype=np.uint64)
+        for j in range(nl):
+            out[:, j, :] = rng.integers(0, int(self.moduli[base + j]), size=(pc, self.n), dtype=np.uint64)
+        return out.reshape(-1)
+
+    def random_key(self, rng, decomp=None):
+        """uniform 'key' [decomp][2][K][N] (structure-free; keyswitch is a deterministic function of it)"""
+        decomp = self.nm - 1 if decomp is None else decomp
+        out = np.empty((decomp, 2, self.nm, self.n), dtype=np.uint64)
+        for i in range(self.nm):
+            out[:, :, i, :] = rng.integers(0, int(self.moduli[i]), size=(decomp, 2, self.n), dtype=np.uint64)
+        return out.reshape(-1)
+
+
+# ---------------------------------------------------------------------------------------------
+_ref = None
+
+
+def ref_available():
+    return os.path.exists(REF_SHIM_SO)
+
+
+def reflib():
+    global _ref
+    if _ref is None:
+        R = C.CDLL(REF_SHIM_SO)
+        R.rs_create.restype = C.c_void_p
+        R.rs_create.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_uint), C.c_size_t, C.c_uint, C.c_uint64, C.c_int]
+        R.rs_error.restype = C.c_char_p
+        R.rs_error.argtypes = [C.c_void_p]
+        R.rs_destroy.argtypes = [C.c_void_p]
+        R.rs_n_key_moduli.restype = C.c_size_t
+        R.rs_n_key_moduli.argtypes = [C.c_void_p]
+        R.rs_key_moduli.argtypes = [C.c_void_p, u64p]
+        R.rs_plain_modulus.restype = C.c_uint64
+        R.rs_plain_modulus.argtypes = [C.c_void_p]
+        R.rs_ntt_table.argtypes = [C.c_void_p, C.c_size_t, u64p, u64p, u64p, C.c_size_t]
+        R.rs_gen_relin.argtypes = [C.c_void_p]
+        R.rs_gen_galois.argtypes = [C.c_void_p, u64p, C.c_size_t]
+        R.rs_relin_key.argtypes = [C.c_void_p, u64p]
+        R.rs_galois_key.argtypes = [C.c_void_p, C.c_uint64, u64p]
+        R.rs_secret_key.argtypes = [C.c_void_p, u64p]
+        R.rs_galois_element_from_step.restype = C.c_uint64
+        R.rs_galois_element_from_step.argtypes = [C.c_void_p, C.c_int]
+        R.rs_encrypt_zero.argtypes = [C.c_void_p, u64p]
+        ntt_args = [C.c_void_p, u64p, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t]
+        R.rs_ntt_fwd.argtypes = ntt_args
+        R.rs_ntt_inv.argtypes = ntt_args
+        R.rs_multiply.argtypes = [C.c_void_p, u64p, u64p, u64p, C.c_size_t]
+        R.rs_square.argtypes = [C.c_void_p, u64p, u64p, C.c_size_t]
+        R.rs_relinearize.argtypes = [C.c_void_p, u64p, u64p, C.c_size_t]
+        R.rs_apply_galois.argtypes = [C.c_void_p, u64p, C.c_uint64, u64p, C.c_size_t]
+        R.rs_rotate.argtypes = [C.c_void_p, u64p, C.c_int, u64p, C.c_size_t]
+        for f in ("rs_mod_switch_scale_to_next", "rs_drop_to_next", "rs_transform_to_ntt", "rs_transform_from_ntt"):
+            getattr(R, f).argtypes = [C.c_void_p, u64p, C.c_size_t, u64p, C.c_size_t]
+        R.rs_multiply_plain_raw.argtypes = [C.c_void_p, u64p, C.c_size_t, u64p, u64p, C.c_size_t, C.c_int]
+        R.rs_galois_raw.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_size_t, C.c_uint64, u64p, C.c_int]
+        R.rs_time_op.restype = C.c_double
+        R.rs_time_op.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int]
+        _ref = R
+    return _ref
+
+
+class Reference:
+    """The unmodified reference (host branch unless device=True) behind the C shim."""
+
+    def __init__(self, scheme, n, bits, t_bits=20, seed=0x123, device=False):
+        self.R = reflib()
+        self.scheme, self.n = scheme, n
+        arr = (C.c_uint * len(bits))(*bits)
+        self.h = self.R.rs_create(scheme, n, arr, len(bits), t_bits, seed, int(device))
+        err = self.R.rs_error(self.h)
+        if err:
+            raise RuntimeError(err.decode())
+        self.nm = self.R.rs_n_key_moduli(self.h)
+        self.moduli = np.zeros(self.nm, dtype=np.uint64)
+        self.R.rs_key_moduli(self.h, _p(self.moduli))
+        self.t = int(self.R.rs_plain_modulus(self.h))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.R.rs_destroy(self.h); self.h = None
+
+    def _chk(self, rc):
+        if rc:
+            raise RuntimeError(self.R.rs_error(self.h).decode())
+
+    def ntt_table(self, i, count):
+        root = C.c_uint64(0)
+        rp = np.zeros((count, 2), dtype=np.uint64); irp = np.zeros((count, 2), dtype=np.uint64)
+        self._chk(self.R.rs_ntt_table(self.h, i, C.byref(root), _p(rp), _p(irp), count))
+        return int(root.value), rp, irp
+
+    def gen_relin(self): self._chk(self.R.rs_gen_relin(self.h))
+
+    def gen_galois(self, elts):
+        e = np.ascontiguousarray(elts, dtype=np.uint64); self._chk(self.R.rs_gen_galois(self.h, _p(e), e.size))
+
+    def relin_key(self):
+        o = np.zeros((self.nm - 1) * 2 * self.nm * self.n, dtype=np.uint64); self._chk(self.R.rs_relin_key(self.h, _p(o))); return o
+
+    def galois_key(self, elt):
+        o = np.zeros((self.nm - 1) * 2 * self.nm * self.n, dtype=np.uint64); self._chk(self.R.rs_galois_key(self.h, elt, _p(o))); return o
+
+    def secret_key(self):
+        o = np.zeros(self.nm * self.n, dtype=np.uint64); self._chk(self.R.rs_secret_key(self.h, _p(o))); return o
+
+    def galois_element_from_step(self, step): return int(self.R.rs_galois_element_from_step(self.h, step))
+
+    def encrypt_zero(self):
+        o = np.zeros(2 * (self.nm - 1) * self.n, dtype=np.uint64); self._chk(self.R.rs_encrypt_zero(self.h, _p(o))); return o
+
+    def ntt_fwd(self, data, pc, nc, mode=0, base=0, decomp=0):
+        d = np.ascontiguousarray(data, dtype=np.uint64).copy(); self._chk(self.R.rs_ntt_fwd(self.h, _p(d), pc, nc, mode, base, decomp)); return d
+
+    def ntt_inv(self, data, pc, nc, mode=0, base=0, decomp=0):
+        d = np.ascontiguousarray(data, dtype=np.uint64).copy(); self._chk(self.R.rs_ntt_inv(self.h, _p(d), pc, nc, mode, base, decomp)); return d
+
+    def multiply(self, a, b, nl):
+        o = np.zeros(3 * nl * self.n, dtype=np.uint64); self._chk(self.R.rs_multiply(self.h, _p(a), _p(b), _p(o), nl)); return o
+
+    def square(self, a, nl):
+        o = np.zeros(3 * nl * self.n, dtype=np.uint64); self._chk(self.R.rs_square(self.h, _p(a), _p(o), nl)); return o
+
+    def relinearize(self, a, nl):
+        o = np.zeros(2 * nl * self.n, dtype=np.uint64); self._chk(self.R.rs_relinearize(self.h, _p(a), _p(o), nl)); return o
+
+    def apply_galois(self, a, elt, nl):
+        o = np.zeros(2 * nl * self.n, dtype=np.uint64); self._chk(self.R.rs_apply_galois(self.h, _p(a), elt, _p(o), nl)); return o
+
+    def rotate(self, a, steps, nl):
+        o = np.zeros(2 * nl * self.n, dtype=np.uint64); self._chk(self.R.rs_rotate(self.h, _p(a), steps, _p(o), nl)); return o
+
+    def mod_switch_scale_to_next(self, a, pc, nl):
+        o = np.zeros(pc * (nl - 1) * self.n, dtype=np.uint64); self._chk(self.R.rs_mod_switch_scale_to_next(self.h, _p(a), pc, _p(o), nl)); return o
+
+    def drop_to_next(self, a, pc, nl):
+        o = np.zeros(pc * (nl - 1) * self.n, dtype=np.uint64); self._chk(self.R.rs_drop_to_next(self.h, _p(a), pc, _p(o), nl)); return o
+
+    def transform_to_ntt(self, a, pc, nl):
+        o = np.zeros(pc * nl * self.n, dtype=np.uint64); self._chk(self.R.rs_transform_to_ntt(self.h, _p(a), pc, _p(o), nl)); return o
+
+    def transform_from_ntt(self, a, pc, nl):
+        o = np.zeros(pc * nl * self.n, dtype=np.uint64); self._chk(self.R.rs_transform_from_ntt(self.h, _p(a), pc, _p(o), nl)); return o
+
+    def multiply_plain_raw(self, a, pc, plain, nl, ntt_form):
+        o = np.zeros(pc * nl * self.n, dtype=np.uint64)
+        self._chk(self.R.rs_multiply_plain_raw(self.h, _p(a), pc, _p(plain), _p(o), nl, int(ntt_form))); return o
+
+    def galois_raw(self, a, pc, nl, elt, ntt_form):
+        o = np.zeros(pc * nl * self.n, dtype=np.uint64); self._chk(self.R.rs_galois_raw(self.h, _p(a), pc, nl, elt, _p(o), int(ntt_form))); return o
+
+    def time_op(self, op, nl, pc=1, warmup=1, iters=3):
+        t = self.R.rs_time_op(self.h, op, nl, pc, warmup, iters)
+        if t < 0:
+            raise RuntimeError(self.R.rs_error(self.h).decode())
+        return t
