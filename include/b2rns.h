@@ -1,0 +1,105 @@
+/*
+ * b2rns.h — C ABI of libb2rns.so: the B200-native (sm_100a) RNS polynomial hot path that slots in
+ * behind Troy-Nova's L2 free-function seam.
+ *
+ * Conventions (mirroring the reference; citations are relative to the reference tree):
+ *   - polynomials are row-major uint64 arrays [poly][limb][N]            (src/ciphertext.h:211-252)
+ *   - a context holds the KEY-LEVEL modulus chain q_0..q_{K-2}, P (special prime last); a ciphertext
+ *     at a level with `nl` limbs uses moduli q_0..q_{nl-1}              (src/he_context.cu:5-45)
+ *   - every stored output is the canonical residue in [0, q_i)
+ *   - all data pointers are DEVICE pointers unless the function name ends in _host
+ *   - calls are asynchronous on `stream` (a cudaStream_t cast to void*; NULL = legacy default
+ *     stream); the reference launches on the per-thread default stream and never synchronises
+ *     (src/utils/memory_pool.cu:10-19), the adapter passes cudaStreamPerThread
+ *   - errors: the reference throws std::invalid_argument / std::runtime_error on the host
+ *     (e.g. src/fgk/ntt_grouped.cu:261-263); here every entry point returns a b2_status and never
+ *     throws; b2_last_error() gives the message for the calling thread
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns
+ *     B2_ERR_NO_DEVICE.
+ */
+#ifndef B2RNS_H
+#define B2RNS_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    B2_OK = 0,
+    B2_ERR_INVALID_ARG = 1,   /* reference: std::invalid_argument */
+    B2_ERR_CUDA = 2,          /* reference: std::runtime_error from cudaMalloc/cudaMemcpy wrappers */
+    B2_ERR_NO_DEVICE = 3,
+    B2_ERR_UNSUPPORTED = 4,
+    B2_ERR_OUT_OF_MEMORY = 5
+} b2_status;
+
+/* SchemeType, src/encryption_parameters.h:7-12 */
+typedef enum { B2_SCHEME_BFV = 1, B2_SCHEME_CKKS = 2, B2_SCHEME_BGV = 3 } b2_scheme;
+/* Evaluator::SwitchKeyDestinationAssignMethod, src/evaluator.h:18-22 */
+typedef enum { B2_ASSIGN_OVERWRITE = 0, B2_ASSIGN_ADD_INPLACE = 1, B2_ASSIGN_OVERWRITE_EXCEPT_FIRST = 2 } b2_assign;
+/* NTTTableIndexer::NTTTableIndexerType, src/utils/ntt.h:93-97 */
+typedef enum { B2_TABLES_COMPONENTWISE = 0, B2_TABLES_KS_SET_PRODUCTS = 1, B2_TABLES_KS_SKIP_FINALS = 2 } b2_table_mode;
+
+typedef struct b2_ctx b2_ctx;
+typedef struct b2_kswitch_key b2_kswitch_key;
+
+typedef struct {
+    uint32_t log_n;            /* poly_modulus_degree = 1 << log_n, 1 <= log_n <= 17 (src/utils/constants.h:13) */
+    uint32_t n_moduli;         /* key-level modulus count K (special prime last), 1..64 */
+    const uint64_t *moduli;    /* host pointer, K primes = 1 mod 2N, < 2^61 (src/modulus.cu:15-16) */
+    uint64_t plain_modulus;    /* t (BFV/BGV), 0 for CKKS */
+    uint32_t scheme;           /* b2_scheme */
+} b2_params;
+
+const char *b2_last_error(void);
+const char *b2_version(void);
+int         b2_device_count(void);
+
+/* ---- context: replaces the device-resident tables of HeContext / ContextData
+ *      (src/he_context.cu:46-145: NTTTables, RNSTool constants, GaloisTool tables) ---- */
+b2_status b2_ctx_create(int device, const b2_params *params, b2_ctx **out);
+void      b2_ctx_destroy(b2_ctx *ctx);
+/* host-side helpers (pure host setup code, mirrors CoeffModulus::create / PlainModulus::batching,
+ * src/coeff_modulus.cu:64-107) */
+b2_status b2_coeff_modulus_create(size_t n, const uint32_t *bit_sizes, size_t count, uint64_t *out);
+/* psi_i: minimal primitive 2N-th root of modulus i (src/utils/number_theory.cu:68-87) */
+b2_status b2_ctx_root(const b2_ctx *ctx, size_t i, uint64_t *psi);
+
+/* ---- device memory helpers for hosts that have no CUDA runtime of their own ---- */
+b2_status b2_malloc(b2_ctx *ctx, size_t bytes, void **dptr);
+b2_status b2_free(b2_ctx *ctx, void *dptr);
+b2_status b2_malloc_host(size_t bytes, void **hptr);       /* pinned */
+b2_status b2_free_host(void *hptr);
+b2_status b2_memcpy_h2d(b2_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream);
+b2_status b2_memcpy_d2h(b2_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream);
+b2_status b2_stream_sync(b2_ctx *ctx, void *stream);
+
+/* ---- N1/N2: utils::ntt_transfer_to_rev / ntt_transfer_from_rev (+_inplace when in == out)
+ *      (src/utils/ntt.h:132-144).  data [pcount][ncomp][N]; the table of element (k, j) is chosen as
+ *      NTTTableIndexer::get does (src/utils/ntt.h:105-123): COMPONENTWISE -> table_base + j;
+ *      KS_SET_PRODUCTS -> (k == decomp ? K-1 : k); KS_SKIP_FINALS -> (j == decomp ? K-1 : j).
+ *      `batch` independent operands are laid out contiguously ([batch][pcount][ncomp][N]); the
+ *      reference's *_batched variants (src/fgk/ntt_grouped.cu:297-344) take a vector of slices,
+ *      b2_ntt_*_ptrs takes the same thing as a HOST array of device pointers.
+ *      forward: input < 4p, output canonical, bit-reversed order; inverse: input < 2p, output
+ *      canonical and scaled by N^-1. ---- */
+b2_status b2_ntt_forward(b2_ctx *ctx, const uint64_t *in, uint64_t *out, size_t batch, size_t pcount, size_t ncomp,
+                         int table_mode, size_t table_base, size_t decomp, void *stream);
+b2_status b2_ntt_inverse(b2_ctx *ctx, const uint64_t *in, uint64_t *out, size_t batch, size_t pcount, size_t ncomp,
+                         int table_mode, size_t table_base, size_t decomp, void *stream);
+b2_status b2_ntt_forward_ptrs(b2_ctx *ctx, const uint64_t *const *in, uint64_t *const *out, size_t batch, size_t pcount,
+                              size_t ncomp, int table_mode, size_t table_base, size_t decomp, void *stream);
+b2_status b2_ntt_inverse_ptrs(b2_ctx *ctx, const uint64_t *const *in, uint64_t *const *out, size_t batch, size_t pcount,
+                              size_t ncomp, int table_mode, size_t table_base, size_t decomp, void *stream);
+/* same with HOST buffers: H2D, transform, D2H on `stream`, synchronised on return (what a host-memory
+ * caller of the reference does with Ciphertext::to_device / to_host around the op) */
+b2_status b2_ntt_forward_host(b2_ctx *ctx, const uint64_t *in, uint64_t *out, size_t batch, size_t pcount, size_t ncomp,
+                              int table_mode, size_t table_base, size_t decomp, void *stream);
+b2_status b2_ntt_inverse_host(b2_ctx *ctx, const uint64_t *in, uint64_t *out, size_t batch, size_t pcount, size_t ncomp,
+                              int table_mode, size_t table_base, size_t decomp, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,155 @@
+"""troy-nova_b200 — python (ctypes) binding of libb2rns.so, the B200-native RNS polynomial hot path.
+
+The product is the C-ABI library (include/b2rns.h) plus the C++ host mirror of the reference's
+Evaluator seam (troy-nova_b200/host/).  This module exists so that tests/ and bench.py can drive
+the C ABI with torch-allocated device memory; it contains no arithmetic and no fallback: if the
+CUDA library is missing or no GPU is present every compute call raises.
+
+Import with  importlib.import_module("troy-nova_b200")  (the directory name is not an identifier).
+"""
+import ctypes as C
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb2rns.so")
+
+BFV, CKKS, BGV = 1, 2, 3
+ASSIGN_OVERWRITE, ASSIGN_ADD_INPLACE, ASSIGN_OVERWRITE_EXCEPT_FIRST = 0, 1, 2
+TABLES_COMPONENTWISE, TABLES_KS_SET_PRODUCTS, TABLES_KS_SKIP_FINALS = 0, 1, 2
+
+u64p = C.POINTER(C.c_uint64)
+vp = C.c_void_p
+
+
+class B2Error(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("b2 status %d: %s" % (status, msg))
+        self.status = status
+
+
+def build(verbose=False):
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> libb2rns.so (in-tree)."""
+    subprocess.check_call(["make", "-s", "-j8", "-C", HERE], stdout=None if verbose else subprocess.DEVNULL)
+
+
+_lib = None
+
+_SIGS = {
+    # name: (restype, argtypes)
+    "b2_last_error": (C.c_char_p, []),
+    "b2_version": (C.c_char_p, []),
+    "b2_device_count": (C.c_int, []),
+    "b2_ctx_destroy": (None, [vp]),
+    "b2_coeff_modulus_create": (C.c_int, [C.c_size_t, C.POINTER(C.c_uint32), C.c_size_t, u64p]),
+    "b2_ctx_root": (C.c_int, [vp, C.c_size_t, u64p]),
+    "b2_malloc": (C.c_int, [vp, C.c_size_t, C.POINTER(vp)]),
+    "b2_free": (C.c_int, [vp, vp]),
+    "b2_malloc_host": (C.c_int, [C.c_size_t, C.POINTER(vp)]),
+    "b2_free_host": (C.c_int, [vp]),
+    "b2_memcpy_h2d": (C.c_int, [vp, vp, vp, C.c_size_t, vp]),
+    "b2_memcpy_d2h": (C.c_int, [vp, vp, vp, C.c_size_t, vp]),
+    "b2_stream_sync": (C.c_int, [vp, vp]),
+}
+_NTT_ARGS = [vp, vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t, vp]
+for _n in ("b2_ntt_forward", "b2_ntt_inverse", "b2_ntt_forward_ptrs", "b2_ntt_inverse_ptrs", "b2_ntt_forward_host", "b2_ntt_inverse_host"):
+    _SIGS[_n] = (C.c_int, _NTT_ARGS)
+
+
+class _Params(C.Structure):
+    _fields_ = [("log_n", C.c_uint32), ("n_moduli", C.c_uint32), ("moduli", u64p), ("plain_modulus", C.c_uint64), ("scheme", C.c_uint32)]
+
+
+def lib():
+    """Load libb2rns.so; raises if it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("libb2rns.so not built: run `python -c 'import __graft_entry__ as g; g.build()'` or `make -C troy-nova_b200`")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            f = getattr(L, name)
+            f.restype, f.argtypes = res, args
+        L.b2_ctx_create.restype = C.c_int
+        L.b2_ctx_create.argtypes = [C.c_int, C.POINTER(_Params), C.POINTER(vp)]
+        _lib = L
+    return _lib
+
+
+def exported_symbols():
+    return sorted(list(_SIGS) + ["b2_ctx_create"])
+
+
+def _chk(st):
+    if st != 0:
+        raise B2Error(st, lib().b2_last_error().decode())
+
+
+def coeff_modulus_create(n, bits):
+    out = (C.c_uint64 * len(bits))()
+    _chk(lib().b2_coeff_modulus_create(n, (C.c_uint32 * len(bits))(*bits), len(bits), out))
+    return [int(x) for x in out]
+
+
+def _dptr(x):
+    """device pointer of a torch tensor / int / None"""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    return x.data_ptr()
+
+
+class Context:
+    """Device-resident tables for one modulus chain (key level, special prime last)."""
+
+    def __init__(self, log_n, moduli, plain_modulus=0, scheme=CKKS, device=0):
+        self.L = lib()
+        self.log_n, self.n = log_n, 1 << log_n
+        self.moduli = [int(m) for m in moduli]
+        self.K = len(self.moduli)
+        self.t, self.scheme, self.device = int(plain_modulus), scheme, device
+        arr = (C.c_uint64 * self.K)(*self.moduli)
+        prm = _Params(log_n, self.K, arr, self.t, scheme)
+        h = vp()
+        _chk(self.L.b2_ctx_create(device, C.byref(prm), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.b2_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def root(self, i):
+        v = C.c_uint64()
+        _chk(self.L.b2_ctx_root(self.h, i, C.byref(v)))
+        return int(v.value)
+
+    @staticmethod
+    def _stream(stream):
+        if stream is None:
+            import torch
+            return torch.cuda.current_stream().cuda_stream
+        return stream
+
+    # N1 / N2 ---------------------------------------------------------------------------------
+    def ntt_forward(self, src, dst=None, batch=1, pcount=1, ncomp=1, mode=TABLES_COMPONENTWISE, table_base=0, decomp=0, stream=None):
+        dst = src if dst is None else dst
+        _chk(self.L.b2_ntt_forward(self.h, _dptr(src), _dptr(dst), batch, pcount, ncomp, mode, table_base, decomp, self._stream(stream)))
+        return dst
+
+    def ntt_inverse(self, src, dst=None, batch=1, pcount=1, ncomp=1, mode=TABLES_COMPONENTWISE, table_base=0, decomp=0, stream=None):
+        dst = src if dst is None else dst
+        _chk(self.L.b2_ntt_inverse(self.h, _dptr(src), _dptr(dst), batch, pcount, ncomp, mode, table_base, decomp, self._stream(stream)))
+        return dst
+
+    def ntt_host(self, forward, src_np, dst_np, batch=1, pcount=1, ncomp=1, mode=TABLES_COMPONENTWISE, table_base=0, decomp=0, stream=0):
+        f = self.L.b2_ntt_forward_host if forward else self.L.b2_ntt_inverse_host
+        _chk(f(self.h, src_np.ctypes.data, dst_np.ctypes.data, batch, pcount, ncomp, mode, table_base, decomp, stream))
+        return dst_np

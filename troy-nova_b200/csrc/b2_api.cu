@@ -1,0 +1,100 @@
+// b2_api.cu — error handling, device memory helpers and misc C-ABI entry points of libb2rns.so.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "b2_ctx.h"
+#include "b2_host_math.h"
+
+namespace b2 {
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+}
+b2_status cuda_fail(cudaError_t e, const char *what) {
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return B2_ERR_NO_DEVICE;
+    if (e == cudaErrorMemoryAllocation) return B2_ERR_OUT_OF_MEMORY;
+    return B2_ERR_CUDA;
+}
+b2_status ensure_ws(b2_ctx *ctx, size_t bytes) {
+    if (ctx->ws_bytes >= bytes) return B2_OK;
+    if (ctx->ws) { B2_CUDA(cudaDeviceSynchronize()); B2_CUDA(cudaFree(ctx->ws)); ctx->ws = nullptr; ctx->ws_bytes = 0; }
+    size_t want = bytes + bytes / 8;
+    B2_CUDA(cudaMalloc(&ctx->ws, want));
+    ctx->ws_bytes = want;
+    return B2_OK;
+}
+b2_status ensure_stage(b2_ctx *ctx, size_t bytes) {
+    if (ctx->stage_bytes >= bytes) return B2_OK;
+    if (ctx->stage) { B2_CUDA(cudaDeviceSynchronize()); B2_CUDA(cudaFree(ctx->stage)); ctx->stage = nullptr; ctx->stage_bytes = 0; }
+    B2_CUDA(cudaMalloc(&ctx->stage, bytes));
+    ctx->stage_bytes = bytes;
+    return B2_OK;
+}
+}  // namespace b2
+
+extern "C" {
+
+const char *b2_last_error(void) { return b2::g_err; }
+const char *b2_version(void) { return "b2rns 0.1 (sm_100a)"; }
+int b2_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+b2_status b2_coeff_modulus_create(size_t n, const uint32_t *bits, size_t count, uint64_t *out) {
+    B2_REQUIRE(n >= 2 && (n & (n - 1)) == 0 && bits && out && count >= 1 && count <= 64, "bad arguments");
+    // CoeffModulus::create: per distinct bit size take as many primes as it occurs (descending from
+    // 2^bits), then hand them out from the smallest upwards in order of appearance.
+    std::vector<uint64_t> lists[64]; size_t used[64] = {0}, mult[64] = {0};
+    for (size_t i = 0; i < count; i++) { B2_REQUIRE(bits[i] >= 2 && bits[i] <= 61, "bit size out of range"); mult[bits[i]]++; }
+    for (unsigned b = 0; b < 64; b++)
+        if (mult[b] && !b2::host::primes_below(2 * (uint64_t)n, b, mult[b], lists[b])) {
+            b2::set_error("b2_coeff_modulus_create: not enough %u-bit primes = 1 mod %zu", b, 2 * n);
+            return B2_ERR_INVALID_ARG;
+        }
+    for (size_t i = 0; i < count; i++) { unsigned b = bits[i]; out[i] = lists[b][mult[b] - 1 - used[b]++]; }
+    return B2_OK;
+}
+
+b2_status b2_ctx_root(const b2_ctx *ctx, size_t i, uint64_t *psi) {
+    B2_REQUIRE(ctx && psi && i < ctx->K, "bad arguments");
+    *psi = ctx->psi[i];
+    return B2_OK;
+}
+
+b2_status b2_malloc(b2_ctx *ctx, size_t bytes, void **dptr) {
+    B2_REQUIRE(ctx && dptr, "null argument");
+    B2_CUDA(cudaSetDevice(ctx->device));
+    B2_CUDA(cudaMalloc(dptr, bytes ? bytes : 1));
+    return B2_OK;
+}
+b2_status b2_free(b2_ctx *ctx, void *dptr) {
+    B2_REQUIRE(ctx, "null ctx");
+    B2_CUDA(cudaSetDevice(ctx->device));
+    B2_CUDA(cudaFree(dptr));
+    return B2_OK;
+}
+b2_status b2_malloc_host(size_t bytes, void **hptr) { B2_REQUIRE(hptr, "null argument"); B2_CUDA(cudaMallocHost(hptr, bytes ? bytes : 1)); return B2_OK; }
+b2_status b2_free_host(void *hptr) { B2_CUDA(cudaFreeHost(hptr)); return B2_OK; }
+b2_status b2_memcpy_h2d(b2_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream) {
+    B2_REQUIRE(ctx, "null ctx");
+    B2_CUDA(cudaSetDevice(ctx->device));
+    B2_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return B2_OK;
+}
+b2_status b2_memcpy_d2h(b2_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream) {
+    B2_REQUIRE(ctx, "null ctx");
+    B2_CUDA(cudaSetDevice(ctx->device));
+    B2_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return B2_OK;
+}
+b2_status b2_stream_sync(b2_ctx *ctx, void *stream) {
+    B2_REQUIRE(ctx, "null ctx");
+    B2_CUDA(cudaSetDevice(ctx->device));
+    B2_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return B2_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,93 @@
+// b2_ctx.cu — context creation: per-modulus constants and twiddle tables, built on the host once and
+// made device-resident.  Replaces the device copies the reference makes in
+// HeContext::to_device_inplace (src/he_context.cu:134-145) of NTTTables (src/utils/ntt.cu:14-76).
+#include "b2_ctx.h"
+#include "b2_host_math.h"
+
+using namespace b2;
+
+extern "C" b2_status b2_ctx_create(int device, const b2_params *prm, b2_ctx **out) {
+    B2_REQUIRE(prm && out && prm->moduli, "null argument");
+    B2_REQUIRE(prm->log_n >= 1 && prm->log_n <= 17, "log_n must be in [1, 17]");
+    B2_REQUIRE(prm->n_moduli >= 1 && prm->n_moduli <= 64, "n_moduli must be in [1, 64]");
+    B2_REQUIRE(prm->scheme >= B2_SCHEME_BFV && prm->scheme <= B2_SCHEME_BGV, "unknown scheme");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("b2_ctx_create: no CUDA device (libb2rns has no CPU fallback)");
+        return B2_ERR_NO_DEVICE;
+    }
+    B2_REQUIRE(device >= 0 && device < ndev, "device index out of range");
+    B2_CUDA(cudaSetDevice(device));
+
+    b2_ctx *c = new b2_ctx();
+    c->device = device; c->logn = prm->log_n; c->n = (size_t)1 << prm->log_n; c->K = prm->n_moduli;
+    c->t = prm->plain_modulus; c->scheme = (int)prm->scheme;
+    const size_t n = c->n, K = c->K; const unsigned logn = c->logn;
+    c->q.assign(prm->moduli, prm->moduli + K);
+    c->psi.resize(K);
+    std::vector<Tw> tw(K * n), itw(K * n);
+    std::vector<double> twd(K * n), itwd(K * n);
+    c->h_mods.resize(K);
+    for (size_t i = 0; i < K; i++) {
+        const uint64_t p = c->q[i];
+        if (p < 2 || (p >> 61) != 0 || !host::is_prime(p)) { delete c; set_error("b2_ctx_create: modulus %zu is not a prime below 2^61", i); return B2_ERR_INVALID_ARG; }
+        const uint64_t psi = host::min_primitive_root(2 * n, p);
+        if (!psi) { delete c; set_error("b2_ctx_create: modulus %zu is not 1 mod 2N", i); return B2_ERR_INVALID_ARG; }
+        c->psi[i] = psi;
+        const uint64_t ipsi = host::invmod(psi, p);
+        Tw *T = &tw[i * n], *IT = &itw[i * n];
+        // root_powers[bitrev(k)] = psi^k ; inv_root_powers[bitrev(k-1)+1] = psi^-k  (src/utils/ntt.cu:36-58)
+        uint64_t pw = psi, ipw = ipsi;
+        T[0].x = 1; T[0].y = host::shoup_quotient(1, p); IT[0] = T[0];
+        for (size_t k = 1; k < n; k++) {
+            size_t a = host::bitrev((uint32_t)k, logn), b = host::bitrev((uint32_t)(k - 1), logn) + 1;
+            T[a].x = pw; T[a].y = host::shoup_quotient(pw, p);
+            IT[b].x = ipw; IT[b].y = host::shoup_quotient(ipw, p);
+            pw = host::mulmod(pw, psi, p); ipw = host::mulmod(ipw, ipsi, p);
+        }
+        ModInfo &M = c->h_mods[i];
+        memset(&M, 0, sizeof M);
+        M.p = p;
+        host::u128 ratio = (~(host::u128)0) / p;
+        M.r0 = (uint64_t)ratio; M.r1 = (uint64_t)(ratio >> 64); M.ratio = M.r1;
+        const uint64_t inv_n = host::invmod(n % p, p);
+        M.inv_n.x = inv_n; M.inv_n.y = host::shoup_quotient(inv_n, p);
+        const uint64_t last_w = n > 1 ? IT[n - 1].x : 1;    // twiddle of the last inverse layer
+        const uint64_t inw = host::mulmod(inv_n, last_w, p);
+        M.inv_n_w.x = inw; M.inv_n_w.y = host::shoup_quotient(inw, p);
+        const unsigned bits = host::bit_count(p);
+        M.fwd_lazy = ((host::u128)(4 + 2 * logn) * p) < ((host::u128)1 << 64) ? 1u : 0u;
+        M.inv_lazy = (bits + logn + 2 <= 64) ? 1u : 0u;
+        // FP64-pipe path: exact double-double arithmetic needs |x| w / p < 2^51 with |x| < 2^10 p
+        M.bits = bits;
+        M.use_f64 = (bits <= 41) ? 1u : 0u;
+        M.pd = (double)p; M.pinv = 1.0 / (double)p;
+        M.inv_n_d = (double)inv_n; M.inv_n_w_d = (double)inw;
+        for (size_t k = 0; k < n; k++) { twd[i * n + k] = (double)T[k].x; itwd[i * n + k] = (double)IT[k].x; }
+    }
+    cudaError_t ce;
+    if ((ce = cudaMalloc(&c->d_tw, K * n * sizeof(Tw))) != cudaSuccess || (ce = cudaMalloc(&c->d_itw, K * n * sizeof(Tw))) != cudaSuccess ||
+        (ce = cudaMalloc(&c->d_twd, K * n * sizeof(double))) != cudaSuccess || (ce = cudaMalloc(&c->d_itwd, K * n * sizeof(double))) != cudaSuccess ||
+        (ce = cudaMalloc(&c->d_mods, K * sizeof(ModInfo))) != cudaSuccess) {
+        b2_ctx_destroy(c);
+        return cuda_fail(ce, "cudaMalloc(tables)");
+    }
+    for (size_t i = 0; i < K; i++) { c->h_mods[i].tw = c->d_tw + i * n; c->h_mods[i].itw = c->d_itw + i * n;
+        c->h_mods[i].twd = c->d_twd + i * n; c->h_mods[i].itwd = c->d_itwd + i * n; }
+    B2_CUDA(cudaMemcpy(c->d_tw, tw.data(), K * n * sizeof(Tw), cudaMemcpyHostToDevice));
+    B2_CUDA(cudaMemcpy(c->d_itw, itw.data(), K * n * sizeof(Tw), cudaMemcpyHostToDevice));
+    B2_CUDA(cudaMemcpy(c->d_twd, twd.data(), K * n * sizeof(double), cudaMemcpyHostToDevice));
+    B2_CUDA(cudaMemcpy(c->d_itwd, itwd.data(), K * n * sizeof(double), cudaMemcpyHostToDevice));
+    B2_CUDA(cudaMemcpy(c->d_mods, c->h_mods.data(), K * sizeof(ModInfo), cudaMemcpyHostToDevice));
+    *out = c;
+    return B2_OK;
+}
+
+extern "C" void b2_ctx_destroy(b2_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaFree(c->d_tw); cudaFree(c->d_itw); cudaFree(c->d_twd); cudaFree(c->d_itwd); cudaFree(c->d_mods); cudaFree(c->ws); cudaFree(c->stage);
+    delete c;
+}

@@ -1,0 +1,43 @@
+// b2_ctx.h — internal definition of the opaque b2_ctx handle.
+#pragma once
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../../include/b2rns.h"
+#include "b2_modarith.cuh"
+
+struct b2_ctx {
+    int device = 0;
+    unsigned logn = 0;
+    size_t n = 0, K = 0;
+    uint64_t t = 0;
+    int scheme = 0;
+    std::vector<uint64_t> q;      // key-level moduli (host copy)
+    std::vector<uint64_t> psi;    // minimal primitive 2N-th roots
+    b2::ModInfo *d_mods = nullptr;   // [K] on device
+    b2::Tw *d_tw = nullptr;          // [K][N] forward twiddles
+    b2::Tw *d_itw = nullptr;         // [K][N] inverse twiddles
+    double *d_twd = nullptr, *d_itwd = nullptr;   // same tables as doubles (FP64-pipe path)
+    std::vector<b2::ModInfo> h_mods;
+    // workspace arena (grown on demand outside the hot path; never shrinks)
+    void *ws = nullptr; size_t ws_bytes = 0;
+    // host-buffer staging for the *_host entry points
+    void *stage = nullptr; size_t stage_bytes = 0;
+};
+
+namespace b2 {
+void set_error(const char *fmt, ...);
+b2_status cuda_fail(cudaError_t e, const char *what);
+b2_status ensure_ws(b2_ctx *ctx, size_t bytes);
+b2_status ensure_stage(b2_ctx *ctx, size_t bytes);
+#define B2_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return b2::cuda_fail(e__, #call); } while (0)
+#define B2_REQUIRE(cond, msg) do { if (!(cond)) { b2::set_error("%s: %s", __func__, msg); return B2_ERR_INVALID_ARG; } } while (0)
+
+// launchers (b2_ntt.cu)
+struct NttOperand {           // where the limbs live: contiguous base, or per-batch pointer tables
+    const uint64_t *in; uint64_t *out;
+    const uint64_t *const *in_ptrs; uint64_t *const *out_ptrs;   // device arrays (or null)
+};
+b2_status ntt_launch(b2_ctx *ctx, bool forward, const uint64_t *in, uint64_t *out, size_t batch, size_t pcount,
+                     size_t ncomp, int mode, size_t table_base, size_t decomp, cudaStream_t stream);
+}
