@@ -41,6 +41,14 @@ typedef enum { B2_ASSIGN_OVERWRITE = 0, B2_ASSIGN_ADD_INPLACE = 1, B2_ASSIGN_OVE
 /* NTTTableIndexer::NTTTableIndexerType, src/utils/ntt.h:93-97 */
 typedef enum { B2_TABLES_COMPONENTWISE = 0, B2_TABLES_KS_SET_PRODUCTS = 1, B2_TABLES_KS_SKIP_FINALS = 2 } b2_table_mode;
 
+/* which rounding division b2_mod_switch_to_next performs */
+typedef enum {
+    B2_MODSWITCH_BFV = 0,   /* RNSTool::divide_and_round_q_last, coefficient form   (src/utils/rns_tool.cu:374-497) */
+    B2_MODSWITCH_CKKS = 1,  /* RNSTool::divide_and_round_q_last_ntt = rescale        (src/utils/rns_tool.cu:499-760) */
+    B2_MODSWITCH_BGV = 2,   /* RNSTool::mod_t_and_divide_q_last_ntt                  (src/utils/rns_tool.cu:1540-1833) */
+    B2_MODSWITCH_DROP = 3   /* CKKS mod_switch_to_next: drop the last limb           (src/evaluator_modswitch.cu:152-171) */
+} b2_modswitch_kind;
+
 typedef struct b2_ctx b2_ctx;
 typedef struct b2_kswitch_key b2_kswitch_key;
 
@@ -98,6 +106,40 @@ b2_status b2_ntt_forward_host(b2_ctx *ctx, const uint64_t *in, uint64_t *out, si
                               int table_mode, size_t table_base, size_t decomp, void *stream);
 b2_status b2_ntt_inverse_host(b2_ctx *ctx, const uint64_t *in, uint64_t *out, size_t batch, size_t pcount, size_t ncomp,
                               int table_mode, size_t table_base, size_t decomp, void *stream);
+
+/* ---- K1-K5: Evaluator::switch_key_internal (src/evaluator_keyswitching_core.cu:757-1052).
+ *      A key is `digits` ciphertexts key_j = [2][K][N] in NTT form at the key level; the reference keeps
+ *      a device array of their base pointers (src/kswitch_keys.h:36-57) and so does b2_kswitch_key.
+ *      digit_ptrs is a HOST array of `digits` DEVICE pointers (not copied: the key data stays owned by
+ *      the caller and must outlive the handle).
+ *      b2_keyswitch: target [decomp][N] (NTT form iff is_ntt), dest [2][decomp][N] written per `assign`
+ *      (b2_assign).  BFV ciphertexts are coefficient form, CKKS / BGV are NTT form. ---- */
+b2_status b2_kswitch_key_create(b2_ctx *ctx, const uint64_t *const *digit_ptrs, size_t digits, b2_kswitch_key **out);
+b2_status b2_kswitch_key_create_contiguous(b2_ctx *ctx, const uint64_t *key /* [digits][2][K][N] */, size_t digits, b2_kswitch_key **out);
+void      b2_kswitch_key_destroy(b2_kswitch_key *key);
+b2_status b2_keyswitch(b2_ctx *ctx, const uint64_t *target, size_t decomp, int is_ntt, const b2_kswitch_key *key,
+                       uint64_t *dest, int assign, void *stream);
+
+/* ---- R1-R4: mod_switch_to_next / rescale_to_next (src/evaluator_modswitch.cu:14-149,445-461).
+ *      in [count][nl][N] -> out [count][nl-1][N]; kind is a b2_modswitch_kind. ---- */
+b2_status b2_mod_switch_to_next(b2_ctx *ctx, const uint64_t *in, uint64_t *out, size_t count, size_t nl, int kind, void *stream);
+
+/* ---- M1, M3, E1, G1: element-wise kernels.  Operands [count][ncomp][N], limb j uses modulus table_base + j. ---- */
+/* utils::add_ps / sub_ps / negate_ps (src/utils/poly_small_mod.cu:263-420) */
+b2_status b2_add(b2_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t count, size_t ncomp, size_t table_base, void *stream);
+b2_status b2_sub(b2_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t count, size_t ncomp, size_t table_base, void *stream);
+b2_status b2_negate(b2_ctx *ctx, const uint64_t *a, uint64_t *out, size_t count, size_t ncomp, size_t table_base, void *stream);
+/* fgk::dyadic_convolute::dyadic_convolute / dyadic_square (src/fgk/dyadic_convolute.cu:6-148):
+ * a [batch][na][ncomp][N], b [batch][nb][ncomp][N] -> out [batch][na+nb-1][ncomp][N]; na, nb <= 3 */
+b2_status b2_dyadic_convolute(b2_ctx *ctx, const uint64_t *a, size_t na, const uint64_t *b, size_t nb, uint64_t *out, size_t batch, size_t ncomp, void *stream);
+b2_status b2_dyadic_square(b2_ctx *ctx, const uint64_t *a, uint64_t *out, size_t batch, size_t ncomp, void *stream);
+/* fgk::dyadic_convolute::dyadic_broadcast_product(_accumulate)_ps (src/fgk/dyadic_convolute.cu:151-292):
+ * out[k] (+)= a[k] o plain, k < pcount; plain [ncomp][N] */
+b2_status b2_dyadic_broadcast(b2_ctx *ctx, const uint64_t *a, const uint64_t *plain, uint64_t *out, size_t pcount, size_t ncomp, int accumulate, void *stream);
+/* utils::negacyclic_shift_ps (src/utils/poly_small_mod.cu:902-949); out of place */
+b2_status b2_negacyclic_shift(b2_ctx *ctx, const uint64_t *a, size_t shift, uint64_t *out, size_t count, size_t ncomp, size_t table_base, void *stream);
+/* GaloisTool::apply_ps / apply_ntt_ps (src/utils/galois.cu:141-300); out of place */
+b2_status b2_galois(b2_ctx *ctx, const uint64_t *in, uint64_t galois_elt, uint64_t *out, size_t count, size_t ncomp, size_t table_base, int is_ntt, void *stream);
 
 #ifdef __cplusplus
 }

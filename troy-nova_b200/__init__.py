@@ -56,6 +56,24 @@ for _n in ("b2_ntt_forward", "b2_ntt_inverse", "b2_ntt_forward_ptrs", "b2_ntt_in
     _SIGS[_n] = (C.c_int, _NTT_ARGS)
 
 
+_SIGS.update({
+    "b2_kswitch_key_create": (C.c_int, [vp, C.POINTER(vp), C.c_size_t, C.POINTER(vp)]),
+    "b2_kswitch_key_create_contiguous": (C.c_int, [vp, vp, C.c_size_t, C.POINTER(vp)]),
+    "b2_kswitch_key_destroy": (None, [vp]),
+    "b2_keyswitch": (C.c_int, [vp, vp, C.c_size_t, C.c_int, vp, vp, C.c_int, vp]),
+    "b2_mod_switch_to_next": (C.c_int, [vp, vp, vp, C.c_size_t, C.c_size_t, C.c_int, vp]),
+    "b2_add": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp]),
+    "b2_sub": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp]),
+    "b2_negate": (C.c_int, [vp, vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp]),
+    "b2_dyadic_convolute": (C.c_int, [vp, vp, C.c_size_t, vp, C.c_size_t, vp, C.c_size_t, C.c_size_t, vp]),
+    "b2_dyadic_square": (C.c_int, [vp, vp, vp, C.c_size_t, C.c_size_t, vp]),
+    "b2_dyadic_broadcast": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_size_t, C.c_int, vp]),
+    "b2_negacyclic_shift": (C.c_int, [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp]),
+    "b2_galois": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, vp]),
+})
+MODSWITCH_BFV, MODSWITCH_CKKS, MODSWITCH_BGV, MODSWITCH_DROP = 0, 1, 2, 3
+
+
 class _Params(C.Structure):
     _fields_ = [("log_n", C.c_uint32), ("n_moduli", C.c_uint32), ("moduli", u64p), ("plain_modulus", C.c_uint64), ("scheme", C.c_uint32)]
 
@@ -153,3 +171,57 @@ class Context:
         f = self.L.b2_ntt_forward_host if forward else self.L.b2_ntt_inverse_host
         _chk(f(self.h, src_np.ctypes.data, dst_np.ctypes.data, batch, pcount, ncomp, mode, table_base, decomp, stream))
         return dst_np
+
+    # K1-K5 -------------------------------------------------------------------------------------
+    def kswitch_key(self, key_tensor, digits=None):
+        """key_tensor: device tensor holding [digits][2][K][N] (kept alive by the returned handle)"""
+        digits = self.K - 1 if digits is None else digits
+        h = vp()
+        _chk(self.L.b2_kswitch_key_create_contiguous(self.h, _dptr(key_tensor), digits, C.byref(h)))
+        return KSwitchKey(self, h, key_tensor)
+
+    def keyswitch(self, target, decomp, is_ntt, key, dest, assign=ASSIGN_OVERWRITE, stream=None):
+        _chk(self.L.b2_keyswitch(self.h, _dptr(target), decomp, int(is_ntt), key.h, _dptr(dest), assign, self._stream(stream)))
+        return dest
+
+    # R1-R4 -------------------------------------------------------------------------------------
+    def mod_switch_to_next(self, src, dst, count, nl, kind, stream=None):
+        _chk(self.L.b2_mod_switch_to_next(self.h, _dptr(src), _dptr(dst), count, nl, kind, self._stream(stream)))
+        return dst
+
+    # element-wise ------------------------------------------------------------------------------
+    def add(self, a, b, out, count, ncomp, table_base=0, stream=None):
+        _chk(self.L.b2_add(self.h, _dptr(a), _dptr(b), _dptr(out), count, ncomp, table_base, self._stream(stream))); return out
+
+    def sub(self, a, b, out, count, ncomp, table_base=0, stream=None):
+        _chk(self.L.b2_sub(self.h, _dptr(a), _dptr(b), _dptr(out), count, ncomp, table_base, self._stream(stream))); return out
+
+    def negate(self, a, out, count, ncomp, table_base=0, stream=None):
+        _chk(self.L.b2_negate(self.h, _dptr(a), _dptr(out), count, ncomp, table_base, self._stream(stream))); return out
+
+    def dyadic_convolute(self, a, na, b, nb, out, ncomp, batch=1, stream=None):
+        _chk(self.L.b2_dyadic_convolute(self.h, _dptr(a), na, _dptr(b), nb, _dptr(out), batch, ncomp, self._stream(stream))); return out
+
+    def dyadic_square(self, a, out, ncomp, batch=1, stream=None):
+        _chk(self.L.b2_dyadic_square(self.h, _dptr(a), _dptr(out), batch, ncomp, self._stream(stream))); return out
+
+    def dyadic_broadcast(self, a, plain, out, pcount, ncomp, accumulate=False, stream=None):
+        _chk(self.L.b2_dyadic_broadcast(self.h, _dptr(a), _dptr(plain), _dptr(out), pcount, ncomp, int(accumulate), self._stream(stream))); return out
+
+    def negacyclic_shift(self, a, shift, out, count, ncomp, table_base=0, stream=None):
+        _chk(self.L.b2_negacyclic_shift(self.h, _dptr(a), shift, _dptr(out), count, ncomp, table_base, self._stream(stream))); return out
+
+    def galois(self, src, galois_elt, out, count, ncomp, is_ntt, table_base=0, stream=None):
+        _chk(self.L.b2_galois(self.h, _dptr(src), galois_elt, _dptr(out), count, ncomp, table_base, int(is_ntt), self._stream(stream))); return out
+
+
+class KSwitchKey:
+    def __init__(self, ctx, h, keep):
+        self.ctx, self.h, self.keep = ctx, h, keep
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().b2_kswitch_key_destroy(self.h); self.h = None
+        except Exception:
+            pass

@@ -81,6 +81,26 @@ extern "C" b2_status b2_ctx_create(int device, const b2_params *prm, b2_ctx **ou
     B2_CUDA(cudaMemcpy(c->d_twd, twd.data(), K * n * sizeof(double), cudaMemcpyHostToDevice));
     B2_CUDA(cudaMemcpy(c->d_itwd, itwd.data(), K * n * sizeof(double), cudaMemcpyHostToDevice));
     B2_CUDA(cudaMemcpy(c->d_mods, c->h_mods.data(), K * sizeof(ModInfo), cudaMemcpyHostToDevice));
+    // cross-modulus inverses used by mod-down / rescale (reference: RNSTool::inv_q_last_mod_q, inv_q_last_mod_t,
+    // src/utils/rns_tool.cu:214-231 — one RNSTool per level there, one K x K table here)
+    {
+        std::vector<Tw> inv(K * K); std::vector<uint64_t> invt(K, 0);
+        for (size_t a = 0; a < K; a++) {
+            for (size_t b = 0; b < K; b++) {
+                if (a == b) { inv[a * K + b].x = 0; inv[a * K + b].y = 0; continue; }
+                uint64_t v = host::invmod(c->q[a] % c->q[b], c->q[b]);
+                inv[a * K + b].x = v; inv[a * K + b].y = host::shoup_quotient(v, c->q[b]);
+            }
+            if (c->t > 1) invt[a] = host::invmod(c->q[a] % c->t, c->t);
+        }
+        if (c->t > 1) { host::u128 r = (~(host::u128)0) / c->t; c->t_r0 = (uint64_t)r; c->t_r1 = (uint64_t)(r >> 64); c->t_ratio = c->t_r1; }
+        c->h_inv_mod_t = invt;
+        B2_CUDA(cudaMalloc(&c->d_inv, K * K * sizeof(Tw)));
+        B2_CUDA(cudaMalloc(&c->d_inv_mod_t, K * sizeof(uint64_t)));
+        B2_CUDA(cudaMalloc(&c->d_galois, n * sizeof(uint32_t)));
+        B2_CUDA(cudaMemcpy(c->d_inv, inv.data(), K * K * sizeof(Tw), cudaMemcpyHostToDevice));
+        B2_CUDA(cudaMemcpy(c->d_inv_mod_t, invt.data(), K * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    }
     *out = c;
     return B2_OK;
 }
@@ -88,6 +108,6 @@ extern "C" b2_status b2_ctx_create(int device, const b2_params *prm, b2_ctx **ou
 extern "C" void b2_ctx_destroy(b2_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaFree(c->d_tw); cudaFree(c->d_itw); cudaFree(c->d_twd); cudaFree(c->d_itwd); cudaFree(c->d_mods); cudaFree(c->ws); cudaFree(c->stage);
+    cudaFree(c->d_tw); cudaFree(c->d_itw); cudaFree(c->d_twd); cudaFree(c->d_itwd); cudaFree(c->d_mods); cudaFree(c->d_inv); cudaFree(c->d_inv_mod_t); cudaFree(c->d_galois); cudaFree(c->ws); cudaFree(c->stage);
     delete c;
 }

@@ -19,6 +19,11 @@ struct b2_ctx {
     b2::Tw *d_itw = nullptr;         // [K][N] inverse twiddles
     double *d_twd = nullptr, *d_itwd = nullptr;   // same tables as doubles (FP64-pipe path)
     std::vector<b2::ModInfo> h_mods;
+    b2::Tw *d_inv = nullptr;         // [K][K]: d_inv[a*K+b] = q_a^-1 mod q_b as a Shoup pair (a != b)
+    uint64_t *d_inv_mod_t = nullptr; // [K]: q_a^-1 mod t (BFV/BGV), 0 when t == 0
+    uint64_t t_ratio = 0, t_r0 = 0, t_r1 = 0;   // floor(2^64 / t), floor(2^128 / t)
+    std::vector<uint64_t> h_inv_mod_t;
+    uint32_t *d_galois = nullptr; uint64_t galois_elt_cached = 0;   // NTT-form permutation table of the last Galois element
     // workspace arena (grown on demand outside the hot path; never shrinks)
     void *ws = nullptr; size_t ws_bytes = 0;
     // host-buffer staging for the *_host entry points
@@ -38,6 +43,7 @@ struct NttOperand {           // where the limbs live: contiguous base, or per-b
     const uint64_t *in; uint64_t *out;
     const uint64_t *const *in_ptrs; uint64_t *const *out_ptrs;   // device arrays (or null)
 };
+struct LimbGroup;
 b2_status ntt_launch(b2_ctx *ctx, bool forward, const uint64_t *in, uint64_t *out, size_t batch, size_t pcount,
                      size_t ncomp, int mode, size_t table_base, size_t decomp, cudaStream_t stream);
 }

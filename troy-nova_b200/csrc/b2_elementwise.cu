@@ -1,0 +1,218 @@
+// b2_elementwise.cu — element-wise RNS kernels (M1, M3, E1, G1 in SURVEY.md §8a): ct x ct dyadic
+// convolution / square (src/fgk/dyadic_convolute.cu:6-148), ct x pt broadcast product with optional
+// accumulate (:151-292), add / sub / negate / negacyclic shift (src/utils/poly_small_mod.cu:263-949) and
+// the Galois automorphisms (src/utils/galois.cu:141-300).  All HBM-bound: 16-byte vector accesses, one
+// pass over the data, the modulus record read once per thread.  Layout [count][ncomp][N]; the modulus
+// of limb j is table_base + j.
+#include "b2_ctx.h"
+
+using namespace b2;
+
+namespace b2 {
+
+struct EwShape { u32 ncomp, n2, table_base; u64 total2; };   // n2 = N/2 (vector units), total2 = count*ncomp*n2
+
+__device__ __forceinline__ const ModInfo &ew_mod(const ModInfo *mods, const EwShape &S, u64 v) {
+    return mods[S.table_base + (u32)((v / S.n2) % S.ncomp)];
+}
+
+template <int OP>   // 0 add, 1 sub, 2 negate
+__global__ void __launch_bounds__(256) ew_addsub_kernel(const ulonglong2 *__restrict__ a, const ulonglong2 *__restrict__ b, ulonglong2 *__restrict__ o,
+                                                          const ModInfo *__restrict__ mods, EwShape S) {
+    for (u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x; v < S.total2; v += (u64)gridDim.x * blockDim.x) {
+        const u64 p = ew_mod(mods, S, v).p;
+        ulonglong2 x = a[v], y, r;
+        if (OP != 2) y = b[v];
+        if (OP == 0) { r.x = addmod(x.x, y.x, p); r.y = addmod(x.y, y.y, p); }
+        if (OP == 1) { r.x = submod(x.x, y.x, p); r.y = submod(x.y, y.y, p); }
+        if (OP == 2) { r.x = negmod(x.x, p); r.y = negmod(x.y, p); }
+        o[v] = r;
+    }
+}
+
+// out[b][pidx] = sum_{x+y=pidx} a[b][x] o b[b][y]     (kernel_dyadic_convolute, dyadic_convolute.cu:6-42)
+__global__ void __launch_bounds__(256) ew_convolute_kernel(const ulonglong2 *__restrict__ a, u32 na, const ulonglong2 *__restrict__ b, u32 nb,
+                                                             ulonglong2 *__restrict__ o, const ModInfo *__restrict__ mods, u32 ncomp, u32 n2, u32 batch) {
+    const u64 per = (u64)ncomp * n2;                      // vectors per polynomial
+    const u64 total = (u64)batch * per;
+    for (u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (u64)gridDim.x * blockDim.x) {
+        const u64 bi = v / per, r = v % per;
+        const ModInfo &M = mods[(u32)(r / n2)];
+        const u64 p = M.p, r0 = M.r0, r1 = M.r1;
+        ulonglong2 av[3], bv[3];
+        for (u32 x = 0; x < na; x++) av[x] = a[(bi * na + x) * per + r];
+        for (u32 y = 0; y < nb; y++) bv[y] = b[(bi * nb + y) * per + r];
+        const u32 no = na + nb - 1;
+        for (u32 pidx = 0; pidx < no; pidx++) {
+            u64 l0 = 0, h0 = 0, l1 = 0, h1 = 0;
+            for (u32 x = 0; x < na; x++) {
+                if (pidx < x || pidx - x >= nb) continue;
+                mac128(l0, h0, av[x].x, bv[pidx - x].x);
+                mac128(l1, h1, av[x].y, bv[pidx - x].y);
+            }
+            ulonglong2 res;
+            res.x = barrett128(l0, h0, p, r0, r1); res.y = barrett128(l1, h1, p, r0, r1);
+            o[(bi * no + pidx) * per + r] = res;
+        }
+    }
+}
+
+// (c0^2, 2 c0 c1, c1^2)     (kernel_dyadic_square, dyadic_convolute.cu:92-112)
+__global__ void __launch_bounds__(256) ew_square_kernel(const ulonglong2 *__restrict__ a, ulonglong2 *__restrict__ o, const ModInfo *__restrict__ mods,
+                                                          u32 ncomp, u32 n2, u32 batch) {
+    const u64 per = (u64)ncomp * n2, total = (u64)batch * per;
+    for (u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (u64)gridDim.x * blockDim.x) {
+        const u64 bi = v / per, r = v % per;
+        const ModInfo &M = mods[(u32)(r / n2)];
+        const u64 p = M.p, r0 = M.r0, r1 = M.r1;
+        const ulonglong2 c0 = a[(bi * 2) * per + r], c1 = a[(bi * 2 + 1) * per + r];
+        ulonglong2 o0, o1, o2;
+        o0.x = mulmod(c0.x, c0.x, p, r0, r1); o0.y = mulmod(c0.y, c0.y, p, r0, r1);
+        u64 cx = mulmod(c0.x, c1.x, p, r0, r1), cy = mulmod(c0.y, c1.y, p, r0, r1);
+        o1.x = addmod(cx, cx, p); o1.y = addmod(cy, cy, p);
+        o2.x = mulmod(c1.x, c1.x, p, r0, r1); o2.y = mulmod(c1.y, c1.y, p, r0, r1);
+        o[(bi * 3) * per + r] = o0; o[(bi * 3 + 1) * per + r] = o1; o[(bi * 3 + 2) * per + r] = o2;
+    }
+}
+
+// out[k] (+)= a[k] o plain , k < pcount          (kernel_dyadic_broadcast_product_ps, dyadic_convolute.cu:151-170)
+template <bool ACC>
+__global__ void __launch_bounds__(256) ew_broadcast_kernel(const ulonglong2 *__restrict__ a, const ulonglong2 *__restrict__ pl, ulonglong2 *__restrict__ o,
+                                                             const ModInfo *__restrict__ mods, EwShape S) {
+    const u64 per = (u64)S.ncomp * S.n2;
+    for (u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x; v < S.total2; v += (u64)gridDim.x * blockDim.x) {
+        const ModInfo &M = ew_mod(mods, S, v);
+        const u64 p = M.p, r0 = M.r0, r1 = M.r1;
+        const ulonglong2 x = a[v], y = pl[v % per];
+        ulonglong2 r;
+        r.x = mulmod(x.x, y.x, p, r0, r1); r.y = mulmod(x.y, y.y, p, r0, r1);
+        if (ACC) { const ulonglong2 d = o[v]; r.x = addmod(d.x, r.x, p); r.y = addmod(d.y, r.y, p); }
+        o[v] = r;
+    }
+}
+
+// multiply by x^shift in Z[x]/(x^N+1)             (host_negacyclic_shift_ps, poly_small_mod.cu:902-925)
+__global__ void __launch_bounds__(256) ew_negacyclic_shift_kernel(const u64 *__restrict__ a, u64 *__restrict__ o, const ModInfo *__restrict__ mods,
+                                                                    u32 ncomp, u32 n, u32 table_base, u64 total, u32 shift) {
+    for (u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (u64)gridDim.x * blockDim.x) {
+        const u32 x = (u32)(v % n);                      // destination index
+        const u64 limb = v / n;
+        const u64 p = mods[table_base + (u32)(limb % ncomp)].p;
+        const u32 src = (x - shift) & (n - 1);           // source index: src + shift = x (mod N)
+        const bool neg = ((src + shift) & n) != 0;
+        const u64 val = a[limb * n + src];
+        o[v] = (neg && val) ? p - val : val;
+    }
+}
+
+// coefficient form: coefficient i moves to i*g mod N with sign (-1)^floor(i*g/N)   (galois.cu:141-156)
+// written as a GATHER (source index = dst * g^-1 mod 2N) so that stores are coalesced.
+__global__ void __launch_bounds__(256) ew_galois_coeff_kernel(const u64 *__restrict__ a, u64 *__restrict__ o, const ModInfo *__restrict__ mods,
+                                                                u32 ncomp, u32 logn, u32 table_base, u64 total, u32 ginv) {
+    const u32 n = 1u << logn;
+    for (u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (u64)gridDim.x * blockDim.x) {
+        const u32 dst = (u32)(v & (n - 1));
+        const u64 limb = v >> logn;
+        const u64 p = mods[table_base + (u32)(limb % ncomp)].p;
+        const u32 raw = (dst * ginv) & (2 * n - 1);      // i or i + N
+        const u32 src = raw & (n - 1);
+        // i*g mod 2N = dst (+N if sign): with i = src: sign bit = bit logN of src*g = bit logN of (raw*g - (raw>=n? n*g:0))...
+        // equivalently x^(src*g) = +-x^dst ; raw >= n  <=>  src*g mod 2N = dst + N  <=> negative
+        const u64 val = a[(limb << logn) + src];
+        const bool neg = raw >= n;
+        o[v] = (neg && val) ? p - val : val;
+    }
+}
+
+// NTT form: out[i] = in[pi_g(i)], pi_g(i) = bitrev(((g * bitrev_{logN+1}(i + N)) >> 1) & (N-1))   (galois.cu:25-42)
+// The permutation is computed with BREV instead of being read from an 8-byte-per-index table.
+__global__ void __launch_bounds__(256) ew_galois_ntt_kernel(const u64 *__restrict__ a, u64 *__restrict__ o, u32 logn, u64 total, u32 g) {
+    const u32 n = 1u << logn;
+    for (u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (u64)gridDim.x * blockDim.x) {
+        const u32 i = (u32)(v & (n - 1));
+        const u32 rev = __brev(i + n) >> (31 - logn);
+        const u32 raw = ((g * rev) >> 1) & (n - 1);
+        const u32 src = __brev(raw) >> (32 - logn);
+        o[v] = a[(v >> logn << logn) + src];
+    }
+}
+
+static inline unsigned ew_grid(u64 total) { return (unsigned)std::min<u64>((total + 255) / 256, 148u * 32u); }
+
+}  // namespace b2
+
+#define EW_PROLOG(cond, msg)                                  \
+    B2_REQUIRE(ctx, "null ctx");                              \
+    B2_REQUIRE(cond, msg);                                    \
+    B2_CUDA(cudaSetDevice(ctx->device));                      \
+    cudaStream_t stream = (cudaStream_t)stream_;              \
+    const size_t n = ctx->n; (void)n;
+
+extern "C" {
+
+static b2_status ew_addsub(int op, b2_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t count, size_t ncomp, size_t table_base, void *stream_) {
+    EW_PROLOG(a && out && (op == 2 || b) && table_base + ncomp <= ctx->K && ctx->n >= 2, "bad arguments");
+    if (count * ncomp == 0) return B2_OK;
+    EwShape S{(u32)ncomp, (u32)(n / 2), (u32)table_base, (u64)count * ncomp * (n / 2)};
+    const unsigned grid = ew_grid(S.total2);
+    if (op == 0) ew_addsub_kernel<0><<<grid, 256, 0, stream>>>((const ulonglong2 *)a, (const ulonglong2 *)b, (ulonglong2 *)out, ctx->d_mods, S);
+    if (op == 1) ew_addsub_kernel<1><<<grid, 256, 0, stream>>>((const ulonglong2 *)a, (const ulonglong2 *)b, (ulonglong2 *)out, ctx->d_mods, S);
+    if (op == 2) ew_addsub_kernel<2><<<grid, 256, 0, stream>>>((const ulonglong2 *)a, nullptr, (ulonglong2 *)out, ctx->d_mods, S);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+b2_status b2_add(b2_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t count, size_t ncomp, size_t table_base, void *stream) { return ew_addsub(0, ctx, a, b, out, count, ncomp, table_base, stream); }
+b2_status b2_sub(b2_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t count, size_t ncomp, size_t table_base, void *stream) { return ew_addsub(1, ctx, a, b, out, count, ncomp, table_base, stream); }
+b2_status b2_negate(b2_ctx *ctx, const uint64_t *a, uint64_t *out, size_t count, size_t ncomp, size_t table_base, void *stream) { return ew_addsub(2, ctx, a, nullptr, out, count, ncomp, table_base, stream); }
+
+b2_status b2_dyadic_convolute(b2_ctx *ctx, const uint64_t *a, size_t na, const uint64_t *b, size_t nb, uint64_t *out, size_t batch, size_t ncomp, void *stream_) {
+    EW_PROLOG(a && b && out && na >= 1 && nb >= 1 && na <= 3 && nb <= 3 && ncomp <= ctx->K && ctx->n >= 2, "bad arguments (polynomial counts must be 1..3)");
+    if (batch * ncomp == 0) return B2_OK;
+    const u64 total = (u64)batch * ncomp * (n / 2);
+    ew_convolute_kernel<<<ew_grid(total), 256, 0, stream>>>((const ulonglong2 *)a, (u32)na, (const ulonglong2 *)b, (u32)nb, (ulonglong2 *)out, ctx->d_mods, (u32)ncomp, (u32)(n / 2), (u32)batch);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+b2_status b2_dyadic_square(b2_ctx *ctx, const uint64_t *a, uint64_t *out, size_t batch, size_t ncomp, void *stream_) {
+    EW_PROLOG(a && out && ncomp <= ctx->K && ctx->n >= 2, "bad arguments");
+    if (batch * ncomp == 0) return B2_OK;
+    const u64 total = (u64)batch * ncomp * (n / 2);
+    ew_square_kernel<<<ew_grid(total), 256, 0, stream>>>((const ulonglong2 *)a, (ulonglong2 *)out, ctx->d_mods, (u32)ncomp, (u32)(n / 2), (u32)batch);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+b2_status b2_dyadic_broadcast(b2_ctx *ctx, const uint64_t *a, const uint64_t *plain, uint64_t *out, size_t pcount, size_t ncomp, int accumulate, void *stream_) {
+    EW_PROLOG(a && plain && out && ncomp <= ctx->K && ctx->n >= 2, "bad arguments");
+    if (pcount * ncomp == 0) return B2_OK;
+    EwShape S{(u32)ncomp, (u32)(n / 2), 0u, (u64)pcount * ncomp * (n / 2)};
+    if (accumulate) ew_broadcast_kernel<true><<<ew_grid(S.total2), 256, 0, stream>>>((const ulonglong2 *)a, (const ulonglong2 *)plain, (ulonglong2 *)out, ctx->d_mods, S);
+    else ew_broadcast_kernel<false><<<ew_grid(S.total2), 256, 0, stream>>>((const ulonglong2 *)a, (const ulonglong2 *)plain, (ulonglong2 *)out, ctx->d_mods, S);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+b2_status b2_negacyclic_shift(b2_ctx *ctx, const uint64_t *a, size_t shift, uint64_t *out, size_t count, size_t ncomp, size_t table_base, void *stream_) {
+    EW_PROLOG(a && out && a != out && table_base + ncomp <= ctx->K && shift < 2 * ctx->n, "bad arguments (shift must be below 2N, out of place)");
+    if (count * ncomp == 0) return B2_OK;
+    const u64 total = (u64)count * ncomp * n;
+    ew_negacyclic_shift_kernel<<<ew_grid(total), 256, 0, stream>>>((const u64 *)a, (u64 *)out, ctx->d_mods, (u32)ncomp, (u32)n, (u32)table_base, total, (u32)shift);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+b2_status b2_galois(b2_ctx *ctx, const uint64_t *in, uint64_t galois_elt, uint64_t *out, size_t count, size_t ncomp, size_t table_base, int is_ntt, void *stream_) {
+    EW_PROLOG(in && out && in != out && table_base + ncomp <= ctx->K, "bad arguments (out of place only)");
+    B2_REQUIRE((galois_elt & 1) && galois_elt < 2 * ctx->n, "Galois element must be odd and below 2N");   // reference: src/utils/galois.cu:147-149
+    if (count * ncomp == 0) return B2_OK;
+    const u64 total = (u64)count * ncomp * n;
+    if (is_ntt) ew_galois_ntt_kernel<<<ew_grid(total), 256, 0, stream>>>((const u64 *)in, (u64 *)out, ctx->logn, total, (u32)galois_elt);
+    else {
+        // g^-1 mod 2N (g odd): Newton iteration
+        u32 g = (u32)galois_elt, inv = g;
+        for (int it = 0; it < 5; it++) inv *= 2 - g * inv;
+        inv &= (u32)(2 * n - 1);
+        ew_galois_coeff_kernel<<<ew_grid(total), 256, 0, stream>>>((const u64 *)in, (u64 *)out, ctx->d_mods, (u32)ncomp, ctx->logn, (u32)table_base, total, inv);
+    }
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+// b2_fused.cuh — load / store functors shared by the fused transforms of keyswitch mod-down and
+// rescale / modswitch (rounding division by the last modulus).
+#pragma once
+#include "b2_ntt.cuh"
+#include "../../include/b2rns.h"
+
+namespace b2 {
+
+// ---- step 5 functors ---------------------------------------------------------------------------------
+// BFV/CKKS: t = ((u + P/2) mod P) mod q_j + q_j - (P/2 mod q_j)      (ski_util6, :570-598)
+// BGV:      t = ((-u P^-1 mod t) mod q_j) * P + u  mod q_j           (ski_util5 step 1, :436-474)
+struct ModDownTerm {
+    const u64 *u;         // [count][N]: coefficient form of the limb being divided out
+    const ModInfo *mods;
+    u32 last, n;     // last: index of the modulus being divided out (P for keyswitch, q_{nl-1} for rescale)
+    int bgv;
+    u64 t, t_ratio, t_r0, t_r1, pinv_t;
+    __device__ __forceinline__ u64 term(int j, int k, u32 x) const {
+        const ModInfo &Q = mods[j];
+        const u64 q = Q.p, P = mods[last].p;
+        const u64 uv = u[(u64)k * n + x];
+        if (!bgv) {
+            const u64 half = P >> 1;
+            u64 r = uv + half; r = r >= P ? r - P : r;
+            const u64 rq = P > q ? barrett64(r, q, Q.ratio) : r;
+            return rq + q - barrett64(half, q, Q.ratio);
+        }
+        u64 kt = barrett64(uv, t, t_ratio);
+        kt = kt ? t - kt : 0;
+        if (pinv_t != 1) kt = mulmod(kt, pinv_t, t, t_r0, t_r1);
+        const u64 a = mulmod(barrett64(kt, q, Q.ratio), barrett64(P, q, Q.ratio), q, Q.r0, Q.r1);
+        return addmod(a, barrett64(uv, q, Q.ratio), q);
+    }
+};
+struct ModDownLoad {      // NTT-form path: the transform's input IS the term
+    ModDownTerm T;
+    __device__ __forceinline__ u64 operator()(int g, int c, u64, u32 x) const { return T.term(g, c, x); }
+};
+// final store: out = (s - t) * P^-1 mod q_j ; then Overwrite / AddInplace / OverwriteExceptFirst
+struct ModDownStore {
+    ModDownTerm T;
+    const u64 *prod;      // [2][R][N]
+    const Tw *pinv;       // [K] : P^-1 mod q_j  (row K-1 of the inverse table)
+    u64 *dest;            // [2][decomp][N]
+    u32 decomp, assign;
+    int t_from_transform; // 1: transformed value is t (NTT-form ciphertext); 0: transformed value is s, t computed here
+    __device__ __forceinline__ void operator()(int j, int k, u64, u32 x, u64 v) const {
+        const u64 q = T.mods[j].p, n = T.n;
+        u64 s, t;
+        if (t_from_transform) { s = prod[((u64)k * (decomp + 1) + j) * n + x]; t = v; }
+        else { s = v; t = T.term(j, k, x); t = csub(t, q); }     // term < 2q -> canonical
+        const u64 r = shoup(submod(s, t, q), pinv[j], q);
+        u64 *d = dest + ((u64)k * decomp + j) * n + x;
+        const bool add = assign == B2_ASSIGN_ADD_INPLACE || (k == 0 && assign == B2_ASSIGN_OVERWRITE_EXCEPT_FIRST);
+        *d = add ? addmod(*d, r, q) : r;
+    }
+};
+
+// rescale / modswitch final store: out[p][i] = (in[p][i] - t) * q_last^-1 mod q_i
+// (src/utils/rns_tool.cu:629-644 CKKS step 2, :1680-1711 BGV step 2)
+struct RescaleStore {
+    const u64 *in;        // [count][nl][N]
+    u64 *out;             // [count][nl-1][N]
+    const ModInfo *mods;
+    const Tw *inv;        // row `last` of the inverse table: q_last^-1 mod q_i
+    u32 nl, n;
+    __device__ __forceinline__ void operator()(int i, int p, u64, u32 x, u64 t) const {
+        const u64 q = mods[i].p;
+        const u64 s = in[((u64)p * nl + i) * n + x];
+        out[((u64)p * (nl - 1) + i) * n + x] = shoup(submod(s, t, q), inv[i], q);
+    }
+};
+struct LastLimbLoad {     // the limb being divided out, for its inverse transform
+    const u64 *in; u32 nl, n;
+    __device__ __forceinline__ u64 operator()(int, int p, u64, u32 x) const { return in[((u64)p * nl + nl - 1) * n + x]; }
+};
+
+}  // namespace b2

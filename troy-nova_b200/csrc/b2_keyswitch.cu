@@ -1,0 +1,175 @@
+// b2_keyswitch.cu — the keyswitching core (K1-K5 in SURVEY.md §8a).  Replaces
+// Evaluator::switch_key_internal(_batched) (src/evaluator_keyswitching_core.cu:757-1267) and its
+// helpers fgk::switch_key::set_accumulate / accumulate_products (src/fgk/switch_key.cu:6-176) and
+// kernel_ski_util5/6/7_merged (src/evaluator_keyswitching_core.cu:436-688).
+//
+// Pipeline (R = decomp + 1 output moduli m_i = q_0..q_{decomp-1}, P; `temp` and `prod` live in the
+// context's workspace arena, nothing is allocated on the hot path):
+//   1. c = INTT(target)                                            (skipped for coefficient-form input)
+//   2. temp[i][j] = NTT_{m_i}(c_j mod m_i)   — the mod-up re-reduction (the reference's set_accumulate
+//      kernel and its (L+1)·L·N-word buffer) is fused into the NTT's first-pass loader
+//   3. prod[k][i] = sum_j temp[i][j] o key_j[k][i]  mod m_i        — 128-bit lazy accumulation, one
+//      Barrett reduction per output (the reference reduces every term; result is canonical either way)
+//   4. u_k = INTT_P(prod[k][decomp])
+//   5. mod-down, fused into ONE forward transform: its loader builds t_{k,j} from u_k on the fly
+//      (ski_util6 / ski_util5_step1) and its last-pass store computes (prod[k][j] - t)·P^-1 mod q_j and
+//      assigns / accumulates into the destination (ski_util7 / ski_util5_step2).
+//      For coefficient-form (BFV) ciphertexts the same happens around INTT(prod[k][j]).
+#include "b2_ntt_launch.cuh"
+#include "b2_fused.cuh"
+
+using namespace b2;
+
+struct b2_kswitch_key {
+    const uint64_t **d_ptrs = nullptr;   // device array of D digit base pointers, each [2][K][N] NTT form
+    size_t digits = 0;
+    int device = 0;
+};
+
+namespace b2 {
+
+// ---- step 2 loader: c_j re-reduced modulo the group's modulus (src/fgk/switch_key.cu:6-27) ----------
+struct ModUpLoad {
+    const u64 *tc;        // [decomp][N] coefficient form
+    const ModInfo *mods;
+    u32 decomp, K, n;
+    __device__ __forceinline__ u64 operator()(int g, int c, u64, u32 x) const {
+        const u32 ki = (u32)g == decomp ? K - 1 : (u32)g;
+        const u64 v = tc[(u64)c * n + x];
+        const u64 m = mods[ki].p;
+        // q_j <= m_i: already canonical modulo m_i
+        return (mods[c].p <= m) ? v : barrett64(v, m, mods[ki].ratio);
+    }
+};
+
+// ---- step 3: key inner product (src/fgk/switch_key.cu:77-132) --------------------------------------
+// one thread per (i, coefficient pair); loops over the decomp digits with 128-bit lazy accumulators.
+__global__ void __launch_bounds__(256) ks_inner_product_kernel(const u64 *__restrict__ temp, const u64 *const *__restrict__ keys,
+                                                                 u64 *__restrict__ prod, const ModInfo *__restrict__ mods,
+                                                                 u32 decomp, u32 K, u32 n) {
+    const u32 i = blockIdx.y;                       // output modulus index 0..decomp
+    const u32 ki = i == decomp ? K - 1 : i;
+    const u32 x = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (x >= n) return;
+    const ModInfo &M = mods[ki];
+    const u64 p = M.p, r0 = M.r0, r1 = M.r1;
+    u64 a0l = 0, a0h = 0, a1l = 0, a1h = 0, b0l = 0, b0h = 0, b1l = 0, b1h = 0;
+    const u64 *tp = temp + ((u64)i * decomp) * n + x;
+    for (u32 j = 0; j < decomp; j++) {
+        const ulonglong2 d = *reinterpret_cast<const ulonglong2 *>(tp + (u64)j * n);
+        const u64 *kp = keys[j] + (u64)ki * n + x;
+        const ulonglong2 k0 = __ldg(reinterpret_cast<const ulonglong2 *>(kp));
+        const ulonglong2 k1 = __ldg(reinterpret_cast<const ulonglong2 *>(kp + (u64)K * n));
+        mac128(a0l, a0h, d.x, k0.x); mac128(a1l, a1h, d.y, k0.y);
+        mac128(b0l, b0h, d.x, k1.x); mac128(b1l, b1h, d.y, k1.y);
+        if ((j & 7) == 7) {     // keep the lazy 128-bit sums below 2^125 (8 products of 61-bit residues)
+            a0l = barrett128(a0l, a0h, p, r0, r1); a0h = 0; a1l = barrett128(a1l, a1h, p, r0, r1); a1h = 0;
+            b0l = barrett128(b0l, b0h, p, r0, r1); b0h = 0; b1l = barrett128(b1l, b1h, p, r0, r1); b1h = 0;
+        }
+    }
+    const u32 R = decomp + 1;
+    ulonglong2 o0, o1;
+    o0.x = barrett128(a0l, a0h, p, r0, r1); o0.y = barrett128(a1l, a1h, p, r0, r1);
+    o1.x = barrett128(b0l, b0h, p, r0, r1); o1.y = barrett128(b1l, b1h, p, r0, r1);
+    *reinterpret_cast<ulonglong2 *>(prod + ((u64)0 * R + i) * n + x) = o0;
+    *reinterpret_cast<ulonglong2 *>(prod + ((u64)1 * R + i) * n + x) = o1;
+}
+
+struct SpecialLoad {      // step 4: the special-prime limb of prod[k]
+    const u64 *prod; u32 R, decomp, n;
+    __device__ __forceinline__ u64 operator()(int, int k, u64, u32 x) const { return prod[((u64)k * R + decomp) * n + x]; }
+};
+struct ProdLoad {         // coefficient-form path: transform prod[k][j] itself (inverse NTT)
+    const u64 *prod; u32 decomp, n;
+    __device__ __forceinline__ u64 operator()(int j, int k, u64, u32 x) const { return prod[((u64)k * (decomp + 1) + j) * n + x]; }
+};
+
+}  // namespace b2
+
+extern "C" {
+
+b2_status b2_kswitch_key_create(b2_ctx *ctx, const uint64_t *const *digit_ptrs, size_t digits, b2_kswitch_key **out) {
+    B2_REQUIRE(ctx && digit_ptrs && out && digits >= 1 && digits <= 64, "bad arguments");
+    B2_CUDA(cudaSetDevice(ctx->device));
+    b2_kswitch_key *k = new b2_kswitch_key();
+    k->digits = digits; k->device = ctx->device;
+    cudaError_t e = cudaMalloc((void **)&k->d_ptrs, digits * sizeof(uint64_t *));
+    if (e != cudaSuccess) { delete k; return cuda_fail(e, "cudaMalloc(key ptrs)"); }
+    e = cudaMemcpy((void *)k->d_ptrs, digit_ptrs, digits * sizeof(uint64_t *), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree((void *)k->d_ptrs); delete k; return cuda_fail(e, "cudaMemcpy(key ptrs)"); }
+    *out = k;
+    return B2_OK;
+}
+b2_status b2_kswitch_key_create_contiguous(b2_ctx *ctx, const uint64_t *key, size_t digits, b2_kswitch_key **out) {
+    B2_REQUIRE(ctx && key && digits >= 1 && digits <= 64, "bad arguments");
+    const uint64_t *ptrs[64];
+    for (size_t j = 0; j < digits; j++) ptrs[j] = key + j * 2 * ctx->K * ctx->n;
+    return b2_kswitch_key_create(ctx, ptrs, digits, out);
+}
+void b2_kswitch_key_destroy(b2_kswitch_key *k) {
+    if (!k) return;
+    cudaSetDevice(k->device);
+    cudaFree((void *)k->d_ptrs);
+    delete k;
+}
+
+b2_status b2_keyswitch(b2_ctx *ctx, const uint64_t *target, size_t decomp, int is_ntt, const b2_kswitch_key *key,
+                       uint64_t *dest, int assign, void *stream_) {
+    B2_REQUIRE(ctx && target && key && dest, "null argument");
+    B2_REQUIRE(decomp >= 1 && decomp + 1 <= ctx->K, "decomp must be in [1, K-1] (keyswitching needs a special prime)");
+    B2_REQUIRE(key->digits >= decomp, "keyswitching key has fewer digits than the ciphertext has limbs");
+    B2_REQUIRE(assign >= 0 && assign <= 2, "unknown assign method");
+    B2_REQUIRE(ctx->scheme != B2_SCHEME_BGV || is_ntt, "BGV ciphertexts are NTT-form");
+    B2_REQUIRE(ctx->scheme != B2_SCHEME_BGV || ctx->t > 1, "BGV needs a plain modulus");
+    B2_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t n = ctx->n, K = ctx->K, R = decomp + 1;
+    // workspace: tc [decomp][N] | temp [R][decomp][N] | prod [2][R][N] | u [2][N] | mid [2][decomp][N]
+    const size_t w_tc = decomp * n, w_temp = R * decomp * n, w_prod = 2 * R * n, w_u = 2 * n, w_mid = 2 * decomp * n;
+    b2_status st = ensure_ws(ctx, (w_tc + w_temp + w_prod + w_u + w_mid) * 8);
+    if (st != B2_OK) return st;
+    u64 *tc = (u64 *)ctx->ws, *temp = tc + w_tc, *prod = temp + w_temp, *u = prod + w_prod, *mid = u + w_u;
+
+    // 1. coefficient form of the target
+    const u64 *tcoef = (const u64 *)target;
+    if (is_ntt) {
+        st = ntt_launch(ctx, false, target, (uint64_t *)tc, 1, 1, decomp, B2_TABLES_COMPONENTWISE, 0, 0, stream);
+        if (st != B2_OK) return st;
+        tcoef = tc;
+    }
+    // 2. mod-up + NTT: group i = output modulus, limbs j = digits; results temp[i][j]
+    {
+        std::vector<LimbGroup> groups;
+        for (size_t i = 0; i < R; i++) groups.push_back(LimbGroup{(u32)(i == decomp ? K - 1 : i), (u32)decomp, (u64)(i * decomp * n), (u64)n});
+        ModUpLoad ld{tcoef, ctx->d_mods, (u32)decomp, (u32)K, (u32)n};
+        st = run_ntt(ctx, true, groups, temp, ld, PlainStore{temp}, stream);
+        if (st != B2_OK) return st;
+    }
+    // 3. key inner product
+    {
+        dim3 grid((unsigned)((n / 2 + 255) / 256), (unsigned)R);
+        ks_inner_product_kernel<<<grid, 256, 0, stream>>>(temp, (const u64 *const *)key->d_ptrs, prod, ctx->d_mods, (u32)decomp, (u32)K, (u32)n);
+        B2_CUDA(cudaGetLastError());
+    }
+    // 4. u_k = INTT_P(prod[k][decomp])
+    {
+        std::vector<LimbGroup> groups{LimbGroup{(u32)(K - 1), 2u, 0, (u64)n}};
+        SpecialLoad ld{prod, (u32)R, (u32)decomp, (u32)n};
+        st = run_ntt(ctx, false, groups, u, ld, PlainStore{u}, stream);
+        if (st != B2_OK) return st;
+    }
+    // 5. mod-down fused around one transform of [2][decomp] limbs (group j = modulus, limb k = poly)
+    {
+        std::vector<LimbGroup> groups;
+        for (size_t j = 0; j < decomp; j++) groups.push_back(LimbGroup{(u32)j, 2u, (u64)(j * n), (u64)(decomp * n)});
+        ModDownTerm T{u, ctx->d_mods, (u32)(K - 1), (u32)n, ctx->scheme == B2_SCHEME_BGV ? 1 : 0, ctx->t, ctx->t_ratio, ctx->t_r0, ctx->t_r1,
+                      ctx->h_inv_mod_t[K - 1]};
+        ModDownStore sst{T, prod, ctx->d_inv + (K - 1) * K, (u64 *)dest, (u32)decomp, (u32)assign, is_ntt ? 1 : 0};
+        if (is_ntt) st = run_ntt(ctx, true, groups, mid, ModDownLoad{T}, sst, stream);
+        else st = run_ntt(ctx, false, groups, mid, ProdLoad{prod, (u32)decomp, (u32)n}, sst, stream);
+        if (st != B2_OK) return st;
+    }
+    return B2_OK;
+}
+
+}  // extern "C"

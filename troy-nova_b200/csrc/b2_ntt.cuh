@@ -46,6 +46,8 @@ struct NttLaunch {
     const ModInfo *mods;
     int logn;
     int chunk;        // limbs of one group handled by one CTA
+    int c_begin, c_end;   // absolute limb-index range of this launch (L2 wave)
+    int g_base;           // index of groups[0] in the caller's group list (functors see absolute indices)
     int n_groups;
     LimbGroup groups[NTT_MAX_GROUPS];
 };
@@ -278,20 +280,21 @@ template <int A, bool COL, bool FWD, bool FIRST, bool FINAL, int LO0, int NL0, i
 __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const __grid_constant__ NttLaunch P, Load ld, Store st) {
     __shared__ __align__(16) u64 sm[NTT_TILE];
     const LimbGroup &grp = P.groups[blockIdx.y];
-    const int c0 = blockIdx.z * P.chunk;
-    if (c0 >= (int)grp.count) return;
-    const int c1 = min((int)grp.count, c0 + P.chunk);
+    const int c0 = P.c_begin + blockIdx.z * P.chunk;
+    const int cend = min((int)grp.count, P.c_end);
+    if (c0 >= cend) return;
+    const int c1 = min(cend, c0 + P.chunk);
     const ModInfo &M = P.mods[grp.table];
     const int path = M.use_f64 ? 2 : ((FWD ? M.fwd_lazy : M.inv_lazy) ? 1 : 0);
     constexpr bool MULTI = NL1 > 0;
     for (int c = c0; c < c1; c++) {
         const u64 off = grp.base + (u64)c * grp.stride;
         if (path == 2)
-            pass_body<A, COL, FWD, FIRST, FINAL, ArithF64, LO0, NL0, LO1, NL1, LO2, NL2>(sm, M, blockIdx.x, blockIdx.y, c, off, P.logn, ld, st);
+            pass_body<A, COL, FWD, FIRST, FINAL, ArithF64, LO0, NL0, LO1, NL1, LO2, NL2>(sm, M, blockIdx.x, P.g_base + blockIdx.y, c, off, P.logn, ld, st);
         else if (path == 1)
-            pass_body<A, COL, FWD, FIRST, FINAL, ArithInt<true>, LO0, NL0, LO1, NL1, LO2, NL2>(sm, M, blockIdx.x, blockIdx.y, c, off, P.logn, ld, st);
+            pass_body<A, COL, FWD, FIRST, FINAL, ArithInt<true>, LO0, NL0, LO1, NL1, LO2, NL2>(sm, M, blockIdx.x, P.g_base + blockIdx.y, c, off, P.logn, ld, st);
         else
-            pass_body<A, COL, FWD, FIRST, FINAL, ArithInt<false>, LO0, NL0, LO1, NL1, LO2, NL2>(sm, M, blockIdx.x, blockIdx.y, c, off, P.logn, ld, st);
+            pass_body<A, COL, FWD, FIRST, FINAL, ArithInt<false>, LO0, NL0, LO1, NL1, LO2, NL2>(sm, M, blockIdx.x, P.g_base + blockIdx.y, c, off, P.logn, ld, st);
         if (MULTI && c + 1 < c1) __syncthreads();
     }
 }
