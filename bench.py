@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native RNS hot path (contract: see the task statement).
+
+Metric (BASELINE.json): NTT limbs/s at N = 2^16, on the CKKS N=65536 / 21-moduli parameter set (config C3);
+relinearize / rotate ops/s on the same parameter set are reported in the same JSON line under "extra".
+
+A "step" is one pass of the hot path over one batch of synthetic input: a forward negacyclic NTT followed
+by an inverse NTT over a key-level operand of 20 x 21 = 420 limbs (210 MiB, larger than the 126 MB L2, so
+every step streams from HBM).  840 limb-transforms per step per GPU.
+
+  value  : limb-transforms/s with the operand already resident in HBM (CUDA events, max over ranks)
+  e2e    : the same metric through the host-buffer C-ABI entry points b2_ntt_forward_host /
+           b2_ntt_inverse_host (pinned host memory -> H2D -> kernels -> D2H inside the timed region)
+  roofline: algorithmic bytes (16 N per limb-transform) / CUDA-event duration of the
+           transform launches, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline: the reference's own host (CPU) NTT, timed on this box's cores through oracle/_ref
+
+Multi-GPU (torchrun, one rank per GPU): the batch is sharded by ciphertext (independent limbs, no data-path
+collective) -> weak scaling; NCCL is only used for the barrier and the max-over-ranks of the timings.
+
+--impl reference : times the reference's CPU implementation of the same path (oracle/_ref when built, else
+the C oracle port) on all host cores, bounded sample per step.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+LOG_N = 16
+BITS = [60] + [40] * 19 + [60]          # CKKS C3: 20 ciphertext limbs + special prime
+PCOUNT, NCOMP = 20, 21                   # one key-level operand [20][21][N] = 420 limbs = 210 MiB
+METRIC = "ntt_limbs_per_s_n65536"
+UNIT = "limbs/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        mhz = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_ntt(seconds_budget=12.0, threads=None):
+    """Reference host NTT (oracle/_ref) on `threads` cores: limb-transforms/s.  Falls back to the C oracle port."""
+    import numpy as np
+    import pyoracle as po
+    n = 1 << LOG_N
+    threads = threads or min(os.cpu_count() or 1, 64)
+    limbs_per_call = 6                      # fwd over [2][3][N] per call, then inv
+    if po.ref_available():
+        kind = "reference"
+        results = [None] * threads
+
+        def work(i):
+            r = po.Reference(po.CKKS, n, [60, 40, 40, 60], seed=0x123 + i)
+            r.time_op(0, 3, 2, 0, 1)       # warm
+            t0 = time.perf_counter(); calls = 0; op_s = 0.0
+            while time.perf_counter() - t0 < seconds_budget:
+                op_s += r.time_op(0, 3, 2, 0, 1) + r.time_op(1, 3, 2, 0, 1); calls += 2
+            results[i] = (calls * limbs_per_call, op_s)
+        ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+        [t.start() for t in ths]; [t.join() for t in ths]
+        total = sum(r[0] for r in results); wall = max(r[1] for r in results)
+        rate = sum(r[0] / r[1] for r in results)
+    else:
+        kind = "port"
+        os.environ["RO_THREADS"] = str(threads)
+        moduli = po.coeff_modulus_create(n, [60, 40, 40, 60])
+        o = po.Oracle(LOG_N, moduli, 0, po.CKKS)
+        rng = np.random.default_rng(1)
+        x = o.random_poly(rng, threads, 3)
+        t0 = time.perf_counter(); total = 0
+        while time.perf_counter() - t0 < seconds_budget:
+            o.ntt_fwd(x, threads, 3); o.ntt_inv(x, threads, 3); total += 2 * threads * 3
+        wall = time.perf_counter() - t0
+        rate = total / wall
+    return {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": "%d limb-transforms (N=2^16, fwd+inv, 60/40-bit primes) over %.1f s on %d threads" % (total, wall, threads)}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    vals = []
+    for s in range(args.warmup + args.steps):
+        r = cpu_reference_ntt(seconds_budget=per_step)
+        if s >= args.warmup:
+            vals.append(r)
+    v = sum(x["value"] for x in vals) / len(vals)
+    cb = dict(vals[-1]); cb["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "C3 CKKS N=65536: forward+inverse negacyclic NTT, 60/40-bit primes, reference host branch, bounded sample per step"},
+            "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b2", choices=["b2", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b2" else args.warmup
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    b2 = importlib.import_module("troy-nova_b200")
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — libb2rns has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n = 1 << LOG_N
+    moduli = b2.coeff_modulus_create(n, BITS)
+    ctx = b2.Context(LOG_N, moduli, 0, b2.CKKS, device=local)
+    limbs = PCOUNT * NCOMP
+    g = torch.Generator(device="cuda"); g.manual_seed(1 + rank)
+    # uniform residues below each limb's modulus
+    x = torch.empty((PCOUNT, NCOMP, n), dtype=torch.int64, device="cuda")
+    for j in range(NCOMP):
+        x[:, j, :] = torch.randint(0, moduli[j], (PCOUNT, n), dtype=torch.int64, device="cuda", generator=g)
+    x0 = x.clone()
+
+    def step():
+        ctx.ntt_forward(x, pcount=PCOUNT, ncomp=NCOMP)
+        ctx.ntt_inverse(x, pcount=PCOUNT, ncomp=NCOMP)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    assert torch.equal(x, x0), "inverse(forward(x)) != x"       # round-trip sanity on the real workload
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = b2.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = b2.launch_count() - l0
+    sec = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    if sampler:
+        sampler.stop_flag = True; sampler.join(timeout=2)
+    value = world * args.steps * 2 * limbs / sec
+
+    # ---- roofline of the dominant kernels: forward transform launches alone, CUDA events on the launch stream
+    ef0, ef1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(3, args.steps // 2)
+    torch.cuda.synchronize(); ef0.record()
+    for _ in range(reps):
+        ctx.ntt_forward(x, pcount=PCOUNT, ncomp=NCOMP)
+    ef1.record(); torch.cuda.synchronize()
+    fwd_s = ef0.elapsed_time(ef1) * 1e-3 / reps
+    peak, peak_src = measured_peaks()
+    achieved = limbs * n * 16 / fwd_s / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "ntt_pass_kernel (column pass + row pass launches of one b2_ntt_forward over 420 limbs)",
+                "algorithmic_bytes_per_call": limbs * n * 16, "call_ms": fwd_s * 1e3, "peak_source": peak_src}
+
+    # ---- end to end through the host-buffer C ABI (pinned host memory, H2D + D2H inside the timed region)
+    e2e = None
+    e2e_pc = 4                                         # 4 x 21 limbs = 42 MiB per direction per call
+    hb = torch.empty((e2e_pc, NCOMP, n), dtype=torch.int64).pin_memory()
+    hb.copy_(x0[:e2e_pc].cpu())
+    hnp = hb.numpy().view(np.uint64).reshape(-1)
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(2):
+        ctx.ntt_host(True, hnp, hnp, pcount=e2e_pc, ncomp=NCOMP, stream=stream)
+        ctx.ntt_host(False, hnp, hnp, pcount=e2e_pc, ncomp=NCOMP, stream=stream)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, args.steps // 2)
+    for _ in range(e2e_steps):
+        ctx.ntt_host(True, hnp, hnp, pcount=e2e_pc, ncomp=NCOMP, stream=stream)
+        ctx.ntt_host(False, hnp, hnp, pcount=e2e_pc, ncomp=NCOMP, stream=stream)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    nbytes = e2e_pc * NCOMP * n * 8
+    e2e = {"value": world * e2e_steps * 2 * e2e_pc * NCOMP / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": 2 * nbytes,
+           "note": "b2_ntt_forward_host + b2_ntt_inverse_host on a [4][21][N] operand in pinned host memory; result verified below"}
+    assert torch.equal(hb, x0[:e2e_pc].cpu()), "e2e round trip mismatch"
+
+    # ---- extra: relinearize / rotate ops/s on the same parameter set (keyswitch core, data resident)
+    extra = {}
+    if not args.no_extra:
+        L = NCOMP - 1
+        key = torch.empty((L, 2, NCOMP, n), dtype=torch.int64, device="cuda")
+        for i in range(NCOMP):
+            key[:, :, i, :] = torch.randint(0, moduli[i], (L, 2, n), dtype=torch.int64, device="cuda", generator=g)
+        kh = ctx.kswitch_key(key)
+        ct3 = x0[:3, :L, :].contiguous()                # [3][L][N] "NTT-form" ciphertext after multiply
+        dest = ct3[:2].clone(); rot = torch.empty_like(dest)
+        gal = pow(3, 1, 2 * n)
+
+        def relin():
+            dest.copy_(ct3[:2])
+            ctx.keyswitch(ct3[2], L, True, kh, dest, b2.ASSIGN_ADD_INPLACE)
+
+        def rotate():
+            ctx.galois(ct3[:2], gal, rot, 2, L, True)
+            ctx.keyswitch(rot[1], L, True, kh, rot, b2.ASSIGN_OVERWRITE_EXCEPT_FIRST)
+        for name, fn in (("relinearize", relin), ("rotate", rotate)):
+            for _ in range(3):
+                fn()
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k = max(5, args.steps)
+            a0.record()
+            for _ in range(k):
+                fn()
+            a1.record(); barrier()
+            s = max_over_ranks(a0.elapsed_time(a1) * 1e-3)
+            extra[name + "_ops_per_s"] = world * k / s
+            extra[name + "_us"] = s / k * 1e6
+        extra["keyswitch_compulsory_bytes"] = 8 * n * (L + 2 * L * (L + 1) + 4 * L)
+        extra["keyswitch_hbm_frac"] = extra["keyswitch_compulsory_bytes"] / (extra["relinearize_us"] * 1e-6) / 1e9 / peak
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_ntt()
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u64 (40-bit limbs: exact FP64-pipe arithmetic; 60-bit limbs: integer pipe)", "data": "synthetic",
+                "config": {"workload": "C3 CKKS N=65536, q={60,40x19,60}: forward+inverse negacyclic NTT of a [20][21][N] operand (420 limbs, 210 MiB) per GPU per step",
+                           "l2": "inputs (210 MiB) larger than L2 (126 MB); no flush needed", "limbs_per_step_per_gpu": 2 * limbs,
+                           "sharding": "by ciphertext batch, no data-path collective"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+                "clocks": sampler.summary() if sampler else None, "extra": extra}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

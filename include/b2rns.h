@@ -63,6 +63,8 @@ typedef struct {
 const char *b2_last_error(void);
 const char *b2_version(void);
 int         b2_device_count(void);
+/* kernels launched by this library in this process so far (instrumentation for bench.py) */
+unsigned long long b2_launch_count(void);
 
 /* ---- context: replaces the device-resident tables of HeContext / ContextData
  *      (src/he_context.cu:46-145: NTTTables, RNSTool constants, GaloisTool tables) ---- */

@@ -1,0 +1,67 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref, host branch).
+
+Run in the build container only (needs /root/reference to build oracle/_ref):
+    python oracle/make_golden.py
+Each file pins, for one scheme at N=256 with CoeffModulus::create(256, {50,40,40,50}) and context seed 0x123:
+moduli, plain modulus, psi roots, relin + Galois keys, a fresh encryption of zero and the reference's outputs of
+multiply, square, relinearize, rotate(1), mod_switch/rescale_to_next (two levels), NTT / INTT in all three
+table-indexer modes, the Galois maps and multiply_plain — the raw uint64 words the reference produced.
+"""
+import os
+import sys
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import pyoracle as po
+
+N, LOGN, BITS = 256, 8, [50, 40, 40, 50]
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    for scheme, name in ((po.BFV, "bfv"), (po.CKKS, "ckks"), (po.BGV, "bgv")):
+        r = po.Reference(scheme, N, BITS, t_bits=20, seed=0x123)
+        K = r.nm; L = K - 1
+        rng = np.random.default_rng(1000 + scheme)
+        g = {"n": N, "scheme": scheme, "moduli": r.moduli, "t": np.uint64(r.t), "bits": np.array(BITS)}
+        roots = []
+        for i in range(K):
+            root, rp, irp = r.ntt_table(i, N)
+            roots.append(root); g["root_powers_%d" % i] = rp; g["inv_root_powers_%d" % i] = irp
+        g["roots"] = np.array(roots, dtype=np.uint64)
+        r.gen_relin(); gal = r.galois_element_from_step(1); r.gen_galois([gal, 2 * N - 1])
+        g["galois_elt"] = np.uint64(gal)
+        g["relin_key"] = r.relin_key(); g["galois_key"] = r.galois_key(gal); g["secret_key"] = r.secret_key()
+        ct = r.encrypt_zero(); g["ct"] = ct
+        ntt = scheme != po.BFV
+
+        def rnd(pc, nl):
+            out = np.empty((pc, nl, N), dtype=np.uint64)
+            for j in range(nl):
+                out[:, j, :] = rng.integers(0, int(r.moduli[j]), size=(pc, N), dtype=np.uint64)
+            return out.reshape(-1)
+        for lvl in (L, L - 1):
+            a, b, c3 = rnd(2, lvl), rnd(2, lvl), rnd(3, lvl)
+            t = "_l%d" % lvl
+            g["a" + t], g["b" + t], g["c3" + t] = a, b, c3
+            g["mul" + t] = r.multiply(a, b, lvl); g["square" + t] = r.square(a, lvl)
+            g["relin" + t] = r.relinearize(c3, lvl); g["rotate1" + t] = r.rotate(a, 1, lvl)
+            g["modswitch" + t] = r.mod_switch_scale_to_next(a, 2, lvl)
+            if scheme == po.CKKS:
+                g["drop" + t] = r.drop_to_next(a, 2, lvl)
+            g["galois_coeff" + t] = r.galois_raw(a, 2, lvl, gal, False); g["galois_ntt" + t] = r.galois_raw(a, 2, lvl, gal, True)
+            pl = rnd(1, lvl); g["plain" + t] = pl
+            g["mulplain_ntt" + t] = r.multiply_plain_raw(a, 2, pl, lvl, True) if ntt else r.multiply_plain_raw(r.transform_to_ntt(a, 2, lvl), 2, pl, lvl, True)
+            g["to_ntt" + t] = r.transform_to_ntt(a, 2, lvl); g["from_ntt" + t] = r.transform_from_ntt(a, 2, lvl)
+        x = rng.integers(0, 1 << 39, size=(L + 1) * L * N, dtype=np.uint64)
+        g["ks_set_in"] = x; g["ks_set_out"] = r.ntt_fwd(x, L + 1, L, 1, 0, L)
+        y = rng.integers(0, 1 << 39, size=2 * (L + 1) * N, dtype=np.uint64)
+        g["ks_skip_in"] = y; g["ks_skip_out"] = r.ntt_inv(y, 2, L + 1, 2, 0, L)
+        np.savez_compressed(os.path.join(OUT, "ref_%s_n256.npz" % name), **g)
+        print("wrote", name, {k: getattr(v, "shape", None) for k, v in list(g.items())[:4]})
+
+
+if __name__ == "__main__":
+    main()

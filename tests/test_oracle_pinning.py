@@ -1,0 +1,142 @@
+"""CPU tests that pin the oracle (oracle/rns_oracle.c):
+ (i)  the reference's own known-answer vectors (test/utils/ntt.cu:33-75, test/utils/uint_small_mod.cu:395-404,
+      :468-475, :680-690, test/utils/galois.cu:20-76),
+ (ii) golden vectors produced by the unmodified reference (tests/golden/, generator oracle/make_golden.py),
+ (iii) live comparison with oracle/_ref when it is built (this container), incl. the SURVEY §8c fingerprints.
+"""
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+# ---- (i) reference KATs -----------------------------------------------------------------------
+def test_kat_primitive_roots_and_small_ntt(po):
+    p = 0xFFFFFFFFFFC0001
+    o1 = po.Oracle(1, [p], 0, po.CKKS)
+    assert o1.root_powers(0)[0, 0] == 1 and o1.root_powers(0)[1, 0] == 288794978602139552
+    assert o1.root_powers(0, True)[1, 0] == po.lib().ro_invmod(288794978602139552, p)
+    o2 = po.Oracle(2, [p], 0, po.CKKS)
+    assert [int(v) for v in o2.root_powers(0)[:, 0]] == [1, 288794978602139552, 178930308976060547, 748001537669050592]
+    z = np.array([0, 0], dtype=np.uint64); assert list(o1.ntt_fwd(z, 1, 1)) == [0, 0]
+    assert list(o1.ntt_fwd(np.array([1, 0], dtype=np.uint64), 1, 1)) == [1, 1]
+    assert list(o1.ntt_fwd(np.array([1, 1], dtype=np.uint64), 1, 1)) == [288794978602139553, 864126526004445282]
+    o5 = po.Oracle(5, [p], 0, po.CKKS)
+    x = np.arange(32, dtype=np.uint64)
+    assert np.array_equal(o5.ntt_inv(o5.ntt_fwd(x, 1, 1), 1, 1), x)
+    assert not o5.ntt_inv(np.zeros(32, dtype=np.uint64), 1, 1).any()
+
+
+def test_kat_uint_small_mod(po):
+    L = po.lib()
+    m = 13131313131313
+    assert L.ro_barrett_reduce128(0, 0, m) == 0 and L.ro_barrett_reduce128(1, 0, m) == 1
+    assert L.ro_barrett_reduce128(123, 456, m) == 8722750765283
+    assert L.ro_barrett_reduce128(24242424242424, 79797979797979, m) == 1010101010101
+    q = 2305843009211596801
+    assert L.ro_mulmod(1152921504605798400, 1152921504605798401, q) == 576460752302899200
+    assert L.ro_mulmod(1152921504605798401, 1152921504605798401, q) == 1729382256908697601
+    assert L.ro_mulmod(2305843009211596800, 2305843009211596800, q) == 1
+    assert L.ro_mulmod(6, 7, 10) == 2
+    assert L.ro_powmod(2424242424, 16, 131313131313) == 39418477653
+    assert L.ro_powmod(2, 0xFFFFFFFFFFFFFFFF, 5) == 3
+    # Shoup multiply agrees with plain modmul on random operands (lazy range [0, 2p))
+    rng = np.random.default_rng(0)
+    for p in (q, 1099511480321, 1032193):
+        for _ in range(200):
+            x = int(rng.integers(0, 1 << 63)) * 2 + 1; w = int(rng.integers(0, p))
+            r = L.ro_shoup_mul_lazy(x, w, L.ro_shoup_quotient(w, p), p)
+            assert r < 2 * p and r % p == (x * w) % p
+            assert L.ro_barrett_reduce64(x, p) == x % p
+
+
+def test_kat_galois(po):
+    assert [po.lib().ro_galois_element_from_step(8, s) for s in (0, 1, -3, 2, -2, 3, -1)] == [15, 3, 3, 9, 9, 11, 11]
+    o = po.Oracle(3, [17], 0, po.CKKS)
+    x = np.arange(8, dtype=np.uint64)
+    assert list(o.galois(x, 3, 1, 1, False)) == [0, 14, 6, 1, 13, 7, 2, 12]
+    assert list(o.galois(x, 3, 1, 1, True)) == [4, 5, 7, 6, 1, 0, 2, 3]
+
+
+def test_prime_generation_matches_reference_defaults(po):
+    # CoeffModulus::bfv_default(32768) first / last primes (src/coeff_modulus.cu:53-56) are what get_primes finds
+    assert int(po.coeff_modulus_create(4096, [50, 40, 40, 50, 20])[4]) == 0xFC001
+    m = po.coeff_modulus_create(4096, [50, 40, 40, 50])
+    assert [hex(int(v)) for v in m] == ["0x3fffffffcc001", "0xfffffc6001", "0xfffffdc001", "0x3ffffffffc001"]
+
+
+# ---- (ii) golden vectors from the unmodified reference -----------------------------------------
+@pytest.mark.parametrize("name", ["bfv", "ckks", "bgv"])
+def test_oracle_reproduces_reference_golden(po, name):
+    g = np.load(os.path.join(GOLD, "ref_%s_n256.npz" % name))
+    n, scheme = int(g["n"]), int(g["scheme"])
+    moduli = po.coeff_modulus_create(n, [int(b) for b in g["bits"]])
+    assert np.array_equal(moduli, g["moduli"])
+    t = po.plain_modulus_batching(n, 20) if scheme != po.CKKS else 0
+    assert t == int(g["t"])
+    o = po.Oracle(8, moduli, t, scheme)
+    K = o.nm; L = K - 1
+    for i in range(K):
+        assert o.root(i) == int(g["roots"][i])
+        assert np.array_equal(o.root_powers(i), g["root_powers_%d" % i])
+        assert np.array_equal(o.root_powers(i, True), g["inv_root_powers_%d" % i])
+    gal = int(g["galois_elt"]); assert gal == o.galois_element_from_step(1)
+    ntt = scheme != po.BFV
+    for lvl in (L, L - 1):
+        s = "_l%d" % lvl
+        a, b, c3 = g["a" + s], g["b" + s], g["c3" + s]
+        sz = lvl * n
+        if ntt:
+            assert np.array_equal(o.dyadic_convolute(a, 2, b, 2, lvl), g["mul" + s])
+            assert np.array_equal(o.dyadic_square(a, lvl), g["square" + s])
+        assert np.array_equal(o.keyswitch(c3[2 * sz:], lvl, ntt, g["relin_key"], dest=c3[:2 * sz], assign=po.ASSIGN_ADD_INPLACE), g["relin" + s])
+        ga = o.galois(a, gal, 2, lvl, ntt)
+        assert np.array_equal(o.keyswitch(ga[sz:], lvl, ntt, g["galois_key"], dest=ga, assign=po.ASSIGN_OVERWRITE_EXCEPT_FIRST), g["rotate1" + s])
+        fn = {po.BFV: o.divide_round_q_last, po.CKKS: o.divide_round_q_last_ntt, po.BGV: o.mod_t_divide_q_last_ntt}[scheme]
+        assert np.array_equal(fn(a, 2, lvl), g["modswitch" + s])
+        if scheme == po.CKKS:
+            assert np.array_equal(o.drop_last_limb(a, 2, lvl), g["drop" + s])
+        assert np.array_equal(o.galois(a, gal, 2, lvl, False), g["galois_coeff" + s])
+        assert np.array_equal(o.galois(a, gal, 2, lvl, True), g["galois_ntt" + s])
+        an = a if ntt else o.ntt_fwd(a, 2, lvl)
+        assert np.array_equal(o.dyadic_broadcast(an, g["plain" + s], 2, lvl), g["mulplain_ntt" + s])
+        assert np.array_equal(o.ntt_fwd(a, 2, lvl), g["to_ntt" + s]) and np.array_equal(o.ntt_inv(a, 2, lvl), g["from_ntt" + s])
+    assert np.array_equal(o.ntt_fwd(g["ks_set_in"], L + 1, L, po.TABLES_KS_SET_PRODUCTS, 0, L), g["ks_set_out"])
+    assert np.array_equal(o.ntt_inv(g["ks_skip_in"], 2, L + 1, po.TABLES_KS_SKIP_FINALS, 0, L), g["ks_skip_out"])
+    # the reference's own ciphertext decrypts to ~0 under its own secret key with the oracle's arithmetic
+    ph = o.phase(g["secret_key"], g["ct"], 2, L, ntt)
+    q0 = int(moduli[0]); c = ph[:n].astype(object) % q0
+    if scheme == po.BGV:      # BGV noise is t*e
+        pass
+    else:
+        assert max(min(int(v), q0 - int(v)) for v in c) < 2 ** 16
+
+
+# ---- (iii) live against the compiled reference --------------------------------------------------
+SURVEY_FPR = {2: ("3866d51961505bd9", "c59ae60bda39e030", "a0e0a04249a08cd3", "4a186e8776597c7e", "eb819b8149c577a2"),
+              3: ("82ff3df13af52835", "2046b27467209ab9", "a967cf538de6dc20", "def3d7ec042efe31", "e11839bb23d6a573"),
+              1: ("6f35b18b9c970541", "18a28bad21f66e14", "e677dc9a95a7f003", "437f3e313696d5a6", "e670adc1a8c7459c")}
+
+
+@pytest.mark.parametrize("scheme", [2, 3, 1])
+def test_live_reference_fingerprints_and_oracle_parity(po, scheme):
+    if not po.ref_available():
+        pytest.skip("oracle/_ref not built (needs /root/reference; run __graft_entry__.build())")
+    n = 4096
+    r = po.Reference(scheme, n, [50, 40, 40, 50], t_bits=20, seed=0x123)
+    r.gen_relin(); gal = r.galois_element_from_step(1); r.gen_galois([gal])
+    L = r.nm - 1
+    c = r.encrypt_zero(); m = r.multiply(c, c, L); rl = r.relinearize(m, L); ro = r.rotate(rl, 1, L); ms = r.mod_switch_scale_to_next(rl, 2, L)
+    assert tuple("%016x" % po.fnv1a64(x) for x in (c, m, rl, ro, ms)) == SURVEY_FPR[scheme]
+    o = po.Oracle(12, r.moduli, r.t, scheme)
+    ntt = scheme != po.BFV
+    sz = L * n
+    assert np.array_equal(o.keyswitch(m[2 * sz:], L, ntt, r.relin_key(), dest=m[:2 * sz], assign=po.ASSIGN_ADD_INPLACE), rl)
+    ga = o.galois(rl, gal, 2, L, ntt)
+    assert np.array_equal(o.keyswitch(ga[sz:], L, ntt, r.galois_key(gal), dest=ga, assign=po.ASSIGN_OVERWRITE_EXCEPT_FIRST), ro)
+    fn = {po.BFV: o.divide_round_q_last, po.CKKS: o.divide_round_q_last_ntt, po.BGV: o.mod_t_divide_q_last_ntt}[scheme]
+    assert np.array_equal(fn(rl, 2, L), ms)
+    if ntt:
+        assert np.array_equal(o.dyadic_convolute(c, 2, c, 2, L), m)

@@ -40,6 +40,7 @@ _SIGS = {
     "b2_last_error": (C.c_char_p, []),
     "b2_version": (C.c_char_p, []),
     "b2_device_count": (C.c_int, []),
+    "b2_launch_count": (C.c_ulonglong, []),
     "b2_ctx_destroy": (None, [vp]),
     "b2_coeff_modulus_create": (C.c_int, [C.c_size_t, C.POINTER(C.c_uint32), C.c_size_t, u64p]),
     "b2_ctx_root": (C.c_int, [vp, C.c_size_t, u64p]),
@@ -101,6 +102,10 @@ def exported_symbols():
 def _chk(st):
     if st != 0:
         raise B2Error(st, lib().b2_last_error().decode())
+
+
+def launch_count():
+    return int(lib().b2_launch_count())
 
 
 def coeff_modulus_create(n, bits):

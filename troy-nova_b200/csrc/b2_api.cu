@@ -5,7 +5,10 @@
 #include "b2_ctx.h"
 #include "b2_host_math.h"
 
+#include <atomic>
 namespace b2 {
+static std::atomic<unsigned long long> g_launches{0};
+void count_launches(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 static thread_local char g_err[512] = "";
 void set_error(const char *fmt, ...) {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
@@ -37,6 +40,7 @@ extern "C" {
 
 const char *b2_last_error(void) { return b2::g_err; }
 const char *b2_version(void) { return "b2rns 0.1 (sm_100a)"; }
+unsigned long long b2_launch_count(void) { return b2::g_launches.load(); }
 int b2_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }

@@ -31,6 +31,8 @@ struct b2_ctx {
 };
 
 namespace b2 {
+// number of kernels this library launched in this process (bench.py reports it as gpu_launches)
+void count_launches(unsigned n);
 void set_error(const char *fmt, ...);
 b2_status cuda_fail(cudaError_t e, const char *what);
 b2_status ensure_ws(b2_ctx *ctx, size_t bytes);

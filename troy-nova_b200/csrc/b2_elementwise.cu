@@ -158,6 +158,7 @@ static b2_status ew_addsub(int op, b2_ctx *ctx, const uint64_t *a, const uint64_
     if (op == 0) ew_addsub_kernel<0><<<grid, 256, 0, stream>>>((const ulonglong2 *)a, (const ulonglong2 *)b, (ulonglong2 *)out, ctx->d_mods, S);
     if (op == 1) ew_addsub_kernel<1><<<grid, 256, 0, stream>>>((const ulonglong2 *)a, (const ulonglong2 *)b, (ulonglong2 *)out, ctx->d_mods, S);
     if (op == 2) ew_addsub_kernel<2><<<grid, 256, 0, stream>>>((const ulonglong2 *)a, nullptr, (ulonglong2 *)out, ctx->d_mods, S);
+    count_launches(1);
     B2_CUDA(cudaGetLastError());
     return B2_OK;
 }
@@ -170,6 +171,7 @@ b2_status b2_dyadic_convolute(b2_ctx *ctx, const uint64_t *a, size_t na, const u
     if (batch * ncomp == 0) return B2_OK;
     const u64 total = (u64)batch * ncomp * (n / 2);
     ew_convolute_kernel<<<ew_grid(total), 256, 0, stream>>>((const ulonglong2 *)a, (u32)na, (const ulonglong2 *)b, (u32)nb, (ulonglong2 *)out, ctx->d_mods, (u32)ncomp, (u32)(n / 2), (u32)batch);
+    count_launches(1);
     B2_CUDA(cudaGetLastError());
     return B2_OK;
 }
@@ -178,6 +180,7 @@ b2_status b2_dyadic_square(b2_ctx *ctx, const uint64_t *a, uint64_t *out, size_t
     if (batch * ncomp == 0) return B2_OK;
     const u64 total = (u64)batch * ncomp * (n / 2);
     ew_square_kernel<<<ew_grid(total), 256, 0, stream>>>((const ulonglong2 *)a, (ulonglong2 *)out, ctx->d_mods, (u32)ncomp, (u32)(n / 2), (u32)batch);
+    count_launches(1);
     B2_CUDA(cudaGetLastError());
     return B2_OK;
 }
@@ -187,6 +190,7 @@ b2_status b2_dyadic_broadcast(b2_ctx *ctx, const uint64_t *a, const uint64_t *pl
     EwShape S{(u32)ncomp, (u32)(n / 2), 0u, (u64)pcount * ncomp * (n / 2)};
     if (accumulate) ew_broadcast_kernel<true><<<ew_grid(S.total2), 256, 0, stream>>>((const ulonglong2 *)a, (const ulonglong2 *)plain, (ulonglong2 *)out, ctx->d_mods, S);
     else ew_broadcast_kernel<false><<<ew_grid(S.total2), 256, 0, stream>>>((const ulonglong2 *)a, (const ulonglong2 *)plain, (ulonglong2 *)out, ctx->d_mods, S);
+    count_launches(1);
     B2_CUDA(cudaGetLastError());
     return B2_OK;
 }
@@ -195,6 +199,7 @@ b2_status b2_negacyclic_shift(b2_ctx *ctx, const uint64_t *a, size_t shift, uint
     if (count * ncomp == 0) return B2_OK;
     const u64 total = (u64)count * ncomp * n;
     ew_negacyclic_shift_kernel<<<ew_grid(total), 256, 0, stream>>>((const u64 *)a, (u64 *)out, ctx->d_mods, (u32)ncomp, (u32)n, (u32)table_base, total, (u32)shift);
+    count_launches(1);
     B2_CUDA(cudaGetLastError());
     return B2_OK;
 }
@@ -211,6 +216,7 @@ b2_status b2_galois(b2_ctx *ctx, const uint64_t *in, uint64_t galois_elt, uint64
         inv &= (u32)(2 * n - 1);
         ew_galois_coeff_kernel<<<ew_grid(total), 256, 0, stream>>>((const u64 *)in, (u64 *)out, ctx->d_mods, (u32)ncomp, ctx->logn, (u32)table_base, total, inv);
     }
+    count_launches(1);
     B2_CUDA(cudaGetLastError());
     return B2_OK;
 }

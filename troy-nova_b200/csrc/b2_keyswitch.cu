@@ -149,6 +149,7 @@ b2_status b2_keyswitch(b2_ctx *ctx, const uint64_t *target, size_t decomp, int i
     {
         dim3 grid((unsigned)((n / 2 + 255) / 256), (unsigned)R);
         ks_inner_product_kernel<<<grid, 256, 0, stream>>>(temp, (const u64 *const *)key->d_ptrs, prod, ctx->d_mods, (u32)decomp, (u32)K, (u32)n);
+        count_launches(1);
         B2_CUDA(cudaGetLastError());
     }
     // 4. u_k = INTT_P(prod[k][decomp])

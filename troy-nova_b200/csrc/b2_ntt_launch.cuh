@@ -106,6 +106,7 @@ static b2_status run_ntt(b2_ctx *ctx, bool forward, const std::vector<LimbGroup>
             dim3 grid(maxc, (unsigned)ng);
             if (forward) ntt_small_kernel<true><<<grid, threads, n * 8, stream>>>(P, ld, st);
             else ntt_small_kernel<false><<<grid, threads, n * 8, stream>>>(P, ld, st);
+            count_launches(1);
             B2_CUDA(cudaGetLastError());
             continue;
         }
@@ -132,6 +133,7 @@ static b2_status run_ntt(b2_ctx *ctx, bool forward, const std::vector<LimbGroup>
                 launch_inv_row(P, grid, stream, ld, PlainStore{mid});
                 B2_DISPATCH_A(A, launch_inv_col, P, grid, stream, PlainLoad{mid}, st);
             }
+            count_launches(2);
             B2_CUDA(cudaGetLastError());
         }
     }

@@ -52,12 +52,14 @@ extern "C" b2_status b2_mod_switch_to_next(b2_ctx *ctx, const uint64_t *in, uint
         B2_REQUIRE(n >= 2, "degree too small");
         const u64 total = (u64)count * (nl - 1) * (n / 2);
         drop_limb_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>((const ulonglong2 *)in, (ulonglong2 *)out, (u32)nl, (u32)(n / 2), (u32)count);
+        count_launches(1);
         B2_CUDA(cudaGetLastError());
         return B2_OK;
     }
     if (kind == B2_MODSWITCH_BFV) {
         const u64 total = (u64)count * n;
         divide_round_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>((const u64 *)in, (u64 *)out, ctx->d_mods, ctx->d_inv + last * K, (u32)nl, (u32)n, (u32)count);
+        count_launches(1);
         B2_CUDA(cudaGetLastError());
         return B2_OK;
     }
