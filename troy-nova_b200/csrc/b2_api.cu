@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include "b2_ctx.h"
 #include "b2_host_math.h"
 
@@ -32,6 +33,15 @@ b2_status ensure_stage(b2_ctx *ctx, size_t bytes) {
     if (ctx->stage) { B2_CUDA(cudaDeviceSynchronize()); B2_CUDA(cudaFree(ctx->stage)); ctx->stage = nullptr; ctx->stage_bytes = 0; }
     B2_CUDA(cudaMalloc(&ctx->stage, bytes));
     ctx->stage_bytes = bytes;
+    return B2_OK;
+}
+b2_status ensure_sync(b2_ctx *ctx, size_t limbs, cudaStream_t stream) {
+    if (ctx->d_sync && ctx->sync_limbs >= limbs) return B2_OK;
+    if (ctx->d_sync) { B2_CUDA(cudaDeviceSynchronize()); B2_CUDA(cudaFree(ctx->d_sync)); ctx->d_sync = nullptr; ctx->sync_limbs = 0; }
+    const size_t want = std::max<size_t>(limbs * 2, 4096);
+    B2_CUDA(cudaMalloc((void **)&ctx->d_sync, (want + 2) * sizeof(unsigned)));
+    B2_CUDA(cudaMemsetAsync(ctx->d_sync, 0, (want + 2) * sizeof(unsigned), stream));
+    ctx->sync_limbs = want;
     return B2_OK;
 }
 }  // namespace b2

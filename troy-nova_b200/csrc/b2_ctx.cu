@@ -20,8 +20,11 @@ extern "C" b2_status b2_ctx_create(int device, const b2_params *prm, b2_ctx **ou
     }
     B2_REQUIRE(device >= 0 && device < ndev, "device index out of range");
     B2_CUDA(cudaSetDevice(device));
+    int sms = 0;
+    B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
 
     b2_ctx *c = new b2_ctx();
+    c->sm_count = sms > 0 ? sms : 148;
     c->device = device; c->logn = prm->log_n; c->n = (size_t)1 << prm->log_n; c->K = prm->n_moduli;
     c->t = prm->plain_modulus; c->scheme = (int)prm->scheme;
     const size_t n = c->n, K = c->K; const unsigned logn = c->logn;
@@ -40,11 +43,11 @@ extern "C" b2_status b2_ctx_create(int device, const b2_params *prm, b2_ctx **ou
         Tw *T = &tw[i * n], *IT = &itw[i * n];
         // root_powers[bitrev(k)] = psi^k ; inv_root_powers[bitrev(k-1)+1] = psi^-k  (src/utils/ntt.cu:36-58)
         uint64_t pw = psi, ipw = ipsi;
-        T[0].x = 1; T[0].y = host::shoup_quotient(1, p); IT[0] = T[0];
+        T[0].x = 1; T[0].y = host::shoup_quotient(1, p); IT[n - 1] = T[0];
         for (size_t k = 1; k < n; k++) {
             size_t a = host::bitrev((uint32_t)k, logn), b = host::bitrev((uint32_t)(k - 1), logn) + 1;
             T[a].x = pw; T[a].y = host::shoup_quotient(pw, p);
-            IT[b].x = ipw; IT[b].y = host::shoup_quotient(ipw, p);
+            IT[b - 1].x = ipw; IT[b - 1].y = host::shoup_quotient(ipw, p);   // device table = inv_root_powers shifted down by one (16-byte aligned runs)
             pw = host::mulmod(pw, psi, p); ipw = host::mulmod(ipw, ipsi, p);
         }
         ModInfo &M = c->h_mods[i];
@@ -54,7 +57,7 @@ extern "C" b2_status b2_ctx_create(int device, const b2_params *prm, b2_ctx **ou
         M.r0 = (uint64_t)ratio; M.r1 = (uint64_t)(ratio >> 64); M.ratio = M.r1;
         const uint64_t inv_n = host::invmod(n % p, p);
         M.inv_n.x = inv_n; M.inv_n.y = host::shoup_quotient(inv_n, p);
-        const uint64_t last_w = n > 1 ? IT[n - 1].x : 1;    // twiddle of the last inverse layer
+        const uint64_t last_w = n > 1 ? IT[n - 2].x : 1;    // twiddle of the last inverse layer
         const uint64_t inw = host::mulmod(inv_n, last_w, p);
         M.inv_n_w.x = inw; M.inv_n_w.y = host::shoup_quotient(inw, p);
         const unsigned bits = host::bit_count(p);
@@ -108,6 +111,6 @@ extern "C" b2_status b2_ctx_create(int device, const b2_params *prm, b2_ctx **ou
 extern "C" void b2_ctx_destroy(b2_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaFree(c->d_tw); cudaFree(c->d_itw); cudaFree(c->d_twd); cudaFree(c->d_itwd); cudaFree(c->d_mods); cudaFree(c->d_inv); cudaFree(c->d_inv_mod_t); cudaFree(c->d_galois); cudaFree(c->ws); cudaFree(c->stage);
+    cudaFree(c->d_tw); cudaFree(c->d_itw); cudaFree(c->d_twd); cudaFree(c->d_itwd); cudaFree(c->d_mods); cudaFree(c->d_inv); cudaFree(c->d_inv_mod_t); cudaFree(c->d_galois); cudaFree(c->ws); cudaFree(c->stage); cudaFree(c->d_sync);
     delete c;
 }

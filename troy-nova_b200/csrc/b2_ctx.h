@@ -28,6 +28,9 @@ struct b2_ctx {
     void *ws = nullptr; size_t ws_bytes = 0;
     // host-buffer staging for the *_host entry points
     void *stage = nullptr; size_t stage_bytes = 0;
+    // persistent-NTT work queue + per-limb completion counters (zero between launches; the kernel resets them)
+    unsigned *d_sync = nullptr; size_t sync_limbs = 0;
+    int sm_count = 148;
 };
 
 namespace b2 {
@@ -37,6 +40,7 @@ void set_error(const char *fmt, ...);
 b2_status cuda_fail(cudaError_t e, const char *what);
 b2_status ensure_ws(b2_ctx *ctx, size_t bytes);
 b2_status ensure_stage(b2_ctx *ctx, size_t bytes);
+b2_status ensure_sync(b2_ctx *ctx, size_t limbs, cudaStream_t stream);
 #define B2_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return b2::cuda_fail(e__, #call); } while (0)
 #define B2_REQUIRE(cond, msg) do { if (!(cond)) { b2::set_error("%s: %s", __func__, msg); return B2_ERR_INVALID_ARG; } } while (0)
 

@@ -15,10 +15,10 @@ struct ModDownTerm {
     u32 last, n;     // last: index of the modulus being divided out (P for keyswitch, q_{nl-1} for rescale)
     int bgv;
     u64 t, t_ratio, t_r0, t_r1, pinv_t;
-    __device__ __forceinline__ u64 term(int j, int k, u32 x) const {
+    __device__ __forceinline__ u64 term(int j, int k, u32 x) const { return term_of(j, u[(u64)k * n + x]); }
+    __device__ __forceinline__ u64 term_of(int j, u64 uv) const {
         const ModInfo &Q = mods[j];
         const u64 q = Q.p, P = mods[last].p;
-        const u64 uv = u[(u64)k * n + x];
         if (!bgv) {
             const u64 half = P >> 1;
             u64 r = uv + half; r = r >= P ? r - P : r;
@@ -34,7 +34,8 @@ struct ModDownTerm {
 };
 struct ModDownLoad {      // NTT-form path: the transform's input IS the term
     ModDownTerm T;
-    __device__ __forceinline__ u64 operator()(int g, int c, u64, u32 x) const { return T.term(g, c, x); }
+    __device__ __forceinline__ const u64 *src(int, int c, u64) const { return T.u + (u64)c * T.n; }
+    __device__ __forceinline__ u64 xf(int g, int, u32, u64 raw) const { return T.term_of(g, raw); }
 };
 // final store: out = (s - t) * P^-1 mod q_j ; then Overwrite / AddInplace / OverwriteExceptFirst
 struct ModDownStore {
@@ -54,6 +55,7 @@ struct ModDownStore {
         const bool add = assign == B2_ASSIGN_ADD_INPLACE || (k == 0 && assign == B2_ASSIGN_OVERWRITE_EXCEPT_FIRST);
         *d = add ? addmod(*d, r, q) : r;
     }
+    __device__ __forceinline__ void st2(int j, int k, u64 off, u32 x, u64 v0, u64 v1) const { (*this)(j, k, off, x, v0); (*this)(j, k, off, x + 1, v1); }
 };
 
 // rescale / modswitch final store: out[p][i] = (in[p][i] - t) * q_last^-1 mod q_i
@@ -69,10 +71,12 @@ struct RescaleStore {
         const u64 s = in[((u64)p * nl + i) * n + x];
         out[((u64)p * (nl - 1) + i) * n + x] = shoup(submod(s, t, q), inv[i], q);
     }
+    __device__ __forceinline__ void st2(int i, int p, u64 off, u32 x, u64 t0, u64 t1) const { (*this)(i, p, off, x, t0); (*this)(i, p, off, x + 1, t1); }
 };
 struct LastLimbLoad {     // the limb being divided out, for its inverse transform
     const u64 *in; u32 nl, n;
-    __device__ __forceinline__ u64 operator()(int, int p, u64, u32 x) const { return in[((u64)p * nl + nl - 1) * n + x]; }
+    __device__ __forceinline__ const u64 *src(int, int p, u64) const { return in + ((u64)p * nl + nl - 1) * n; }
+    __device__ __forceinline__ u64 xf(int, int, u32, u64 raw) const { return raw; }
 };
 
 }  // namespace b2

@@ -33,9 +33,9 @@ struct ModUpLoad {
     const u64 *tc;        // [decomp][N] coefficient form
     const ModInfo *mods;
     u32 decomp, K, n;
-    __device__ __forceinline__ u64 operator()(int g, int c, u64, u32 x) const {
+    __device__ __forceinline__ const u64 *src(int, int c, u64) const { return tc + (u64)c * n; }
+    __device__ __forceinline__ u64 xf(int g, int c, u32, u64 v) const {
         const u32 ki = (u32)g == decomp ? K - 1 : (u32)g;
-        const u64 v = tc[(u64)c * n + x];
         const u64 m = mods[ki].p;
         // q_j <= m_i: already canonical modulo m_i
         return (mods[c].p <= m) ? v : barrett64(v, m, mods[ki].ratio);
@@ -77,11 +77,13 @@ __global__ void __launch_bounds__(256) ks_inner_product_kernel(const u64 *__rest
 
 struct SpecialLoad {      // step 4: the special-prime limb of prod[k]
     const u64 *prod; u32 R, decomp, n;
-    __device__ __forceinline__ u64 operator()(int, int k, u64, u32 x) const { return prod[((u64)k * R + decomp) * n + x]; }
+    __device__ __forceinline__ const u64 *src(int, int k, u64) const { return prod + ((u64)k * R + decomp) * n; }
+    __device__ __forceinline__ u64 xf(int, int, u32, u64 raw) const { return raw; }
 };
 struct ProdLoad {         // coefficient-form path: transform prod[k][j] itself (inverse NTT)
     const u64 *prod; u32 decomp, n;
-    __device__ __forceinline__ u64 operator()(int j, int k, u64, u32 x) const { return prod[((u64)k * (decomp + 1) + j) * n + x]; }
+    __device__ __forceinline__ const u64 *src(int j, int k, u64) const { return prod + ((u64)k * (decomp + 1) + j) * n; }
+    __device__ __forceinline__ u64 xf(int, int, u32, u64 raw) const { return raw; }
 };
 
 }  // namespace b2
@@ -116,6 +118,7 @@ void b2_kswitch_key_destroy(b2_kswitch_key *k) {
 b2_status b2_keyswitch(b2_ctx *ctx, const uint64_t *target, size_t decomp, int is_ntt, const b2_kswitch_key *key,
                        uint64_t *dest, int assign, void *stream_) {
     B2_REQUIRE(ctx && target && key && dest, "null argument");
+    B2_REQUIRE((((uintptr_t)target | (uintptr_t)dest) & 15) == 0, "operands must be 16-byte aligned");
     B2_REQUIRE(decomp >= 1 && decomp + 1 <= ctx->K, "decomp must be in [1, K-1] (keyswitching needs a special prime)");
     B2_REQUIRE(key->digits >= decomp, "keyswitching key has fewer digits than the ciphertext has limbs");
     B2_REQUIRE(assign >= 0 && assign <= 2, "unknown assign method");

@@ -21,6 +21,7 @@ b2_status ntt_launch(b2_ctx *ctx, bool forward, const uint64_t *in, uint64_t *ou
     b2_status st = check_ntt_args(ctx, batch, pcount, ncomp, mode, table_base, decomp);
     if (st != B2_OK) return st;
     B2_REQUIRE(in && out, "null data pointer");
+    B2_REQUIRE((((uintptr_t)in | (uintptr_t)out) & 15) == 0, "operands must be 16-byte aligned");
     B2_CUDA(cudaSetDevice(ctx->device));
     const size_t n = ctx->n, K = ctx->K;
     std::vector<LimbGroup> groups;

@@ -8,21 +8,27 @@
 //   * N = 2^logN is viewed as a (2^A rows) x (256 columns) matrix, A = logN - 8.  The forward
 //     transform is a COLUMN pass (layers 0..A-1, strides >= 256) followed by a ROW pass (layers
 //     A..logN-1 inside contiguous 2 KiB rows); the inverse runs the two passes in the opposite
-//     order.  Each pass moves a 4096-coefficient tile (32 KiB) per CTA: 16 columns x 2^A rows
-//     (128-byte row segments) or 16 whole rows.
+//     order.  Each pass works on 4096-coefficient tiles (32 KiB): 2^(12-A) columns x 2^A rows
+//     (128-byte row segments when N = 2^16) or 16 whole rows.
+//   * ONE persistent launch per transform call (ntt_persistent_kernel): 2 CTAs per SM pull (pass,
+//     limb, tile) items from an in-order work queue.  The second-pass items of limb l are queued
+//     `lag` limbs behind its first-pass items and wait on a per-limb completion counter, so the
+//     intermediate of a limb (512 KiB at N = 2^16) is still in L2 when the second pass reads it:
+//     HBM sees one read and one write per coefficient, there are no per-wave launches and no tails.
+//   * Tiles are staged into shared memory with 16-byte cp.async (LDGSTS) copies, double buffered: the
+//     copy of item i+1 is in flight while item i is computed, so no warp waits on a global load.
+//     The stage uses a 16-byte-granular XOR swizzle, the exchange buffer an 8-byte-granular one; every
+//     access pattern of every round is bank-conflict free.
 //   * Inside a pass every thread keeps 16 coefficients in registers and performs a radix-16
-//     (four-layer) butterfly network on them; the tile is re-distributed between radix-16 rounds
-//     through XOR-swizzled shared memory (conflict-free for every round's access pattern).  An
-//     8-layer pass therefore touches shared memory once and global memory once in / once out.
+//     (four-layer) butterfly network on them; an 8-layer pass touches the exchange buffer once.
 //   * Two arithmetic back ends (b2_modarith.cuh): ArithF64 — exact double-double modular multiply on
 //     the FP64 pipe for p < 2^41, signed lazy values, 8 DP instructions per butterfly; ArithInt —
 //     Harvey/Shoup lazy butterflies on the integer pipe for larger p, with no per-layer correction
 //     at all when the modulus leaves enough headroom (ModInfo::fwd_lazy / inv_lazy).
-//   * N^-1 is folded into the last inverse layer's twiddles (no extra pass).
-//   * Limbs that share a modulus are processed by the same CTA back to back ("limb groups"), so
-//     the twiddles of a tile are fetched once per group chunk and then hit in L1.
+//   * N^-1 is folded into the last inverse layer's twiddles (no extra pass).  Twiddles of one
+//     butterfly layer are contiguous per thread and fetched with 16-byte loads.
 //   * Loads and stores go through functors so callers can fuse a prologue / epilogue into the
-//     transform (keyswitch mod-up, key inner product, rescale, mod-down: b2_keyswitch.cu).
+//     transform (keyswitch mod-up, rescale, mod-down: b2_keyswitch.cu, b2_rescale.cu).
 #pragma once
 #include "b2_modarith.cuh"
 
@@ -42,12 +48,18 @@ struct LimbGroup {
     u64 stride;
 };
 
-struct NttLaunch {
+// One transform call = one persistent launch over n_groups * count limbs.
+struct NttJob {
     const ModInfo *mods;
+    u64 *mid;           // raw intermediate between the two passes; groups[].base/stride address it
+    u32 *sync;          // [0] work-queue head, [1] finished CTAs, [2 + l] first-pass tiles of limb l completed
     int logn;
-    int chunk;        // limbs of one group handled by one CTA
-    int c_begin, c_end;   // absolute limb-index range of this launch (L2 wave)
-    int g_base;           // index of groups[0] in the caller's group list (functors see absolute indices)
+    u32 count;          // limbs per group (equal for all groups of a call)
+    u32 n_limbs;        // n_groups * count
+    u32 lag;            // second-pass items trail first-pass items by this many limbs (<= n_limbs)
+    u32 tile_shift;     // log2(tiles per limb) = logN - 12
+    u32 total_items;    // 2 * n_limbs * tiles
+    int g_base;         // index of groups[0] in the caller's group list (functors see absolute indices)
     int n_groups;
     LimbGroup groups[NTT_MAX_GROUPS];
 };
@@ -56,6 +68,10 @@ struct NttLaunch {
 // swz(a | b) == swz(a) ^ swz(b) for disjoint a, b: per-register offsets are compile-time constants.
 // For every round's access pattern a half-warp lands on 16 distinct 8-byte slots.
 __host__ __device__ constexpr int swz(int idx) { return idx ^ ((idx >> 4) & 15); }
+// Stage-buffer swizzle: 16-byte granular (cp.async writes whole 16-byte chunks): chunk index within a
+// 128-byte row XOR the low three bits of the row index.  Also GF(2)-linear.
+__host__ __device__ constexpr int swz16(int idx) { return idx ^ (((idx >> 4) & 7) << 1); }
+constexpr int NTT_SMEM_BYTES = 3 * NTT_TILE * 8;   // two stage buffers + one exchange buffer = 96 KiB (2 CTAs per SM)
 
 // tile-local index of register 0 of thread t in a round whose 4-bit window starts at bit LO
 template <int LO>
@@ -74,7 +90,11 @@ struct ArithInt {
     __device__ __forceinline__ T from_ext(u64 x) const { return x; }
     __device__ __forceinline__ T from_raw(u64 x) const { return x; }
     __device__ __forceinline__ u64 to_raw(T v) const { return v; }
-    __device__ __forceinline__ TwT ldtw(const TwT *t, u32 i) const { return __ldg(t + i); }
+    // cnt is a compile-time constant after unrolling at every call site
+    __device__ __forceinline__ void ldtw_n(const TwT *t, u32 i, int cnt, TwT (&w)[8]) const {
+#pragma unroll
+        for (int a = 0; a < 8; a++) if (a < cnt) w[a] = __ldg(t + i + a);
+    }
     __device__ __forceinline__ void bf_fwd(T &X, T &Y, TwT w) const {
         u64 x = LAZY ? X : csub(X, p2);
         u64 t = shoup_lazy(Y, w, p);
@@ -108,7 +128,16 @@ struct ArithF64 {
     __device__ __forceinline__ T from_ext(u64 x) const { return u64_to_dd(x); }
     __device__ __forceinline__ T from_raw(u64 x) const { return __longlong_as_double((long long)x); }
     __device__ __forceinline__ u64 to_raw(T v) const { return (u64)__double_as_longlong(v); }
-    __device__ __forceinline__ TwT ldtw(const TwT *t, u32 i) const { return __ldg(t + i); }
+    // CNT consecutive table entries starting at an index that is a multiple of CNT: 16-byte loads
+    // (cnt is a compile-time constant after unrolling at every call site)
+    __device__ __forceinline__ void ldtw_n(const TwT *t, u32 i, int cnt, TwT (&w)[8]) const {
+        if (cnt == 1) { w[0] = __ldg(t + i); return; }
+#pragma unroll
+        for (int a = 0; a < 4; a++) if (2 * a < cnt) {
+            const double2 d = __ldg(reinterpret_cast<const double2 *>(t + i) + a);
+            w[2 * a] = d.x; w[2 * a + 1] = d.y;
+        }
+    }
     __device__ __forceinline__ void bf_fwd(T &X, T &Y, TwT w) const {
         double t = mulmod_dd(Y, w, p, pinv);
         Y = X - t;
@@ -141,8 +170,7 @@ __device__ __forceinline__ void fwd_round(const AR &ar, typename AR::T (&v)[16],
         const int l = logn - 1 - (XLO + j);
         const u32 tb = (1u << l) + (xt >> (XLO + j + 1));
         typename AR::TwT w[8];
-#pragma unroll
-        for (int i = 0; i < (16 >> (j + 1)); i++) w[i] = ar.ldtw(ar.ftab, tb + i);
+        ar.ldtw_n(ar.ftab, tb, 16 >> (j + 1), w);
 #pragma unroll
         for (int k = 0; k < 16; k++) {
             if (k & (1 << j)) continue;
@@ -167,10 +195,9 @@ __device__ __forceinline__ void inv_round(const AR &ar, typename AR::T (&v)[16],
                 ar.bf_inv_last(v[k], v[k | (1 << j)], l);
             }
         } else {
-            const u32 tb = n - (n >> l) + 1 + (xt >> (l + 1));
+            const u32 tb = n - (n >> l) + (xt >> (l + 1));     // device table = inv_root_powers shifted down by one
             typename AR::TwT w[8];
-#pragma unroll
-            for (int i = 0; i < (16 >> (j + 1)); i++) w[i] = ar.ldtw(ar.itab, tb + i);
+            ar.ldtw_n(ar.itab, tb, 16 >> (j + 1), w);
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 if (k & (1 << j)) continue;
@@ -180,15 +207,24 @@ __device__ __forceinline__ void inv_round(const AR &ar, typename AR::T (&v)[16],
     }
 }
 
-// ---- default load / store functors ------------------------------------------------------------
-// ld(group, limb_in_group, element offset of the limb, x) -> external (integer) coefficient at position x
+// ---- load / store functors -------------------------------------------------------------------------
+// A LOAD functor names, for limb c of group g, where the limb's N source words live (src) and an
+// element-wise transform applied when the staged word is read into registers (xf).  `off` is the limb's
+// element offset in the intermediate buffer (LimbGroup base + c * stride); plain transforms use it for
+// the operand as well.  Sources must be 16-byte aligned (cp.async).
 struct PlainLoad {
     const u64 *base;
-    __device__ __forceinline__ u64 operator()(int, int, u64 off, u32 x) const { return base[off + x]; }
+    __device__ __forceinline__ const u64 *src(int, int, u64 off) const { return base + off; }
+    __device__ __forceinline__ u64 xf(int, int, u32, u64 raw) const { return raw; }
 };
+// A STORE functor receives canonical results: st(g, c, off, x, v) one word, st2 two adjacent words
+// (x even).  The default st2 is two st calls.
 struct PlainStore {
     u64 *base;
     __device__ __forceinline__ void operator()(int, int, u64 off, u32 x, u64 v) const { base[off + x] = v; }
+    __device__ __forceinline__ void st2(int, int, u64 off, u32 x, u64 v0, u64 v1) const {
+        *reinterpret_cast<ulonglong2 *>(base + off + x) = make_ulonglong2(v0, v1);
+    }
 };
 
 // Tile geometry.  COL: tile = 2^A rows x 2^(12-A) columns of the 2^A x 256 matrix, local index =
@@ -203,12 +239,35 @@ struct Geo {
     static constexpr int xbit(int b) { return COL ? (b >= CB ? b + 8 - CB : b) : b; }
 };
 
-// One pass = one to three radix-16 rounds over a tile.  (LOr, NLr) per round; NLr == 0: round absent.
-//   FIRST: the pass reads external data (ld -> from_ext); otherwise it reads the raw intermediate
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ u32 ld_acquire(const u32 *p) {
+    u32 v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Stage one tile of a limb (N contiguous words at `limb`) into `stage`: 2048 16-byte chunks, 8 per thread.
+template <int A, bool COL>
+__device__ __forceinline__ void stage_tile(u64 *stage, const u64 *limb, int tile) {
+    using G = Geo<A, COL>;
+#pragma unroll
+    for (int m = 0; m < 8; m++) {
+        const int idx = 2 * ((int)threadIdx.x + NTT_THREADS * m);
+        cp_async16(stage + swz16(idx), limb + G::pos(tile, idx));
+    }
+}
+
+// One pass = one to three radix-16 rounds over a staged tile.  (LOr, NLr) per round; NLr == 0: round absent.
+//   FIRST: the pass reads external data (xf -> from_ext); otherwise it reads the raw intermediate
 //   FINAL: the pass writes canonical results; otherwise it writes the raw intermediate
 template <int A, bool COL, bool FWD, bool FIRST, bool FINAL, class AR, int LO0, int NL0, int LO1, int NL1, int LO2, int NL2,
           class Load, class Store>
-__device__ __forceinline__ void pass_body(u64 *sm, const ModInfo &M, int tile, int g, int c, u64 off, int logn,
+__device__ __forceinline__ void pass_body(const u64 *stage, u64 *sm, const ModInfo &M, int tile, int g, int c, u64 off, int logn,
                                           const Load &ld, const Store &st) {
     using G = Geo<A, COL>;
     typedef typename AR::T T;
@@ -219,20 +278,30 @@ __device__ __forceinline__ void pass_body(u64 *sm, const ModInfo &M, int tile, i
     constexpr int LOL = NR == 3 ? LO2 : (NR == 2 ? LO1 : LO0);
     constexpr bool LASTL = FINAL && !FWD;    // the pass contains the last inverse layer
 
-    {   // ---- round 0: from global memory
+    {   // ---- round 0: from the stage buffer
         const int it = round_base<LO0>(t);
         const u32 xt = G::pos(tile, it);
+        const int sb = swz16(it);
+        u64 raw[16];
+        if (LO0 == 0) {
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            u64 raw = ld(g, c, off, xt + ((u32)k << G::xbit(LO0)));
-            v[k] = FIRST ? ar.from_ext(raw) : ar.from_raw(raw);
+            for (int k = 0; k < 16; k += 2) {
+                const ulonglong2 d = *reinterpret_cast<const ulonglong2 *>(stage + (sb ^ k));
+                raw[k] = d.x; raw[k + 1] = d.y;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; k++) raw[k] = stage[sb ^ swz16(k << LO0)];
         }
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            v[k] = FIRST ? ar.from_ext(ld.xf(g, c, xt + ((u32)k << G::xbit(LO0)), raw[k])) : ar.from_raw(raw[k]);
         if (FWD) fwd_round<NL0, G::xbit(LO0)>(ar, v, xt, logn);
         else inv_round<NL0, G::xbit(LO0), LASTL && NR == 1>(ar, v, xt, logn);
         if (NR > 1) {
-            const int sb = swz(it);
+            const int xb = swz(it);
 #pragma unroll
-            for (int k = 0; k < 16; k++) sm[sb ^ swz(k << LO0)] = ar.to_raw(v[k]);
+            for (int k = 0; k < 16; k++) sm[xb ^ swz(k << LO0)] = ar.to_raw(v[k]);
         }
     }
     if (NR > 1) {   // ---- round 1
@@ -244,7 +313,7 @@ __device__ __forceinline__ void pass_body(u64 *sm, const ModInfo &M, int tile, i
         for (int k = 0; k < 16; k++) v[k] = ar.from_raw(sm[sb ^ swz(k << LO1)]);
         if (FWD) fwd_round<(NL1 > 0 ? NL1 : 1), G::xbit(LO1)>(ar, v, xt, logn);
         else inv_round<(NL1 > 0 ? NL1 : 1), G::xbit(LO1), LASTL && NR == 2>(ar, v, xt, logn);
-        if (NR > 2) {
+        if (NR > 2) {     // each thread overwrites exactly the slots it has just read
 #pragma unroll
             for (int k = 0; k < 16; k++) sm[sb ^ swz(k << LO1)] = ar.to_raw(v[k]);
         }
@@ -262,40 +331,22 @@ __device__ __forceinline__ void pass_body(u64 *sm, const ModInfo &M, int tile, i
     {   // ---- to global memory
         const int it = round_base<LOL>(t);
         const u32 xt = G::pos(tile, it);
+        u64 o[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) {
-            u64 o;
-            if (FINAL) o = FWD ? ar.final_fwd(v[k]) : ar.final_inv(v[k]);
+            if (FINAL) o[k] = FWD ? ar.final_fwd(v[k]) : ar.final_inv(v[k]);
             else {
                 if (!FWD) ar.pass_boundary_inv(v[k]);
-                o = ar.to_raw(v[k]);
+                o[k] = ar.to_raw(v[k]);
             }
-            st(g, c, off, xt + ((u32)k << G::xbit(LOL)), o);
         }
-    }
-}
-
-template <int A, bool COL, bool FWD, bool FIRST, bool FINAL, int LO0, int NL0, int LO1, int NL1, int LO2, int NL2, class Load,
-          class Store>
-__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const __grid_constant__ NttLaunch P, Load ld, Store st) {
-    __shared__ __align__(16) u64 sm[NTT_TILE];
-    const LimbGroup &grp = P.groups[blockIdx.y];
-    const int c0 = P.c_begin + blockIdx.z * P.chunk;
-    const int cend = min((int)grp.count, P.c_end);
-    if (c0 >= cend) return;
-    const int c1 = min(cend, c0 + P.chunk);
-    const ModInfo &M = P.mods[grp.table];
-    const int path = M.use_f64 ? 2 : ((FWD ? M.fwd_lazy : M.inv_lazy) ? 1 : 0);
-    constexpr bool MULTI = NL1 > 0;
-    for (int c = c0; c < c1; c++) {
-        const u64 off = grp.base + (u64)c * grp.stride;
-        if (path == 2)
-            pass_body<A, COL, FWD, FIRST, FINAL, ArithF64, LO0, NL0, LO1, NL1, LO2, NL2>(sm, M, blockIdx.x, P.g_base + blockIdx.y, c, off, P.logn, ld, st);
-        else if (path == 1)
-            pass_body<A, COL, FWD, FIRST, FINAL, ArithInt<true>, LO0, NL0, LO1, NL1, LO2, NL2>(sm, M, blockIdx.x, P.g_base + blockIdx.y, c, off, P.logn, ld, st);
-        else
-            pass_body<A, COL, FWD, FIRST, FINAL, ArithInt<false>, LO0, NL0, LO1, NL1, LO2, NL2>(sm, M, blockIdx.x, P.g_base + blockIdx.y, c, off, P.logn, ld, st);
-        if (MULTI && c + 1 < c1) __syncthreads();
+        if (G::xbit(LOL) == 0) {     // 16 adjacent words per thread: 16-byte stores
+#pragma unroll
+            for (int k = 0; k < 16; k += 2) st.st2(g, c, off, xt + (u32)k, o[k], o[k + 1]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; k++) st(g, c, off, xt + ((u32)k << G::xbit(LOL)), o[k]);
+        }
     }
 }
 
@@ -314,5 +365,148 @@ template <int A> struct InvColPlan {
     static constexpr int LO1 = (A >= 8) ? CB + 4 : 8, NL1 = (A >= 8) ? 4 : A - 4;
     static constexpr int LO2 = 8, NL2 = (A > 8) ? A - 8 : 0;
 };
+
+// ---- work items ----------------------------------------------------------------------------------------
+// Item order (TP = tiles per limb, D = lag, NL = limbs):  P1(0..D-1) | [P1(D+b), P2(b)] for b < NL-D | P2(NL-D..NL-1)
+// where Px(l) stands for the TP tiles of pass x of limb l.  Every P2(l) item comes after all P1(l) items.
+struct NttItem { u32 phase, limb, tile; };
+__device__ __forceinline__ NttItem ntt_decode(const NttJob &J, u32 item) {
+    const u32 ts = J.tile_shift, tm = (1u << ts) - 1, D = J.lag;
+    NttItem r;
+    if (item < (D << ts)) { r.phase = 0; r.limb = item >> ts; r.tile = item & tm; return r; }
+    u32 rem = item - (D << ts);
+    const u32 mid_items = (J.n_limbs - D) << (ts + 1);
+    if (rem < mid_items) {
+        const u32 b = rem >> (ts + 1), w = rem & ((2u << ts) - 1);
+        r.phase = w >> ts; r.tile = w & tm; r.limb = r.phase ? b : D + b;
+        return r;
+    }
+    rem -= mid_items;
+    r.phase = 1; r.limb = J.n_limbs - D + (rem >> ts); r.tile = rem & tm;
+    return r;
+}
+
+template <int A, bool COL, bool FWD, bool FIRST, bool FINAL, int LO0, int NL0, int LO1, int NL1, int LO2, int NL2, class Load, class Store>
+__device__ __forceinline__ void pass_dispatch(const u64 *stage, u64 *xch, const ModInfo &M, int tile, int g, int c, u64 off, int logn,
+                                              const Load &ld, const Store &st) {
+    const int path = M.use_f64 ? 2 : ((FWD ? M.fwd_lazy : M.inv_lazy) ? 1 : 0);
+    if (path == 2)
+        pass_body<A, COL, FWD, FIRST, FINAL, ArithF64, LO0, NL0, LO1, NL1, LO2, NL2>(stage, xch, M, tile, g, c, off, logn, ld, st);
+    else if (path == 1)
+        pass_body<A, COL, FWD, FIRST, FINAL, ArithInt<true>, LO0, NL0, LO1, NL1, LO2, NL2>(stage, xch, M, tile, g, c, off, logn, ld, st);
+    else
+        pass_body<A, COL, FWD, FIRST, FINAL, ArithInt<false>, LO0, NL0, LO1, NL1, LO2, NL2>(stage, xch, M, tile, g, c, off, logn, ld, st);
+}
+
+// The persistent transform kernel.  FWD: first pass = column pass (reads the operand through `ld`), second
+// pass = row pass (writes through `st`); inverse: first pass = row pass, second pass = column pass.
+template <int A, bool FWD, class Load, class Store>
+__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_persistent_kernel(const __grid_constant__ NttJob J, Load ld, Store st) {
+    extern __shared__ __align__(128) u64 smem[];
+    __shared__ u32 s_item, s_ready;
+    u64 *const xch = smem + 2 * NTT_TILE;
+    const int t = threadIdx.x;
+    const u32 total = J.total_items, tiles = 1u << J.tile_shift;
+    u32 *const queue = J.sync, *const finished = J.sync + 1, *const done = J.sync + 2;
+    const PlainLoad mid_ld{J.mid};
+    const PlainStore mid_st{J.mid};
+
+    auto stage_item = [&](const NttItem &it, u64 *stage) {
+        const u32 g = it.limb / J.count, c = it.limb - g * J.count;
+        const LimbGroup &grp = J.groups[g];
+        const u64 off = grp.base + (u64)c * grp.stride;
+        if (it.phase == 0) {
+            const u64 *src = ld.src(J.g_base + (int)g, (int)c, off);
+            stage_tile<A, FWD>(stage, src, (int)it.tile);          // forward: column tile; inverse: row tile
+        } else {
+            stage_tile<A, !FWD>(stage, J.mid + off, (int)it.tile);
+        }
+        cp_async_commit();
+    };
+    auto compute_item = [&](const NttItem &it, const u64 *stage) {
+        const u32 g = it.limb / J.count, c = it.limb - g * J.count;
+        const LimbGroup &grp = J.groups[g];
+        const u64 off = grp.base + (u64)c * grp.stride;
+        const ModInfo &M = J.mods[grp.table];
+        const int ga = J.g_base + (int)g;
+        if (FWD) {
+            using Pl = FwdColPlan<A>;
+            if (it.phase == 0)
+                pass_dispatch<A, true, true, true, false, Pl::LO0, Pl::NL0, Pl::LO1, Pl::NL1, Pl::LO2, Pl::NL2>(stage, xch, M, (int)it.tile, ga, (int)c, off, J.logn, ld, mid_st);
+            else
+                pass_dispatch<8, false, true, false, true, 4, 4, 0, 4, 0, 0>(stage, xch, M, (int)it.tile, ga, (int)c, off, J.logn, mid_ld, st);
+        } else {
+            using Pl = InvColPlan<A>;
+            if (it.phase == 0)
+                pass_dispatch<8, false, false, true, false, 0, 4, 4, 4, 0, 0>(stage, xch, M, (int)it.tile, ga, (int)c, off, J.logn, ld, mid_st);
+            else
+                pass_dispatch<A, true, false, false, true, Pl::LO0, Pl::NL0, Pl::LO1, Pl::NL1, Pl::LO2, Pl::NL2>(stage, xch, M, (int)it.tile, ga, (int)c, off, J.logn, mid_ld, st);
+        }
+    };
+
+    // ---- prologue: claim the first item and stage it (blocking on its dependency)
+    if (t == 0) {
+        const u32 i0 = atomicAdd(queue, 1u);
+        s_item = i0;
+        if (i0 < total) {
+            const NttItem it = ntt_decode(J, i0);
+            if (it.phase) while (ld_acquire(done + it.limb) < tiles) __nanosleep(100);
+        }
+    }
+    __syncthreads();
+    u32 cur_id = s_item;
+    if (cur_id < total) {
+        NttItem cur = ntt_decode(J, cur_id);
+        int buf = 0;
+        stage_item(cur, smem);
+        bool publish = false; u32 publish_limb = 0;       // a finished first-pass item whose completion is not yet signalled
+        while (true) {
+            __syncthreads();          // previous item's stores and exchange reads are complete CTA-wide
+            if (t == 0) {
+                if (publish) { __threadfence(); atomicAdd(done + publish_limb, 1u); }
+                const u32 nx = atomicAdd(queue, 1u);
+                u32 ready = 0;
+                if (nx < total) {
+                    const NttItem ni = ntt_decode(J, nx);
+                    ready = (ni.phase == 0 || ld_acquire(done + ni.limb) >= tiles) ? 1u : 0u;
+                }
+                s_item = nx; s_ready = ready;
+            }
+            cp_async_wait_all();
+            __syncthreads();          // stage[buf] complete and visible; next item known
+            const u32 nxt_id = s_item;
+            const bool pre = s_ready != 0;
+            NttItem nxt = cur;
+            if (nxt_id < total) nxt = ntt_decode(J, nxt_id);
+            if (pre) stage_item(nxt, smem + (buf ^ 1) * NTT_TILE);
+            compute_item(cur, smem + buf * NTT_TILE);
+            publish = cur.phase == 0; publish_limb = cur.limb;
+            if (nxt_id >= total) break;
+            if (!pre) {               // dependency not met at prefetch time: signal our own completion, then wait
+                __syncthreads();
+                if (t == 0) {
+                    if (publish) { __threadfence(); atomicAdd(done + publish_limb, 1u); }
+                    while (ld_acquire(done + nxt.limb) < tiles) __nanosleep(100);
+                }
+                publish = false;
+                __syncthreads();
+                stage_item(nxt, smem + (buf ^ 1) * NTT_TILE);
+            }
+            cur = nxt; buf ^= 1;
+        }
+        __syncthreads();
+        if (t == 0 && publish) { __threadfence(); atomicAdd(done + publish_limb, 1u); }
+    }
+    // ---- teardown: the last CTA to finish resets the queue and the counters for the next launch
+    if (t == 0) {
+        __threadfence();
+        s_ready = (atomicAdd(finished, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_ready) {
+        for (u32 i = t; i < J.n_limbs; i += NTT_THREADS) done[i] = 0;
+        if (t == 0) { *queue = 0; *finished = 0; }
+    }
+}
 
 }  // namespace b2

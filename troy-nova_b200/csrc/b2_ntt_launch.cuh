@@ -1,4 +1,4 @@
-// b2_ntt_launch.cuh — host-side launcher template for the two-pass NTT with fused load / store functors.
+// b2_ntt_launch.cuh — host-side launcher template for the persistent NTT with fused load / store functors.
 // Included by every translation unit that launches a transform (b2_ntt.cu, b2_keyswitch.cu, b2_rescale.cu).
 #pragma once
 #include <algorithm>
@@ -10,17 +10,19 @@ namespace b2 {
 
 // ---- tiny transforms (N <= 2048): one CTA per limb, everything in shared memory -----------------
 template <bool FWD, class Load, class Store>
-__global__ void ntt_small_kernel(const __grid_constant__ NttLaunch P, Load ld, Store st) {
+__global__ void ntt_small_kernel(const __grid_constant__ NttJob P, Load ld, Store st) {
     extern __shared__ u64 sm[];
     const LimbGroup &grp = P.groups[blockIdx.y];
-    const int c = P.c_begin + blockIdx.x;
+    const int c = blockIdx.x;
     if (c >= (int)grp.count) return;
     const ModInfo M = P.mods[grp.table];
     const u64 off = grp.base + (u64)c * grp.stride;
     const int logn = P.logn, n = 1 << logn, half = n >> 1;
+    const int g = P.g_base + (int)blockIdx.y;
     const u64 p = M.p, p2 = p << 1;
     const ArithInt<false> ar(M);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) sm[i] = ld(P.g_base + (int)blockIdx.y, c, off, (u32)i);
+    const u64 *src = ld.src(g, c, off);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sm[i] = ld.xf(g, c, (u32)i, src[i]);
     __syncthreads();
     for (int layer = 0; layer < logn; layer++) {
         for (int i = threadIdx.x; i < half; i += blockDim.x) {
@@ -39,7 +41,7 @@ __global__ void ntt_small_kernel(const __grid_constant__ NttLaunch P, Load ld, S
                     ar.bf_inv_last(U, V, layer);
                     sm[xi] = U; sm[xi + gap] = V;
                 } else {
-                    Tw w = M.itw[n - (n >> layer) + 1 + (i >> gp)];
+                    Tw w = M.itw[n - (n >> layer) + (i >> gp)];
                     ar.bf_inv(U, V, w, layer);
                     sm[xi] = U; sm[xi + gap] = V;
                 }
@@ -47,63 +49,47 @@ __global__ void ntt_small_kernel(const __grid_constant__ NttLaunch P, Load ld, S
         }
         __syncthreads();
     }
-    for (int i = threadIdx.x; i < n; i += blockDim.x) st(P.g_base + (int)blockIdx.y, c, off, (u32)i, FWD ? csub(csub(sm[i], p2), p) : sm[i]);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) st(g, c, off, (u32)i, FWD ? csub(csub(sm[i], p2), p) : sm[i]);
 }
 
-// ---- pass dispatch ---------------------------------------------------------------------------------
-template <int A, class Load, class Store>
-static void launch_fwd_col(const NttLaunch &P, dim3 grid, cudaStream_t s, Load ld, Store st) {
-    using Pl = FwdColPlan<A>;
-    ntt_pass_kernel<A, true, true, true, false, Pl::LO0, Pl::NL0, Pl::LO1, Pl::NL1, Pl::LO2, Pl::NL2><<<grid, NTT_THREADS, 0, s>>>(P, ld, st);
-}
-template <int A, class Load, class Store>
-static void launch_inv_col(const NttLaunch &P, dim3 grid, cudaStream_t s, Load ld, Store st) {
-    using Pl = InvColPlan<A>;
-    ntt_pass_kernel<A, true, false, false, true, Pl::LO0, Pl::NL0, Pl::LO1, Pl::NL1, Pl::LO2, Pl::NL2><<<grid, NTT_THREADS, 0, s>>>(P, ld, st);
-}
-template <class Load, class Store>
-static void launch_fwd_row(const NttLaunch &P, dim3 grid, cudaStream_t s, Load ld, Store st) {
-    ntt_pass_kernel<8, false, true, false, true, 4, 4, 0, 4, 0, 0><<<grid, NTT_THREADS, 0, s>>>(P, ld, st);
-}
-template <class Load, class Store>
-static void launch_inv_row(const NttLaunch &P, dim3 grid, cudaStream_t s, Load ld, Store st) {
-    ntt_pass_kernel<8, false, false, true, false, 0, 4, 4, 4, 0, 0><<<grid, NTT_THREADS, 0, s>>>(P, ld, st);
-}
+// second-pass items trail first-pass items by this many limbs: at N = 2^16 the in-flight intermediate is
+// NTT_LAG x 512 KiB = 16 MiB, far inside the 126 MB L2, and ~600 items (2 per resident CTA) are ~19 limbs.
+static constexpr u32 NTT_LAG = 32;
 
-#define B2_DISPATCH_A(A_, FN, ...)                                     \
-    switch (A_) {                                                      \
-    case 4: FN<4>(__VA_ARGS__); break;                                 \
-    case 5: FN<5>(__VA_ARGS__); break;                                 \
-    case 6: FN<6>(__VA_ARGS__); break;                                 \
-    case 7: FN<7>(__VA_ARGS__); break;                                 \
-    case 8: FN<8>(__VA_ARGS__); break;                                 \
-    default: FN<9>(__VA_ARGS__); break;                                \
+template <int A, bool FWD, class Load, class Store>
+static cudaError_t launch_persistent(const NttJob &J, unsigned grid, cudaStream_t s, Load ld, Store st) {
+    static bool configured = false;     // per instantiation; the attribute is per function and device-independent here
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(ntt_persistent_kernel<A, FWD, Load, Store>, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
     }
-
-// L2 budget for the intermediate between the two passes: limbs are processed in waves small
-// enough that pass 2 finds pass 1's output still resident in the 126 MB L2.
-static constexpr size_t L2_WAVE_BYTES = 40u << 20;
+    ntt_persistent_kernel<A, FWD, Load, Store><<<grid, NTT_THREADS, NTT_SMEM_BYTES, s>>>(J, ld, st);
+    return cudaGetLastError();
+}
 
 // groups' base/stride address the intermediate buffer `mid` (raw values between the passes); the
-// functors map (group, limb, x) to wherever the external operands live.
+// functors map (group, limb) to wherever the external operands live.  All groups must have the same count.
 template <class Load, class Store>
 static b2_status run_ntt(b2_ctx *ctx, bool forward, const std::vector<LimbGroup> &groups, u64 *mid, Load ld, Store st,
                          cudaStream_t stream) {
     const unsigned logn = ctx->logn;
     const size_t n = ctx->n;
-    NttLaunch P;
+    if (groups.empty() || groups[0].count == 0) return B2_OK;
+    NttJob P;
     P.mods = ctx->d_mods;
+    P.mid = mid;
     P.logn = (int)logn;
+    P.count = groups[0].count;
+    for (const LimbGroup &g : groups) B2_REQUIRE(g.count == P.count, "internal: limb groups of one transform must have equal counts");
     for (size_t g0 = 0; g0 < groups.size(); g0 += NTT_MAX_GROUPS) {
         const size_t ng = std::min(groups.size() - g0, (size_t)NTT_MAX_GROUPS);
-        u32 maxc = 0;
         P.g_base = (int)g0;
-        for (size_t g = 0; g < ng; g++) maxc = std::max(maxc, groups[g0 + g].count);
+        P.n_groups = (int)ng;
+        for (size_t g = 0; g < ng; g++) P.groups[g] = groups[g0 + g];
         if (logn <= 11) {
-            P.n_groups = (int)ng; P.chunk = 1; P.c_begin = 0; P.c_end = (int)maxc;
-            for (size_t g = 0; g < ng; g++) P.groups[g] = groups[g0 + g];
             const int threads = (int)std::max<size_t>(32, std::min<size_t>(n / 2, 1024));
-            dim3 grid(maxc, (unsigned)ng);
+            dim3 grid(P.count, (unsigned)ng);
             if (forward) ntt_small_kernel<true><<<grid, threads, n * 8, stream>>>(P, ld, st);
             else ntt_small_kernel<false><<<grid, threads, n * 8, stream>>>(P, ld, st);
             count_launches(1);
@@ -111,34 +97,38 @@ static b2_status run_ntt(b2_ctx *ctx, bool forward, const std::vector<LimbGroup>
             continue;
         }
         const int A = (int)logn - 8;
-        const unsigned tiles = 1u << (A - 4);
-        // wave over the limb index so that ng * wave * N * 8 bytes stay L2-resident between passes
-        size_t wave = std::max<size_t>(1, L2_WAVE_BYTES / (ng * n * 8));
-        for (u32 cs = 0; cs < maxc; cs += (u32)wave) {
-            const u32 ce = (u32)std::min<size_t>(maxc, (size_t)cs + wave);
-            const u32 wmax = ce - cs;
-            for (size_t g = 0; g < ng; g++) P.groups[g] = groups[g0 + g];
-            P.c_begin = (int)cs; P.c_end = (int)ce;
-            P.n_groups = (int)ng;
-            // enough CTAs to fill the machine a few times over, but keep limbs of a modulus together
-            const size_t want_ctas = 148 * 8;
-            size_t chunk = std::max<size_t>(1, ((size_t)tiles * ng * wmax) / want_ctas);
-            chunk = std::min<size_t>(chunk, 8);
-            P.chunk = (int)chunk;
-            dim3 grid(tiles, (unsigned)ng, (unsigned)((wmax + chunk - 1) / chunk));
-            if (forward) {
-                B2_DISPATCH_A(A, launch_fwd_col, P, grid, stream, ld, PlainStore{mid});
-                launch_fwd_row(P, grid, stream, PlainLoad{mid}, st);
-            } else {
-                launch_inv_row(P, grid, stream, ld, PlainStore{mid});
-                B2_DISPATCH_A(A, launch_inv_col, P, grid, stream, PlainLoad{mid}, st);
+        P.tile_shift = logn - NTT_TB;
+        P.n_limbs = (u32)(ng * P.count);
+        P.lag = std::min<u32>(NTT_LAG, P.n_limbs);
+        P.total_items = (P.n_limbs << P.tile_shift) * 2;
+        b2_status s = ensure_sync(ctx, P.n_limbs, stream);
+        if (s != B2_OK) return s;
+        P.sync = ctx->d_sync;
+        const unsigned grid = std::min<unsigned>(P.total_items, 2u * (unsigned)ctx->sm_count);
+        cudaError_t e;
+        if (forward) {
+            switch (A) {
+            case 4: e = launch_persistent<4, true>(P, grid, stream, ld, st); break;
+            case 5: e = launch_persistent<5, true>(P, grid, stream, ld, st); break;
+            case 6: e = launch_persistent<6, true>(P, grid, stream, ld, st); break;
+            case 7: e = launch_persistent<7, true>(P, grid, stream, ld, st); break;
+            case 8: e = launch_persistent<8, true>(P, grid, stream, ld, st); break;
+            default: e = launch_persistent<9, true>(P, grid, stream, ld, st); break;
             }
-            count_launches(2);
-            B2_CUDA(cudaGetLastError());
+        } else {
+            switch (A) {
+            case 4: e = launch_persistent<4, false>(P, grid, stream, ld, st); break;
+            case 5: e = launch_persistent<5, false>(P, grid, stream, ld, st); break;
+            case 6: e = launch_persistent<6, false>(P, grid, stream, ld, st); break;
+            case 7: e = launch_persistent<7, false>(P, grid, stream, ld, st); break;
+            case 8: e = launch_persistent<8, false>(P, grid, stream, ld, st); break;
+            default: e = launch_persistent<9, false>(P, grid, stream, ld, st); break;
+            }
         }
+        count_launches(1);
+        B2_CUDA(e);
     }
     return B2_OK;
 }
-
 
 }  // namespace b2

@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(256) drop_limb_kernel(const ulonglong2 *__rest
 extern "C" b2_status b2_mod_switch_to_next(b2_ctx *ctx, const uint64_t *in, uint64_t *out, size_t count, size_t nl, int kind,
                                            void *stream_) {
     B2_REQUIRE(ctx && in && out, "null argument");
+    B2_REQUIRE((((uintptr_t)in | (uintptr_t)out) & 15) == 0, "operands must be 16-byte aligned");
     B2_REQUIRE(nl >= 2 && nl <= ctx->K, "need at least two limbs to drop one");
     B2_REQUIRE(kind >= 0 && kind <= 3, "unknown kind");
     if (count == 0) return B2_OK;
