@@ -12,7 +12,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb2rns.so")
+LIB_PATH = os.environ.get("B2RNS_LIB") or os.path.join(HERE, "libb2rns.so")   # B2RNS_LIB: developer override for A/B builds
 
 BFV, CKKS, BGV = 1, 2, 3
 ASSIGN_OVERWRITE, ASSIGN_ADD_INPLACE, ASSIGN_OVERWRITE_EXCEPT_FIRST = 0, 1, 2

@@ -45,17 +45,32 @@ struct ModDownStore {
     u64 *dest;            // [2][decomp][N]
     u32 decomp, assign;
     int t_from_transform; // 1: transformed value is t (NTT-form ciphertext); 0: transformed value is s, t computed here
+    __device__ __forceinline__ u64 one(int j, u64 q, u64 s, u64 v, u64 uv, u64 d, bool add) const {
+        u64 t;
+        if (t_from_transform) t = v;
+        else { s = v; t = csub(T.term_of(j, uv), q); }           // term < 2q -> canonical
+        const u64 r = shoup(submod(s, t, q), pinv[j], q);
+        return add ? addmod(d, r, q) : r;
+    }
     __device__ __forceinline__ void operator()(int j, int k, u64, u32 x, u64 v) const {
         const u64 q = T.mods[j].p, n = T.n;
-        u64 s, t;
-        if (t_from_transform) { s = prod[((u64)k * (decomp + 1) + j) * n + x]; t = v; }
-        else { s = v; t = T.term(j, k, x); t = csub(t, q); }     // term < 2q -> canonical
-        const u64 r = shoup(submod(s, t, q), pinv[j], q);
-        u64 *d = dest + ((u64)k * decomp + j) * n + x;
         const bool add = assign == B2_ASSIGN_ADD_INPLACE || (k == 0 && assign == B2_ASSIGN_OVERWRITE_EXCEPT_FIRST);
-        *d = add ? addmod(*d, r, q) : r;
+        u64 *d = dest + ((u64)k * decomp + j) * n + x;
+        const u64 s = t_from_transform ? prod[((u64)k * (decomp + 1) + j) * n + x] : 0;
+        const u64 uv = t_from_transform ? 0 : T.u[(u64)k * n + x];
+        *d = one(j, q, s, v, uv, add ? *d : 0, add);
     }
-    __device__ __forceinline__ void st2(int j, int k, u64 off, u32 x, u64 v0, u64 v1) const { (*this)(j, k, off, x, v0); (*this)(j, k, off, x + 1, v1); }
+    // two adjacent coefficients: 16-byte accesses to prod / u / dest
+    __device__ __forceinline__ void st2(int j, int k, u64, u32 x, u64 v0, u64 v1) const {
+        const u64 q = T.mods[j].p, n = T.n;
+        const bool add = assign == B2_ASSIGN_ADD_INPLACE || (k == 0 && assign == B2_ASSIGN_OVERWRITE_EXCEPT_FIRST);
+        ulonglong2 *d = reinterpret_cast<ulonglong2 *>(dest + ((u64)k * decomp + j) * n + x);
+        ulonglong2 s = make_ulonglong2(0, 0), uv = make_ulonglong2(0, 0), dv = make_ulonglong2(0, 0);
+        if (t_from_transform) s = *reinterpret_cast<const ulonglong2 *>(prod + ((u64)k * (decomp + 1) + j) * n + x);
+        else uv = *reinterpret_cast<const ulonglong2 *>(T.u + (u64)k * n + x);
+        if (add) dv = *d;
+        *d = make_ulonglong2(one(j, q, s.x, v0, uv.x, dv.x, add), one(j, q, s.y, v1, uv.y, dv.y, add));
+    }
 };
 
 // rescale / modswitch final store: out[p][i] = (in[p][i] - t) * q_last^-1 mod q_i
@@ -71,7 +86,12 @@ struct RescaleStore {
         const u64 s = in[((u64)p * nl + i) * n + x];
         out[((u64)p * (nl - 1) + i) * n + x] = shoup(submod(s, t, q), inv[i], q);
     }
-    __device__ __forceinline__ void st2(int i, int p, u64 off, u32 x, u64 t0, u64 t1) const { (*this)(i, p, off, x, t0); (*this)(i, p, off, x + 1, t1); }
+    __device__ __forceinline__ void st2(int i, int p, u64, u32 x, u64 t0, u64 t1) const {
+        const u64 q = mods[i].p;
+        const ulonglong2 s = *reinterpret_cast<const ulonglong2 *>(in + ((u64)p * nl + i) * n + x);
+        *reinterpret_cast<ulonglong2 *>(out + ((u64)p * (nl - 1) + i) * n + x) =
+            make_ulonglong2(shoup(submod(s.x, t0, q), inv[i], q), shoup(submod(s.y, t1, q), inv[i], q));
+    }
 };
 struct LastLimbLoad {     // the limb being divided out, for its inverse transform
     const u64 *in; u32 nl, n;

@@ -15,6 +15,8 @@
 //      (ski_util6 / ski_util5_step1) and its last-pass store computes (prod[k][j] - t)·P^-1 mod q_j and
 //      assigns / accumulates into the destination (ski_util7 / ski_util5_step2).
 //      For coefficient-form (BFV) ciphertexts the same happens around INTT(prod[k][j]).
+#include <cstdio>
+#include <cstdlib>
 #include "b2_ntt_launch.cuh"
 #include "b2_fused.cuh"
 
@@ -56,10 +58,10 @@ __global__ void __launch_bounds__(256) ks_inner_product_kernel(const u64 *__rest
     u64 a0l = 0, a0h = 0, a1l = 0, a1h = 0, b0l = 0, b0h = 0, b1l = 0, b1h = 0;
     const u64 *tp = temp + ((u64)i * decomp) * n + x;
     for (u32 j = 0; j < decomp; j++) {
-        const ulonglong2 d = *reinterpret_cast<const ulonglong2 *>(tp + (u64)j * n);
+        const ulonglong2 d = __ldcs(reinterpret_cast<const ulonglong2 *>(tp + (u64)j * n));   // streamed once: evict-first
         const u64 *kp = keys[j] + (u64)ki * n + x;
-        const ulonglong2 k0 = __ldg(reinterpret_cast<const ulonglong2 *>(kp));
-        const ulonglong2 k1 = __ldg(reinterpret_cast<const ulonglong2 *>(kp + (u64)K * n));
+        const ulonglong2 k0 = __ldcs(reinterpret_cast<const ulonglong2 *>(kp));
+        const ulonglong2 k1 = __ldcs(reinterpret_cast<const ulonglong2 *>(kp + (u64)K * n));
         mac128(a0l, a0h, d.x, k0.x); mac128(a1l, a1h, d.y, k0.y);
         mac128(b0l, b0h, d.x, k1.x); mac128(b1l, b1h, d.y, k1.y);
         if ((j & 7) == 7) {     // keep the lazy 128-bit sums below 2^125 (8 products of 61-bit residues)
@@ -133,6 +135,12 @@ b2_status b2_keyswitch(b2_ctx *ctx, const uint64_t *target, size_t decomp, int i
     if (st != B2_OK) return st;
     u64 *tc = (u64 *)ctx->ws, *temp = tc + w_tc, *prod = temp + w_temp, *u = prod + w_prod, *mid = u + w_u;
 
+    // developer aid: B2_KS_TIMING=1 prints per-stage device times (synchronises; never set in production)
+    static const bool timing = getenv("B2_KS_TIMING") != nullptr;
+    cudaEvent_t ev[6];
+    int nev = 0;
+    auto mark = [&]() { if (timing) { cudaEventCreate(&ev[nev]); cudaEventRecord(ev[nev], stream); nev++; } };
+    mark();
     // 1. coefficient form of the target
     const u64 *tcoef = (const u64 *)target;
     if (is_ntt) {
@@ -140,6 +148,7 @@ b2_status b2_keyswitch(b2_ctx *ctx, const uint64_t *target, size_t decomp, int i
         if (st != B2_OK) return st;
         tcoef = tc;
     }
+    mark();
     // 2. mod-up + NTT: group i = output modulus, limbs j = digits; results temp[i][j]
     {
         std::vector<LimbGroup> groups;
@@ -148,6 +157,7 @@ b2_status b2_keyswitch(b2_ctx *ctx, const uint64_t *target, size_t decomp, int i
         st = run_ntt(ctx, true, groups, temp, ld, PlainStore{temp}, stream);
         if (st != B2_OK) return st;
     }
+    mark();
     // 3. key inner product
     {
         dim3 grid((unsigned)((n / 2 + 255) / 256), (unsigned)R);
@@ -155,6 +165,7 @@ b2_status b2_keyswitch(b2_ctx *ctx, const uint64_t *target, size_t decomp, int i
         count_launches(1);
         B2_CUDA(cudaGetLastError());
     }
+    mark();
     // 4. u_k = INTT_P(prod[k][decomp])
     {
         std::vector<LimbGroup> groups{LimbGroup{(u32)(K - 1), 2u, 0, (u64)n}};
@@ -162,6 +173,7 @@ b2_status b2_keyswitch(b2_ctx *ctx, const uint64_t *target, size_t decomp, int i
         st = run_ntt(ctx, false, groups, u, ld, PlainStore{u}, stream);
         if (st != B2_OK) return st;
     }
+    mark();
     // 5. mod-down fused around one transform of [2][decomp] limbs (group j = modulus, limb k = poly)
     {
         std::vector<LimbGroup> groups;
@@ -172,6 +184,16 @@ b2_status b2_keyswitch(b2_ctx *ctx, const uint64_t *target, size_t decomp, int i
         if (is_ntt) st = run_ntt(ctx, true, groups, mid, ModDownLoad{T}, sst, stream);
         else st = run_ntt(ctx, false, groups, mid, ProdLoad{prod, (u32)decomp, (u32)n}, sst, stream);
         if (st != B2_OK) return st;
+    }
+    mark();
+    if (timing) {
+        cudaEventSynchronize(ev[nev - 1]);
+        static const char *names[] = {"intt(target)", "modup+ntt", "inner product", "intt(special)", "moddown+ntt"};
+        float tot = 0; cudaEventElapsedTime(&tot, ev[0], ev[nev - 1]);
+        fprintf(stderr, "[b2 keyswitch] total %.1f us:", tot * 1e3f);
+        for (int i = 0; i + 1 < nev; i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); fprintf(stderr, " %s %.1f", names[i], ms * 1e3f); }
+        fprintf(stderr, "\n");
+        for (int i = 0; i < nev; i++) cudaEventDestroy(ev[i]);
     }
     return B2_OK;
 }

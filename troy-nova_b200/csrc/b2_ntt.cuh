@@ -10,13 +10,14 @@
 //     A..logN-1 inside contiguous 2 KiB rows); the inverse runs the two passes in the opposite
 //     order.  Each pass works on 4096-coefficient tiles (32 KiB): 2^(12-A) columns x 2^A rows
 //     (128-byte row segments when N = 2^16) or 16 whole rows.
-//   * ONE persistent launch per transform call (ntt_persistent_kernel): 2 CTAs per SM pull (pass,
+//   * ONE persistent launch per transform call (ntt_persistent_kernel): 3 CTAs per SM pull (pass,
 //     limb, tile) items from an in-order work queue.  The second-pass items of limb l are queued
 //     `lag` limbs behind its first-pass items and wait on a per-limb completion counter, so the
 //     intermediate of a limb (512 KiB at N = 2^16) is still in L2 when the second pass reads it:
 //     HBM sees one read and one write per coefficient, there are no per-wave launches and no tails.
-//   * Tiles are staged into shared memory with 16-byte cp.async (LDGSTS) copies, double buffered: the
-//     copy of item i+1 is in flight while item i is computed, so no warp waits on a global load.
+//   * Tiles are staged into shared memory with 16-byte cp.async (LDGSTS) copies: as soon as every thread has
+//     pulled item i out of the stage buffer (the pass's first barrier) the copy of item i+1 is issued and is in
+//     flight while item i is computed; 3 CTAs per SM (64 KiB shared memory, <= 80 registers) cover the rest.
 //     The stage uses a 16-byte-granular XOR swizzle, the exchange buffer an 8-byte-granular one; every
 //     access pattern of every round is bank-conflict free.
 //   * Inside a pass every thread keeps 16 coefficients in registers and performs a radix-16
@@ -71,7 +72,7 @@ __host__ __device__ constexpr int swz(int idx) { return idx ^ ((idx >> 4) & 15);
 // Stage-buffer swizzle: 16-byte granular (cp.async writes whole 16-byte chunks): chunk index within a
 // 128-byte row XOR the low three bits of the row index.  Also GF(2)-linear.
 __host__ __device__ constexpr int swz16(int idx) { return idx ^ (((idx >> 4) & 7) << 1); }
-constexpr int NTT_SMEM_BYTES = 3 * NTT_TILE * 8;   // two stage buffers + one exchange buffer = 96 KiB (2 CTAs per SM)
+constexpr int NTT_SMEM_BYTES = 2 * NTT_TILE * 8;   // one stage buffer + one exchange buffer = 64 KiB (3 CTAs per SM)
 
 // tile-local index of register 0 of thread t in a round whose 4-bit window starts at bit LO
 template <int LO>
@@ -266,9 +267,9 @@ __device__ __forceinline__ void stage_tile(u64 *stage, const u64 *limb, int tile
 //   FIRST: the pass reads external data (xf -> from_ext); otherwise it reads the raw intermediate
 //   FINAL: the pass writes canonical results; otherwise it writes the raw intermediate
 template <int A, bool COL, bool FWD, bool FIRST, bool FINAL, class AR, int LO0, int NL0, int LO1, int NL1, int LO2, int NL2,
-          class Load, class Store>
+          class Load, class Store, class Hook>
 __device__ __forceinline__ void pass_body(const u64 *stage, u64 *sm, const ModInfo &M, int tile, int g, int c, u64 off, int logn,
-                                          const Load &ld, const Store &st) {
+                                          const Load &ld, const Store &st, const Hook &stage_free) {
     using G = Geo<A, COL>;
     typedef typename AR::T T;
     const AR ar(M);
@@ -304,8 +305,9 @@ __device__ __forceinline__ void pass_body(const u64 *stage, u64 *sm, const ModIn
             for (int k = 0; k < 16; k++) sm[xb ^ swz(k << LO0)] = ar.to_raw(v[k]);
         }
     }
+    __syncthreads();   // every thread has consumed the stage buffer (and, for NR > 1, written the exchange buffer)
+    stage_free();      // -> the next item's tile is staged while this one is computed
     if (NR > 1) {   // ---- round 1
-        __syncthreads();
         const int it = round_base<LO1>(t);
         const u32 xt = G::pos(tile, it);
         const int sb = swz(it);
@@ -386,33 +388,36 @@ __device__ __forceinline__ NttItem ntt_decode(const NttJob &J, u32 item) {
     return r;
 }
 
-template <int A, bool COL, bool FWD, bool FIRST, bool FINAL, int LO0, int NL0, int LO1, int NL1, int LO2, int NL2, class Load, class Store>
+template <int A, bool COL, bool FWD, bool FIRST, bool FINAL, int LO0, int NL0, int LO1, int NL1, int LO2, int NL2, class Load, class Store, class Hook>
 __device__ __forceinline__ void pass_dispatch(const u64 *stage, u64 *xch, const ModInfo &M, int tile, int g, int c, u64 off, int logn,
-                                              const Load &ld, const Store &st) {
+                                              const Load &ld, const Store &st, const Hook &hk) {
     const int path = M.use_f64 ? 2 : ((FWD ? M.fwd_lazy : M.inv_lazy) ? 1 : 0);
     if (path == 2)
-        pass_body<A, COL, FWD, FIRST, FINAL, ArithF64, LO0, NL0, LO1, NL1, LO2, NL2>(stage, xch, M, tile, g, c, off, logn, ld, st);
+        pass_body<A, COL, FWD, FIRST, FINAL, ArithF64, LO0, NL0, LO1, NL1, LO2, NL2>(stage, xch, M, tile, g, c, off, logn, ld, st, hk);
     else if (path == 1)
-        pass_body<A, COL, FWD, FIRST, FINAL, ArithInt<true>, LO0, NL0, LO1, NL1, LO2, NL2>(stage, xch, M, tile, g, c, off, logn, ld, st);
+        pass_body<A, COL, FWD, FIRST, FINAL, ArithInt<true>, LO0, NL0, LO1, NL1, LO2, NL2>(stage, xch, M, tile, g, c, off, logn, ld, st, hk);
     else
-        pass_body<A, COL, FWD, FIRST, FINAL, ArithInt<false>, LO0, NL0, LO1, NL1, LO2, NL2>(stage, xch, M, tile, g, c, off, logn, ld, st);
+        pass_body<A, COL, FWD, FIRST, FINAL, ArithInt<false>, LO0, NL0, LO1, NL1, LO2, NL2>(stage, xch, M, tile, g, c, off, logn, ld, st, hk);
 }
 
 // The persistent transform kernel.  FWD: first pass = column pass (reads the operand through `ld`), second
 // pass = row pass (writes through `st`); inverse: first pass = row pass, second pass = column pass.
-template <int A, bool FWD, class Load, class Store>
-__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_persistent_kernel(const __grid_constant__ NttJob J, Load ld, Store st) {
+// OCC = resident CTAs per SM the register allocation is held to.
+template <int A, bool FWD, int OCC, class Load, class Store>
+__global__ void __launch_bounds__(NTT_THREADS, OCC) ntt_persistent_kernel(const __grid_constant__ NttJob J, Load ld, Store st) {
     extern __shared__ __align__(128) u64 smem[];
     __shared__ u32 s_item, s_ready;
-    u64 *const xch = smem + 2 * NTT_TILE;
+    u64 *const stage = smem, *const xch = smem + NTT_TILE;
     const int t = threadIdx.x;
     const u32 total = J.total_items, tiles = 1u << J.tile_shift;
     u32 *const queue = J.sync, *const finished = J.sync + 1, *const done = J.sync + 2;
     const PlainLoad mid_ld{J.mid};
     const PlainStore mid_st{J.mid};
 
-    auto stage_item = [&](const NttItem &it, u64 *stage) {
-        const u32 g = it.limb / J.count, c = it.limb - g * J.count;
+    // limb l -> (group, limb in group): consecutive limbs cycle through the groups, so CTAs working on FP64-pipe
+    // moduli and on integer-pipe moduli are resident on an SM at the same time and the two pipes overlap
+    auto stage_item = [&](const NttItem &it) {
+        const u32 c = it.limb / (u32)J.n_groups, g = it.limb - c * (u32)J.n_groups;
         const LimbGroup &grp = J.groups[g];
         const u64 off = grp.base + (u64)c * grp.stride;
         if (it.phase == 0) {
@@ -423,8 +428,8 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_persistent_kernel(const __
         }
         cp_async_commit();
     };
-    auto compute_item = [&](const NttItem &it, const u64 *stage) {
-        const u32 g = it.limb / J.count, c = it.limb - g * J.count;
+    auto compute_item = [&](const NttItem &it, const auto &hook) {
+        const u32 c = it.limb / (u32)J.n_groups, g = it.limb - c * (u32)J.n_groups;
         const LimbGroup &grp = J.groups[g];
         const u64 off = grp.base + (u64)c * grp.stride;
         const ModInfo &M = J.mods[grp.table];
@@ -432,15 +437,15 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_persistent_kernel(const __
         if (FWD) {
             using Pl = FwdColPlan<A>;
             if (it.phase == 0)
-                pass_dispatch<A, true, true, true, false, Pl::LO0, Pl::NL0, Pl::LO1, Pl::NL1, Pl::LO2, Pl::NL2>(stage, xch, M, (int)it.tile, ga, (int)c, off, J.logn, ld, mid_st);
+                pass_dispatch<A, true, true, true, false, Pl::LO0, Pl::NL0, Pl::LO1, Pl::NL1, Pl::LO2, Pl::NL2>(stage, xch, M, (int)it.tile, ga, (int)c, off, J.logn, ld, mid_st, hook);
             else
-                pass_dispatch<8, false, true, false, true, 4, 4, 0, 4, 0, 0>(stage, xch, M, (int)it.tile, ga, (int)c, off, J.logn, mid_ld, st);
+                pass_dispatch<8, false, true, false, true, 4, 4, 0, 4, 0, 0>(stage, xch, M, (int)it.tile, ga, (int)c, off, J.logn, mid_ld, st, hook);
         } else {
             using Pl = InvColPlan<A>;
             if (it.phase == 0)
-                pass_dispatch<8, false, false, true, false, 0, 4, 4, 4, 0, 0>(stage, xch, M, (int)it.tile, ga, (int)c, off, J.logn, ld, mid_st);
+                pass_dispatch<8, false, false, true, false, 0, 4, 4, 4, 0, 0>(stage, xch, M, (int)it.tile, ga, (int)c, off, J.logn, ld, mid_st, hook);
             else
-                pass_dispatch<A, true, false, false, true, Pl::LO0, Pl::NL0, Pl::LO1, Pl::NL1, Pl::LO2, Pl::NL2>(stage, xch, M, (int)it.tile, ga, (int)c, off, J.logn, mid_ld, st);
+                pass_dispatch<A, true, false, false, true, Pl::LO0, Pl::NL0, Pl::LO1, Pl::NL1, Pl::LO2, Pl::NL2>(stage, xch, M, (int)it.tile, ga, (int)c, off, J.logn, mid_ld, st, hook);
         }
     };
 
@@ -457,8 +462,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_persistent_kernel(const __
     u32 cur_id = s_item;
     if (cur_id < total) {
         NttItem cur = ntt_decode(J, cur_id);
-        int buf = 0;
-        stage_item(cur, smem);
+        stage_item(cur);
         bool publish = false; u32 publish_limb = 0;       // a finished first-pass item whose completion is not yet signalled
         while (true) {
             __syncthreads();          // previous item's stores and exchange reads are complete CTA-wide
@@ -473,13 +477,12 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_persistent_kernel(const __
                 s_item = nx; s_ready = ready;
             }
             cp_async_wait_all();
-            __syncthreads();          // stage[buf] complete and visible; next item known
+            __syncthreads();          // stage complete and visible; next item known
             const u32 nxt_id = s_item;
             const bool pre = s_ready != 0;
             NttItem nxt = cur;
             if (nxt_id < total) nxt = ntt_decode(J, nxt_id);
-            if (pre) stage_item(nxt, smem + (buf ^ 1) * NTT_TILE);
-            compute_item(cur, smem + buf * NTT_TILE);
+            compute_item(cur, [&]() { if (pre) stage_item(nxt); });
             publish = cur.phase == 0; publish_limb = cur.limb;
             if (nxt_id >= total) break;
             if (!pre) {               // dependency not met at prefetch time: signal our own completion, then wait
@@ -490,9 +493,9 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_persistent_kernel(const __
                 }
                 publish = false;
                 __syncthreads();
-                stage_item(nxt, smem + (buf ^ 1) * NTT_TILE);
+                stage_item(nxt);
             }
-            cur = nxt; buf ^= 1;
+            cur = nxt;
         }
         __syncthreads();
         if (t == 0 && publish) { __threadfence(); atomicAdd(done + publish_limb, 1u); }

@@ -56,15 +56,20 @@ __global__ void ntt_small_kernel(const __grid_constant__ NttJob P, Load ld, Stor
 // NTT_LAG x 512 KiB = 16 MiB, far inside the 126 MB L2, and ~600 items (2 per resident CTA) are ~19 limbs.
 static constexpr u32 NTT_LAG = 32;
 
+#ifndef B2_NTT_OCC
+#define B2_NTT_OCC 3
+#endif
+constexpr int NTT_OCC = B2_NTT_OCC;     // resident CTAs per SM (register allocation is held to 65536 / (256 * NTT_OCC))
+
 template <int A, bool FWD, class Load, class Store>
 static cudaError_t launch_persistent(const NttJob &J, unsigned grid, cudaStream_t s, Load ld, Store st) {
     static bool configured = false;     // per instantiation; the attribute is per function and device-independent here
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(ntt_persistent_kernel<A, FWD, Load, Store>, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(ntt_persistent_kernel<A, FWD, NTT_OCC, Load, Store>, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    ntt_persistent_kernel<A, FWD, Load, Store><<<grid, NTT_THREADS, NTT_SMEM_BYTES, s>>>(J, ld, st);
+    ntt_persistent_kernel<A, FWD, NTT_OCC, Load, Store><<<grid, NTT_THREADS, NTT_SMEM_BYTES, s>>>(J, ld, st);
     return cudaGetLastError();
 }
 
@@ -104,7 +109,7 @@ static b2_status run_ntt(b2_ctx *ctx, bool forward, const std::vector<LimbGroup>
         b2_status s = ensure_sync(ctx, P.n_limbs, stream);
         if (s != B2_OK) return s;
         P.sync = ctx->d_sync;
-        const unsigned grid = std::min<unsigned>(P.total_items, 2u * (unsigned)ctx->sm_count);
+        const unsigned grid = std::min<unsigned>(P.total_items, (unsigned)NTT_OCC * (unsigned)ctx->sm_count);
         cudaError_t e;
         if (forward) {
             switch (A) {
