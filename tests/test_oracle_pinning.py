@@ -91,6 +91,9 @@ def test_oracle_reproduces_reference_golden(po, name):
         if ntt:
             assert np.array_equal(o.dyadic_convolute(a, 2, b, 2, lvl), g["mul" + s])
             assert np.array_equal(o.dyadic_square(a, lvl), g["square" + s])
+        else:       # BFV: BEHZ multiply (src/evaluator.cu:29-116), pinned word for word
+            assert np.array_equal(o.bfv_multiply(a, b, lvl), g["mul" + s])
+            assert np.array_equal(o.bfv_multiply(a, a, lvl), g["square" + s])
         assert np.array_equal(o.keyswitch(c3[2 * sz:], lvl, ntt, g["relin_key"], dest=c3[:2 * sz], assign=po.ASSIGN_ADD_INPLACE), g["relin" + s])
         ga = o.galois(a, gal, 2, lvl, ntt)
         assert np.array_equal(o.keyswitch(ga[sz:], lvl, ntt, g["galois_key"], dest=ga, assign=po.ASSIGN_OVERWRITE_EXCEPT_FIRST), g["rotate1" + s])
@@ -140,3 +143,21 @@ def test_live_reference_fingerprints_and_oracle_parity(po, scheme):
     assert np.array_equal(fn(rl, 2, L), ms)
     if ntt:
         assert np.array_equal(o.dyadic_convolute(c, 2, c, 2, L), m)
+    else:
+        assert np.array_equal(o.bfv_multiply(c, c, L), m)
+
+
+@pytest.mark.parametrize("log_n,bits,t_bits", [(6, [40, 40, 40], 20), (10, [60, 40, 40, 60], 20), (9, [50, 36, 45, 60, 55], 30), (7, [60] * 6, 59)])
+def test_live_reference_behz_multiply(po, log_n, bits, t_bits):
+    """BEHZ multiply at every level of several modulus chains, incl. a 60-bit plain modulus (|B| = |q| + 1 branch,
+    src/utils/rns_tool.cu:59-62): oracle == unmodified reference, word for word."""
+    if not po.ref_available():
+        pytest.skip("oracle/_ref not built")
+    n = 1 << log_n
+    r = po.Reference(po.BFV, n, bits, t_bits=t_bits, seed=7)
+    o = po.Oracle(log_n, r.moduli, r.t, po.BFV)
+    rng = np.random.default_rng(log_n)
+    for nl in range(len(bits) - 1, 0, -1):
+        a = o.random_poly(rng, 2, nl); b = o.random_poly(rng, 2, nl)
+        assert np.array_equal(o.bfv_multiply(a, b, nl), r.multiply(a, b, nl)), nl
+        assert np.array_equal(o.bfv_multiply(a, a, nl), r.square(a, nl)), nl
