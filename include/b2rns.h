@@ -121,6 +121,11 @@ b2_status b2_kswitch_key_create_contiguous(b2_ctx *ctx, const uint64_t *key /* [
 void      b2_kswitch_key_destroy(b2_kswitch_key *key);
 b2_status b2_keyswitch(b2_ctx *ctx, const uint64_t *target, size_t decomp, int is_ntt, const b2_kswitch_key *key,
                        uint64_t *dest, int assign, void *stream);
+/* K5: Evaluator::switch_key_internal_batched (src/evaluator_keyswitching_core.cu:1055-1267): `batch` ciphertexts sharing one
+ * key.  targets / dests are HOST arrays of `batch` DEVICE pointers (the reference's ConstSliceVec / vector<Ciphertext*>);
+ * the same five launches serve up to 16 ciphertexts at a time, pointer tables travel as kernel arguments. */
+b2_status b2_keyswitch_batched(b2_ctx *ctx, const uint64_t *const *targets, uint64_t *const *dests, size_t batch, size_t decomp, int is_ntt,
+                               const b2_kswitch_key *key, int assign, void *stream);
 
 /* ---- R1-R4: mod_switch_to_next / rescale_to_next (src/evaluator_modswitch.cu:14-149,445-461).
  *      in [count][nl][N] -> out [count][nl-1][N]; kind is a b2_modswitch_kind. ---- */
@@ -138,6 +143,16 @@ b2_status b2_dyadic_square(b2_ctx *ctx, const uint64_t *a, uint64_t *out, size_t
 /* fgk::dyadic_convolute::dyadic_broadcast_product(_accumulate)_ps (src/fgk/dyadic_convolute.cu:151-292):
  * out[k] (+)= a[k] o plain, k < pcount; plain [ncomp][N] */
 b2_status b2_dyadic_broadcast(b2_ctx *ctx, const uint64_t *a, const uint64_t *plain, uint64_t *out, size_t pcount, size_t ncomp, int accumulate, void *stream);
+/* Evaluator::bfv_multiply / bfv_square device branch (src/evaluator.cu:29-116,199-282) = BEHZ RNS multiplication:
+ * RNSTool::fast_b_conv_m_tilde_sm_mrq + NTT + dyadic convolution + INTT + RNSTool::fast_floor_fast_b_conv_sk
+ * (src/fgk/rns_tool.cu:7-343).  a, b [batch][2][nl][N] coefficient form -> out [batch][3][nl][N] coefficient form.
+ * The context must be BFV with a plain modulus; the auxiliary bases B, m_sk (61-bit primes = 1 mod 2N descending from
+ * 2^61, src/utils/rns_tool.cu:59-90) are derived inside the library and can be read back with b2_behz_bases. */
+b2_status b2_bfv_multiply(b2_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t batch, size_t nl, void *stream);
+b2_status b2_behz_bases(b2_ctx *ctx, size_t nl, uint64_t *bsk /* >= K+2 */, size_t *bsk_count, uint64_t *gamma);
+/* utils::ntt_multiply_inv_degree (src/utils/ntt.cu:78-149): x <- x * (N^-1 * scalar) mod q_j, in place;
+ * data [count][ncomp][N], limb j uses modulus table_base + j */
+b2_status b2_scale_inv_degree(b2_ctx *ctx, uint64_t *data, size_t count, size_t ncomp, size_t table_base, uint64_t scalar, void *stream);
 /* utils::negacyclic_shift_ps (src/utils/poly_small_mod.cu:902-949); out of place */
 b2_status b2_negacyclic_shift(b2_ctx *ctx, const uint64_t *a, size_t shift, uint64_t *out, size_t count, size_t ncomp, size_t table_base, void *stream);
 /* GaloisTool::apply_ps / apply_ntt_ps (src/utils/galois.cu:141-300); out of place */

@@ -91,6 +91,7 @@ def lib():
         L.ro_keyswitch.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_int, C.POINTER(u64p), u64p, C.c_int]
         for f in ("ro_divide_round_q_last", "ro_divide_round_q_last_ntt", "ro_mod_t_divide_q_last_ntt", "ro_drop_last_limb"):
             getattr(L, f).argtypes = [C.c_void_p, u64p, u64p, C.c_size_t, C.c_size_t]
+        L.ro_ntt_multiply_inv_degree.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint64]
         L.ro_bfv_multiply.argtypes = [C.c_void_p, u64p, u64p, u64p, C.c_size_t]
         L.ro_behz_bases.argtypes = [C.c_void_p, C.c_size_t, u64p, C.POINTER(C.c_size_t), u64p]
         L.ro_keygen_secret.argtypes = [C.c_void_p, C.c_uint64, u64p]
@@ -216,6 +217,16 @@ class Oracle:
         if self.L.ro_bfv_multiply(self.h, _p(a), _p(b), _p(o), nl):
             raise NotImplementedError("ro_bfv_multiply")
         return o
+
+    def behz_bases(self, nl):
+        bsk = np.zeros(self.nm + 2, dtype=np.uint64); cnt = C.c_size_t(); g = np.zeros(1, dtype=np.uint64)
+        if self.L.ro_behz_bases(self.h, nl, _p(bsk), C.byref(cnt), _p(g)):
+            raise ValueError("ro_behz_bases")
+        return [int(v) for v in bsk[:cnt.value]], int(g[0])
+
+    def ntt_multiply_inv_degree(self, data, pc, nc, scalar=1, base=0):
+        d = np.ascontiguousarray(data, dtype=np.uint64).copy()
+        self.L.ro_ntt_multiply_inv_degree(self.h, _p(d), pc, nc, base, scalar); return d
 
     # toy RLWE -----------------------------------------------------------
     def keygen_secret(self, seed):

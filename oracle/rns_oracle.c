@@ -290,6 +290,17 @@ void ro_ntt_inv(const ro_ctx *c, u64 *d, size_t pc, size_t nc, int mode, size_t 
     ntt_job j = {c, d, nc, mode, base, decomp, 1}; par_for((long)(pc * nc), ntt_job_fn, &j);
 }
 
+/* host_ntt_multiply_inv_degree, src/utils/ntt.cu:78-91: x <- (x * N^-1 lazily) * scalar mod p */
+void ro_ntt_multiply_inv_degree(const ro_ctx *c, u64 *d, size_t pc, size_t nc, size_t base, u64 scalar) {
+    for (size_t k = 0; k < pc; k++) for (size_t j = 0; j < nc; j++) {
+        size_t ti = base + j; u64 p = c->q[ti];
+        for (size_t i = 0; i < c->n; i++) {
+            u64 *x = d + (k * nc + j) * c->n + i;
+            *x = ro_mulmod(ro_shoup_mul_lazy(*x, c->inv_n[ti], c->inv_n_q[ti], p), scalar, p);
+        }
+    }
+}
+
 /* ------------------------------------------------------------------ element-wise */
 
 #define FOR_PLN(pc, nc) for (size_t k = 0; k < (pc); k++) for (size_t j = 0; j < (nc); j++) \

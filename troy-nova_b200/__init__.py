@@ -62,6 +62,7 @@ _SIGS.update({
     "b2_kswitch_key_create_contiguous": (C.c_int, [vp, vp, C.c_size_t, C.POINTER(vp)]),
     "b2_kswitch_key_destroy": (None, [vp]),
     "b2_keyswitch": (C.c_int, [vp, vp, C.c_size_t, C.c_int, vp, vp, C.c_int, vp]),
+    "b2_keyswitch_batched": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.c_size_t, C.c_size_t, C.c_int, vp, C.c_int, vp]),
     "b2_mod_switch_to_next": (C.c_int, [vp, vp, vp, C.c_size_t, C.c_size_t, C.c_int, vp]),
     "b2_add": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp]),
     "b2_sub": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp]),
@@ -71,6 +72,9 @@ _SIGS.update({
     "b2_dyadic_broadcast": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_size_t, C.c_int, vp]),
     "b2_negacyclic_shift": (C.c_int, [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp]),
     "b2_galois": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, vp]),
+    "b2_bfv_multiply": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_size_t, vp]),
+    "b2_behz_bases": (C.c_int, [vp, C.c_size_t, u64p, C.POINTER(C.c_size_t), u64p]),
+    "b2_scale_inv_degree": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint64, vp]),
 })
 MODSWITCH_BFV, MODSWITCH_CKKS, MODSWITCH_BGV, MODSWITCH_DROP = 0, 1, 2, 3
 
@@ -189,6 +193,13 @@ class Context:
         _chk(self.L.b2_keyswitch(self.h, _dptr(target), decomp, int(is_ntt), key.h, _dptr(dest), assign, self._stream(stream)))
         return dest
 
+    def keyswitch_batched(self, targets, decomp, is_ntt, key, dests, assign=ASSIGN_OVERWRITE, stream=None):
+        """targets / dests: lists of device tensors (or raw device pointers), one per ciphertext"""
+        nb = len(targets)
+        tp = (vp * nb)(*[_dptr(t) for t in targets]); dp = (vp * nb)(*[_dptr(d) for d in dests])
+        _chk(self.L.b2_keyswitch_batched(self.h, tp, dp, nb, decomp, int(is_ntt), key.h, assign, self._stream(stream)))
+        return dests
+
     # R1-R4 -------------------------------------------------------------------------------------
     def mod_switch_to_next(self, src, dst, count, nl, kind, stream=None):
         _chk(self.L.b2_mod_switch_to_next(self.h, _dptr(src), _dptr(dst), count, nl, kind, self._stream(stream)))
@@ -212,6 +223,17 @@ class Context:
 
     def dyadic_broadcast(self, a, plain, out, pcount, ncomp, accumulate=False, stream=None):
         _chk(self.L.b2_dyadic_broadcast(self.h, _dptr(a), _dptr(plain), _dptr(out), pcount, ncomp, int(accumulate), self._stream(stream))); return out
+
+    def bfv_multiply(self, a, b, out, nl, batch=1, stream=None):
+        _chk(self.L.b2_bfv_multiply(self.h, _dptr(a), _dptr(b), _dptr(out), batch, nl, self._stream(stream))); return out
+
+    def behz_bases(self, nl):
+        bsk = (C.c_uint64 * (self.K + 2))(); cnt = C.c_size_t(); g = C.c_uint64()
+        _chk(self.L.b2_behz_bases(self.h, nl, bsk, C.byref(cnt), C.byref(g)))
+        return [int(bsk[i]) for i in range(cnt.value)], int(g.value)
+
+    def scale_inv_degree(self, data, count, ncomp, scalar=1, table_base=0, stream=None):
+        _chk(self.L.b2_scale_inv_degree(self.h, _dptr(data), count, ncomp, table_base, scalar, self._stream(stream))); return data
 
     def negacyclic_shift(self, a, shift, out, count, ncomp, table_base=0, stream=None):
         _chk(self.L.b2_negacyclic_shift(self.h, _dptr(a), shift, _dptr(out), count, ncomp, table_base, self._stream(stream))); return out

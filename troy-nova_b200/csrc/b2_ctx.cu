@@ -6,6 +6,47 @@
 
 using namespace b2;
 
+namespace b2 {
+// Per-modulus constants and twiddle tables (host side).  T / IT: N Shoup pairs each; TD / ITD: the same values as
+// doubles (may be null).  Returns 0, 1 (not a prime below 2^61) or 2 (not 1 mod 2N).
+// root_powers[bitrev(k)] = psi^k ; inv_root_powers[bitrev(k-1)+1] = psi^-k  (src/utils/ntt.cu:36-58)
+int build_modulus_tables(uint64_t p, unsigned logn, Tw *T, Tw *IT, double *TD, double *ITD, ModInfo &M, uint64_t &psi_out) {
+    const size_t n = (size_t)1 << logn;
+    if (p < 2 || (p >> 61) != 0 || !host::is_prime(p)) return 1;
+    const uint64_t psi = host::min_primitive_root(2 * n, p);
+    if (!psi) return 2;
+    psi_out = psi;
+    const uint64_t ipsi = host::invmod(psi, p);
+    uint64_t pw = psi, ipw = ipsi;
+    T[0].x = 1; T[0].y = host::shoup_quotient(1, p); IT[n - 1] = T[0];
+    for (size_t k = 1; k < n; k++) {
+        size_t a = host::bitrev((uint32_t)k, logn), b = host::bitrev((uint32_t)(k - 1), logn) + 1;
+        T[a].x = pw; T[a].y = host::shoup_quotient(pw, p);
+        IT[b - 1].x = ipw; IT[b - 1].y = host::shoup_quotient(ipw, p);   // device table = inv_root_powers shifted down by one (16-byte aligned runs)
+        pw = host::mulmod(pw, psi, p); ipw = host::mulmod(ipw, ipsi, p);
+    }
+    memset(&M, 0, sizeof M);
+    M.p = p;
+    host::u128 ratio = (~(host::u128)0) / p;
+    M.r0 = (uint64_t)ratio; M.r1 = (uint64_t)(ratio >> 64); M.ratio = M.r1;
+    const uint64_t inv_n = host::invmod(n % p, p);
+    M.inv_n.x = inv_n; M.inv_n.y = host::shoup_quotient(inv_n, p);
+    const uint64_t last_w = n > 1 ? IT[n - 2].x : 1;    // twiddle of the last inverse layer
+    const uint64_t inw = host::mulmod(inv_n, last_w, p);
+    M.inv_n_w.x = inw; M.inv_n_w.y = host::shoup_quotient(inw, p);
+    const unsigned bits = host::bit_count(p);
+    M.fwd_lazy = ((host::u128)(4 + 2 * logn) * p) < ((host::u128)1 << 64) ? 1u : 0u;
+    M.inv_lazy = (bits + logn + 2 <= 64) ? 1u : 0u;
+    // FP64-pipe path: exact double-double arithmetic needs |x| w / p < 2^51 with |x| < 2^10 p
+    M.bits = bits;
+    M.use_f64 = (bits <= 41 && TD && ITD) ? 1u : 0u;
+    M.pd = (double)p; M.pinv = 1.0 / (double)p;
+    M.inv_n_d = (double)inv_n; M.inv_n_w_d = (double)inw;
+    if (TD && ITD) for (size_t k = 0; k < n; k++) { TD[k] = (double)T[k].x; ITD[k] = (double)IT[k].x; }
+    return 0;
+}
+}  // namespace b2
+
 extern "C" b2_status b2_ctx_create(int device, const b2_params *prm, b2_ctx **out) {
     B2_REQUIRE(prm && out && prm->moduli, "null argument");
     B2_REQUIRE(prm->log_n >= 1 && prm->log_n <= 17, "log_n must be in [1, 17]");
@@ -34,46 +75,14 @@ extern "C" b2_status b2_ctx_create(int device, const b2_params *prm, b2_ctx **ou
     std::vector<double> twd(K * n), itwd(K * n);
     c->h_mods.resize(K);
     for (size_t i = 0; i < K; i++) {
-        const uint64_t p = c->q[i];
-        if (p < 2 || (p >> 61) != 0 || !host::is_prime(p)) { delete c; set_error("b2_ctx_create: modulus %zu is not a prime below 2^61", i); return B2_ERR_INVALID_ARG; }
-        const uint64_t psi = host::min_primitive_root(2 * n, p);
-        if (!psi) { delete c; set_error("b2_ctx_create: modulus %zu is not 1 mod 2N", i); return B2_ERR_INVALID_ARG; }
-        c->psi[i] = psi;
-        const uint64_t ipsi = host::invmod(psi, p);
-        Tw *T = &tw[i * n], *IT = &itw[i * n];
-        // root_powers[bitrev(k)] = psi^k ; inv_root_powers[bitrev(k-1)+1] = psi^-k  (src/utils/ntt.cu:36-58)
-        uint64_t pw = psi, ipw = ipsi;
-        T[0].x = 1; T[0].y = host::shoup_quotient(1, p); IT[n - 1] = T[0];
-        for (size_t k = 1; k < n; k++) {
-            size_t a = host::bitrev((uint32_t)k, logn), b = host::bitrev((uint32_t)(k - 1), logn) + 1;
-            T[a].x = pw; T[a].y = host::shoup_quotient(pw, p);
-            IT[b - 1].x = ipw; IT[b - 1].y = host::shoup_quotient(ipw, p);   // device table = inv_root_powers shifted down by one (16-byte aligned runs)
-            pw = host::mulmod(pw, psi, p); ipw = host::mulmod(ipw, ipsi, p);
-        }
-        ModInfo &M = c->h_mods[i];
-        memset(&M, 0, sizeof M);
-        M.p = p;
-        host::u128 ratio = (~(host::u128)0) / p;
-        M.r0 = (uint64_t)ratio; M.r1 = (uint64_t)(ratio >> 64); M.ratio = M.r1;
-        const uint64_t inv_n = host::invmod(n % p, p);
-        M.inv_n.x = inv_n; M.inv_n.y = host::shoup_quotient(inv_n, p);
-        const uint64_t last_w = n > 1 ? IT[n - 2].x : 1;    // twiddle of the last inverse layer
-        const uint64_t inw = host::mulmod(inv_n, last_w, p);
-        M.inv_n_w.x = inw; M.inv_n_w.y = host::shoup_quotient(inw, p);
-        const unsigned bits = host::bit_count(p);
-        M.fwd_lazy = ((host::u128)(4 + 2 * logn) * p) < ((host::u128)1 << 64) ? 1u : 0u;
-        M.inv_lazy = (bits + logn + 2 <= 64) ? 1u : 0u;
-        // FP64-pipe path: exact double-double arithmetic needs |x| w / p < 2^51 with |x| < 2^10 p
-        M.bits = bits;
-        M.use_f64 = (bits <= 41) ? 1u : 0u;
-        M.pd = (double)p; M.pinv = 1.0 / (double)p;
-        M.inv_n_d = (double)inv_n; M.inv_n_w_d = (double)inw;
-        for (size_t k = 0; k < n; k++) { twd[i * n + k] = (double)T[k].x; itwd[i * n + k] = (double)IT[k].x; }
+        const int rc = build_modulus_tables(c->q[i], logn, &tw[i * n], &itw[i * n], &twd[i * n], &itwd[i * n], c->h_mods[i], c->psi[i]);
+        if (rc == 1) { delete c; set_error("b2_ctx_create: modulus %zu is not a prime below 2^61", i); return B2_ERR_INVALID_ARG; }
+        if (rc == 2) { delete c; set_error("b2_ctx_create: modulus %zu is not 1 mod 2N", i); return B2_ERR_INVALID_ARG; }
     }
     cudaError_t ce;
     if ((ce = cudaMalloc(&c->d_tw, K * n * sizeof(Tw))) != cudaSuccess || (ce = cudaMalloc(&c->d_itw, K * n * sizeof(Tw))) != cudaSuccess ||
         (ce = cudaMalloc(&c->d_twd, K * n * sizeof(double))) != cudaSuccess || (ce = cudaMalloc(&c->d_itwd, K * n * sizeof(double))) != cudaSuccess ||
-        (ce = cudaMalloc(&c->d_mods, K * sizeof(ModInfo))) != cudaSuccess) {
+        (ce = cudaMalloc(&c->d_mods, (2 * K + 2) * sizeof(ModInfo))) != cudaSuccess) {
         b2_ctx_destroy(c);
         return cuda_fail(ce, "cudaMalloc(tables)");
     }
@@ -111,6 +120,6 @@ extern "C" b2_status b2_ctx_create(int device, const b2_params *prm, b2_ctx **ou
 extern "C" void b2_ctx_destroy(b2_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaFree(c->d_tw); cudaFree(c->d_itw); cudaFree(c->d_twd); cudaFree(c->d_itwd); cudaFree(c->d_mods); cudaFree(c->d_inv); cudaFree(c->d_inv_mod_t); cudaFree(c->d_galois); cudaFree(c->ws); cudaFree(c->stage); cudaFree(c->d_sync);
+    cudaFree(c->d_tw); cudaFree(c->d_itw); cudaFree(c->d_twd); cudaFree(c->d_itwd); cudaFree(c->d_mods); b2::behz_release(c); cudaFree(c->d_inv); cudaFree(c->d_inv_mod_t); cudaFree(c->d_galois); cudaFree(c->ws); cudaFree(c->stage); cudaFree(c->d_sync);
     delete c;
 }

@@ -1,5 +1,6 @@
 // b2_ctx.h — internal definition of the opaque b2_ctx handle.
 #pragma once
+#include <cstring>
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
@@ -31,6 +32,9 @@ struct b2_ctx {
     // persistent-NTT work queue + per-limb completion counters (zero between launches; the kernel resets them)
     unsigned *d_sync = nullptr; size_t sync_limbs = 0;
     int sm_count = 148;
+    // BEHZ (BFV multiply) auxiliary base, built lazily by the first b2_bfv_multiply: ModInfo slots K .. 2K+1 hold
+    // B_0 .. B_K (K+1 primes) and m_sk; per-level constant blobs keyed by the number of ciphertext limbs
+    struct b2_behz *behz = nullptr;
 };
 
 namespace b2 {
@@ -41,6 +45,8 @@ b2_status cuda_fail(cudaError_t e, const char *what);
 b2_status ensure_ws(b2_ctx *ctx, size_t bytes);
 b2_status ensure_stage(b2_ctx *ctx, size_t bytes);
 b2_status ensure_sync(b2_ctx *ctx, size_t limbs, cudaStream_t stream);
+int build_modulus_tables(uint64_t p, unsigned logn, Tw *T, Tw *IT, double *TD, double *ITD, ModInfo &M, uint64_t &psi_out);
+void behz_release(b2_ctx *ctx);
 #define B2_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return b2::cuda_fail(e__, #call); } while (0)
 #define B2_REQUIRE(cond, msg) do { if (!(cond)) { b2::set_error("%s: %s", __func__, msg); return B2_ERR_INVALID_ARG; } } while (0)
 

@@ -137,6 +137,17 @@ __global__ void __launch_bounds__(256) ew_galois_ntt_kernel(const u64 *__restric
     }
 }
 
+// x <- x * (N^-1 * scalar) mod p      (kernel_ntt_multiply_inv_degree, src/utils/ntt.cu:109-117)
+__global__ void __launch_bounds__(256) ew_scale_inv_degree_kernel(ulonglong2 *__restrict__ d, const ModInfo *__restrict__ mods, EwShape S, u64 scalar) {
+    for (u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x; v < S.total2; v += (u64)gridDim.x * blockDim.x) {
+        const ModInfo &M = ew_mod(mods, S, v);
+        const u64 p = M.p, f = mulmod(M.inv_n.x, barrett64(scalar, p, M.ratio), p, M.r0, M.r1);
+        ulonglong2 x = d[v];
+        x.x = mulmod(x.x, f, p, M.r0, M.r1); x.y = mulmod(x.y, f, p, M.r0, M.r1);
+        d[v] = x;
+    }
+}
+
 static inline unsigned ew_grid(u64 total) { return (unsigned)std::min<u64>((total + 255) / 256, 148u * 32u); }
 
 }  // namespace b2
@@ -190,6 +201,15 @@ b2_status b2_dyadic_broadcast(b2_ctx *ctx, const uint64_t *a, const uint64_t *pl
     EwShape S{(u32)ncomp, (u32)(n / 2), 0u, (u64)pcount * ncomp * (n / 2)};
     if (accumulate) ew_broadcast_kernel<true><<<ew_grid(S.total2), 256, 0, stream>>>((const ulonglong2 *)a, (const ulonglong2 *)plain, (ulonglong2 *)out, ctx->d_mods, S);
     else ew_broadcast_kernel<false><<<ew_grid(S.total2), 256, 0, stream>>>((const ulonglong2 *)a, (const ulonglong2 *)plain, (ulonglong2 *)out, ctx->d_mods, S);
+    count_launches(1);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+b2_status b2_scale_inv_degree(b2_ctx *ctx, uint64_t *data, size_t count, size_t ncomp, size_t table_base, uint64_t scalar, void *stream_) {
+    EW_PROLOG(data && table_base + ncomp <= ctx->K && ctx->n >= 2, "bad arguments");
+    if (count * ncomp == 0) return B2_OK;
+    EwShape S{(u32)ncomp, (u32)(n / 2), (u32)table_base, (u64)count * ncomp * (n / 2)};
+    ew_scale_inv_degree_kernel<<<ew_grid(S.total2), 256, 0, stream>>>((ulonglong2 *)data, ctx->d_mods, S, scalar);
     count_launches(1);
     B2_CUDA(cudaGetLastError());
     return B2_OK;

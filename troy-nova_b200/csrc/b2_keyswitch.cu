@@ -30,38 +30,54 @@ struct b2_kswitch_key {
 
 namespace b2 {
 
+// ---- step 1 loader: limb j of the target of ciphertext b (NTT form) -------------------------------------
+struct TargetLoad {
+    PtrTab t; u32 n;
+    __device__ __forceinline__ const u64 *src(int j, int b, u64) const { return t.p[b] + (u64)j * n; }
+    __device__ __forceinline__ u64 xf(int, int, u32, u64 raw) const { return raw; }
+};
+
 // ---- step 2 loader: c_j re-reduced modulo the group's modulus (src/fgk/switch_key.cu:6-27) ----------
+// limb index c = b * decomp + j; coefficient-form source of ciphertext b at tc.p[b] ([decomp][N])
 struct ModUpLoad {
-    const u64 *tc;        // [decomp][N] coefficient form
+    PtrTab tc;
     const ModInfo *mods;
     u32 decomp, K, n;
-    __device__ __forceinline__ const u64 *src(int, int c, u64) const { return tc + (u64)c * n; }
+    __device__ __forceinline__ const u64 *src(int, int c, u64) const {
+        const u32 b = (u32)c / decomp, j = (u32)c - b * decomp;
+        return tc.p[b] + (u64)j * n;
+    }
     __device__ __forceinline__ u64 xf(int g, int c, u32, u64 v) const {
         const u32 ki = (u32)g == decomp ? K - 1 : (u32)g;
+        const u32 j = (u32)c % decomp;
         const u64 m = mods[ki].p;
         // q_j <= m_i: already canonical modulo m_i
-        return (mods[c].p <= m) ? v : barrett64(v, m, mods[ki].ratio);
+        return (mods[j].p <= m) ? v : barrett64(v, m, mods[ki].ratio);
     }
 };
 
 // ---- step 3: key inner product (src/fgk/switch_key.cu:77-132) --------------------------------------
-// one thread per (i, coefficient pair); loops over the decomp digits with 128-bit lazy accumulators.
+// one thread per (ciphertext b, output modulus i, coefficient pair); loops over the decomp digits with 128-bit lazy
+// accumulators.  temp [R][B][decomp][N], prod [B][2][R][N].  blockIdx.x = b so that the CTAs that read the same key
+// rows are co-scheduled and all but the first hit in L2.
 __global__ void __launch_bounds__(256) ks_inner_product_kernel(const u64 *__restrict__ temp, const u64 *const *__restrict__ keys,
                                                                  u64 *__restrict__ prod, const ModInfo *__restrict__ mods,
                                                                  u32 decomp, u32 K, u32 n) {
-    const u32 i = blockIdx.y;                       // output modulus index 0..decomp
+    const u32 b = blockIdx.x, nb = gridDim.x;
+    const u32 i = blockIdx.z;                       // output modulus index 0..decomp
     const u32 ki = i == decomp ? K - 1 : i;
-    const u32 x = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    const u32 x = (blockIdx.y * blockDim.x + threadIdx.x) * 2;
     if (x >= n) return;
     const ModInfo &M = mods[ki];
     const u64 p = M.p, r0 = M.r0, r1 = M.r1;
     u64 a0l = 0, a0h = 0, a1l = 0, a1h = 0, b0l = 0, b0h = 0, b1l = 0, b1h = 0;
-    const u64 *tp = temp + ((u64)i * decomp) * n + x;
+    const u64 *tp = temp + (((u64)i * nb + b) * decomp) * n + x;
     for (u32 j = 0; j < decomp; j++) {
         const ulonglong2 d = __ldcs(reinterpret_cast<const ulonglong2 *>(tp + (u64)j * n));   // streamed once: evict-first
         const u64 *kp = keys[j] + (u64)ki * n + x;
-        const ulonglong2 k0 = __ldcs(reinterpret_cast<const ulonglong2 *>(kp));
-        const ulonglong2 k1 = __ldcs(reinterpret_cast<const ulonglong2 *>(kp + (u64)K * n));
+        ulonglong2 k0, k1;
+        if (nb == 1) { k0 = __ldcs(reinterpret_cast<const ulonglong2 *>(kp)); k1 = __ldcs(reinterpret_cast<const ulonglong2 *>(kp + (u64)K * n)); }
+        else { k0 = __ldg(reinterpret_cast<const ulonglong2 *>(kp)); k1 = __ldg(reinterpret_cast<const ulonglong2 *>(kp + (u64)K * n)); }
         mac128(a0l, a0h, d.x, k0.x); mac128(a1l, a1h, d.y, k0.y);
         mac128(b0l, b0h, d.x, k1.x); mac128(b1l, b1h, d.y, k1.y);
         if ((j & 7) == 7) {     // keep the lazy 128-bit sums below 2^125 (8 products of 61-bit residues)
@@ -73,18 +89,18 @@ __global__ void __launch_bounds__(256) ks_inner_product_kernel(const u64 *__rest
     ulonglong2 o0, o1;
     o0.x = barrett128(a0l, a0h, p, r0, r1); o0.y = barrett128(a1l, a1h, p, r0, r1);
     o1.x = barrett128(b0l, b0h, p, r0, r1); o1.y = barrett128(b1l, b1h, p, r0, r1);
-    *reinterpret_cast<ulonglong2 *>(prod + ((u64)0 * R + i) * n + x) = o0;
-    *reinterpret_cast<ulonglong2 *>(prod + ((u64)1 * R + i) * n + x) = o1;
+    *reinterpret_cast<ulonglong2 *>(prod + (((u64)b * 2 + 0) * R + i) * n + x) = o0;
+    *reinterpret_cast<ulonglong2 *>(prod + (((u64)b * 2 + 1) * R + i) * n + x) = o1;
 }
 
-struct SpecialLoad {      // step 4: the special-prime limb of prod[k]
+struct SpecialLoad {      // step 4: the special-prime limb of prod[b][k], c = 2 b + k
     const u64 *prod; u32 R, decomp, n;
-    __device__ __forceinline__ const u64 *src(int, int k, u64) const { return prod + ((u64)k * R + decomp) * n; }
+    __device__ __forceinline__ const u64 *src(int, int c, u64) const { return prod + ((u64)c * R + decomp) * n; }
     __device__ __forceinline__ u64 xf(int, int, u32, u64 raw) const { return raw; }
 };
-struct ProdLoad {         // coefficient-form path: transform prod[k][j] itself (inverse NTT)
+struct ProdLoad {         // coefficient-form path: transform prod[b][k][j] itself (inverse NTT)
     const u64 *prod; u32 decomp, n;
-    __device__ __forceinline__ const u64 *src(int j, int k, u64) const { return prod + ((u64)k * (decomp + 1) + j) * n; }
+    __device__ __forceinline__ const u64 *src(int j, int c, u64) const { return prod + ((u64)c * (decomp + 1) + j) * n; }
     __device__ __forceinline__ u64 xf(int, int, u32, u64 raw) const { return raw; }
 };
 
@@ -117,20 +133,12 @@ void b2_kswitch_key_destroy(b2_kswitch_key *k) {
     delete k;
 }
 
-b2_status b2_keyswitch(b2_ctx *ctx, const uint64_t *target, size_t decomp, int is_ntt, const b2_kswitch_key *key,
-                       uint64_t *dest, int assign, void *stream_) {
-    B2_REQUIRE(ctx && target && key && dest, "null argument");
-    B2_REQUIRE((((uintptr_t)target | (uintptr_t)dest) & 15) == 0, "operands must be 16-byte aligned");
-    B2_REQUIRE(decomp >= 1 && decomp + 1 <= ctx->K, "decomp must be in [1, K-1] (keyswitching needs a special prime)");
-    B2_REQUIRE(key->digits >= decomp, "keyswitching key has fewer digits than the ciphertext has limbs");
-    B2_REQUIRE(assign >= 0 && assign <= 2, "unknown assign method");
-    B2_REQUIRE(ctx->scheme != B2_SCHEME_BGV || is_ntt, "BGV ciphertexts are NTT-form");
-    B2_REQUIRE(ctx->scheme != B2_SCHEME_BGV || ctx->t > 1, "BGV needs a plain modulus");
-    B2_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t stream = (cudaStream_t)stream_;
+// one chunk of nb <= KS_MAXB ciphertexts sharing `key`
+static b2_status keyswitch_chunk(b2_ctx *ctx, const uint64_t *const *targets, uint64_t *const *dests, size_t nb, size_t decomp, int is_ntt,
+                                 const b2_kswitch_key *key, int assign, cudaStream_t stream) {
     const size_t n = ctx->n, K = ctx->K, R = decomp + 1;
-    // workspace: tc [decomp][N] | temp [R][decomp][N] | prod [2][R][N] | u [2][N] | mid [2][decomp][N]
-    const size_t w_tc = decomp * n, w_temp = R * decomp * n, w_prod = 2 * R * n, w_u = 2 * n, w_mid = 2 * decomp * n;
+    // workspace: tc [B][decomp][N] | temp [R][B][decomp][N] | prod [B][2][R][N] | u [B][2][N] | mid [B][2][decomp][N]
+    const size_t w_tc = nb * decomp * n, w_temp = R * nb * decomp * n, w_prod = nb * 2 * R * n, w_u = nb * 2 * n, w_mid = nb * 2 * decomp * n;
     b2_status st = ensure_ws(ctx, (w_tc + w_temp + w_prod + w_u + w_mid) * 8);
     if (st != B2_OK) return st;
     u64 *tc = (u64 *)ctx->ws, *temp = tc + w_tc, *prod = temp + w_temp, *u = prod + w_prod, *mid = u + w_u;
@@ -141,46 +149,53 @@ b2_status b2_keyswitch(b2_ctx *ctx, const uint64_t *target, size_t decomp, int i
     int nev = 0;
     auto mark = [&]() { if (timing) { cudaEventCreate(&ev[nev]); cudaEventRecord(ev[nev], stream); nev++; } };
     mark();
-    // 1. coefficient form of the target
-    const u64 *tcoef = (const u64 *)target;
+    // 1. coefficient form of the targets
+    PtrTab coef;
+    for (size_t b = 0; b < nb; b++) coef.p[b] = (const u64 *)targets[b];
+    for (size_t b = nb; b < (size_t)KS_MAXB; b++) coef.p[b] = nullptr;
     if (is_ntt) {
-        st = ntt_launch(ctx, false, target, (uint64_t *)tc, 1, 1, decomp, B2_TABLES_COMPONENTWISE, 0, 0, stream);
+        std::vector<LimbGroup> groups;
+        for (size_t j = 0; j < decomp; j++) groups.push_back(LimbGroup{(u32)j, (u32)nb, (u64)(j * n), (u64)(decomp * n)});
+        TargetLoad ld{coef, (u32)n};
+        st = run_ntt(ctx, false, groups, tc, ld, PlainStore{tc}, stream);
         if (st != B2_OK) return st;
-        tcoef = tc;
+        for (size_t b = 0; b < nb; b++) coef.p[b] = tc + b * decomp * n;
     }
     mark();
-    // 2. mod-up + NTT: group i = output modulus, limbs j = digits; results temp[i][j]
+    // 2. mod-up + NTT: group i = output modulus, limbs c = (b, j); results temp[i][b][j]
     {
         std::vector<LimbGroup> groups;
-        for (size_t i = 0; i < R; i++) groups.push_back(LimbGroup{(u32)(i == decomp ? K - 1 : i), (u32)decomp, (u64)(i * decomp * n), (u64)n});
-        ModUpLoad ld{tcoef, ctx->d_mods, (u32)decomp, (u32)K, (u32)n};
+        for (size_t i = 0; i < R; i++) groups.push_back(LimbGroup{(u32)(i == decomp ? K - 1 : i), (u32)(nb * decomp), (u64)(i * nb * decomp * n), (u64)n});
+        ModUpLoad ld{coef, ctx->d_mods, (u32)decomp, (u32)K, (u32)n};
         st = run_ntt(ctx, true, groups, temp, ld, PlainStore{temp}, stream);
         if (st != B2_OK) return st;
     }
     mark();
     // 3. key inner product
     {
-        dim3 grid((unsigned)((n / 2 + 255) / 256), (unsigned)R);
+        dim3 grid((unsigned)nb, (unsigned)((n / 2 + 255) / 256), (unsigned)R);
         ks_inner_product_kernel<<<grid, 256, 0, stream>>>(temp, (const u64 *const *)key->d_ptrs, prod, ctx->d_mods, (u32)decomp, (u32)K, (u32)n);
         count_launches(1);
         B2_CUDA(cudaGetLastError());
     }
     mark();
-    // 4. u_k = INTT_P(prod[k][decomp])
+    // 4. u_{b,k} = INTT_P(prod[b][k][decomp])
     {
-        std::vector<LimbGroup> groups{LimbGroup{(u32)(K - 1), 2u, 0, (u64)n}};
+        std::vector<LimbGroup> groups{LimbGroup{(u32)(K - 1), (u32)(2 * nb), 0, (u64)n}};
         SpecialLoad ld{prod, (u32)R, (u32)decomp, (u32)n};
         st = run_ntt(ctx, false, groups, u, ld, PlainStore{u}, stream);
         if (st != B2_OK) return st;
     }
     mark();
-    // 5. mod-down fused around one transform of [2][decomp] limbs (group j = modulus, limb k = poly)
+    // 5. mod-down fused around one transform of [B][2][decomp] limbs (group j = modulus, limb c = 2 b + k)
     {
         std::vector<LimbGroup> groups;
-        for (size_t j = 0; j < decomp; j++) groups.push_back(LimbGroup{(u32)j, 2u, (u64)(j * n), (u64)(decomp * n)});
+        for (size_t j = 0; j < decomp; j++) groups.push_back(LimbGroup{(u32)j, (u32)(2 * nb), (u64)(j * n), (u64)(decomp * n)});
         ModDownTerm T{u, ctx->d_mods, (u32)(K - 1), (u32)n, ctx->scheme == B2_SCHEME_BGV ? 1 : 0, ctx->t, ctx->t_ratio, ctx->t_r0, ctx->t_r1,
                       ctx->h_inv_mod_t[K - 1]};
-        ModDownStore sst{T, prod, ctx->d_inv + (K - 1) * K, (u64 *)dest, (u32)decomp, (u32)assign, is_ntt ? 1 : 0};
+        PtrTabW dp;
+        for (size_t b = 0; b < (size_t)KS_MAXB; b++) dp.p[b] = b < nb ? (u64 *)dests[b] : nullptr;
+        ModDownStore sst{T, prod, ctx->d_inv + (K - 1) * K, dp, (u32)decomp, (u32)assign, is_ntt ? 1 : 0};
         if (is_ntt) st = run_ntt(ctx, true, groups, mid, ModDownLoad{T}, sst, stream);
         else st = run_ntt(ctx, false, groups, mid, ProdLoad{prod, (u32)decomp, (u32)n}, sst, stream);
         if (st != B2_OK) return st;
@@ -190,12 +205,41 @@ b2_status b2_keyswitch(b2_ctx *ctx, const uint64_t *target, size_t decomp, int i
         cudaEventSynchronize(ev[nev - 1]);
         static const char *names[] = {"intt(target)", "modup+ntt", "inner product", "intt(special)", "moddown+ntt"};
         float tot = 0; cudaEventElapsedTime(&tot, ev[0], ev[nev - 1]);
-        fprintf(stderr, "[b2 keyswitch] total %.1f us:", tot * 1e3f);
+        fprintf(stderr, "[b2 keyswitch x%zu] total %.1f us:", nb, tot * 1e3f);
         for (int i = 0; i + 1 < nev; i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); fprintf(stderr, " %s %.1f", names[i], ms * 1e3f); }
         fprintf(stderr, "\n");
         for (int i = 0; i < nev; i++) cudaEventDestroy(ev[i]);
     }
     return B2_OK;
+}
+
+b2_status b2_keyswitch_batched(b2_ctx *ctx, const uint64_t *const *targets, uint64_t *const *dests, size_t batch, size_t decomp, int is_ntt,
+                               const b2_kswitch_key *key, int assign, void *stream_) {
+    B2_REQUIRE(ctx && key && (batch == 0 || (targets && dests)), "null argument");
+    B2_REQUIRE(decomp >= 1 && decomp + 1 <= ctx->K, "decomp must be in [1, K-1] (keyswitching needs a special prime)");
+    B2_REQUIRE(key->digits >= decomp, "keyswitching key has fewer digits than the ciphertext has limbs");
+    B2_REQUIRE(assign >= 0 && assign <= 2, "unknown assign method");
+    B2_REQUIRE(ctx->scheme != B2_SCHEME_BGV || is_ntt, "BGV ciphertexts are NTT-form");
+    B2_REQUIRE(ctx->scheme != B2_SCHEME_BGV || ctx->t > 1, "BGV needs a plain modulus");
+    for (size_t b = 0; b < batch; b++) {
+        B2_REQUIRE(targets[b] && dests[b], "null operand in batch");
+        B2_REQUIRE((((uintptr_t)targets[b] | (uintptr_t)dests[b]) & 15) == 0, "operands must be 16-byte aligned");
+    }
+    B2_CUDA(cudaSetDevice(ctx->device));
+    // chunk so that the workspace of one chunk stays below ~4 GiB
+    const size_t per_ct = (decomp + (decomp + 1) * decomp + 2 * (decomp + 1) + 2 + 2 * decomp) * ctx->n * 8;
+    size_t chunk = std::max<size_t>(1, std::min<size_t>((size_t)KS_MAXB, ((size_t)4 << 30) / per_ct));
+    for (size_t b0 = 0; b0 < batch; b0 += chunk) {
+        b2_status st = keyswitch_chunk(ctx, targets + b0, dests + b0, std::min(chunk, batch - b0), decomp, is_ntt, key, assign, (cudaStream_t)stream_);
+        if (st != B2_OK) return st;
+    }
+    return B2_OK;
+}
+
+b2_status b2_keyswitch(b2_ctx *ctx, const uint64_t *target, size_t decomp, int is_ntt, const b2_kswitch_key *key,
+                       uint64_t *dest, int assign, void *stream_) {
+    B2_REQUIRE(ctx && target && key && dest, "null argument");
+    return b2_keyswitch_batched(ctx, &target, &dest, 1, decomp, is_ntt, key, assign, stream_);
 }
 
 }  // extern "C"
