@@ -223,12 +223,12 @@ def main():
     peak, peak_src = measured_peaks()
     achieved = limbs * n * 16 / fwd_s / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "ntt_pass_kernel (column pass + row pass launches of one b2_ntt_forward over 420 limbs)",
+                "kernel": "ntt_persistent_kernel (one launch = one b2_ntt_forward over 420 limbs, both passes)",
                 "algorithmic_bytes_per_call": limbs * n * 16, "call_ms": fwd_s * 1e3, "peak_source": peak_src}
 
     # ---- end to end through the host-buffer C ABI (pinned host memory, H2D + D2H inside the timed region)
     e2e = None
-    e2e_pc = 4                                         # 4 x 21 limbs = 42 MiB per direction per call
+    e2e_pc = PCOUNT                                    # the same [20][21][N] operand: 210 MiB per direction per call
     hb = torch.empty((e2e_pc, NCOMP, n), dtype=torch.int64).pin_memory()
     hb.copy_(x0[:e2e_pc].cpu())
     hnp = hb.numpy().view(np.uint64).reshape(-1)
@@ -246,7 +246,7 @@ def main():
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     nbytes = e2e_pc * NCOMP * n * 8
     e2e = {"value": world * e2e_steps * 2 * e2e_pc * NCOMP / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": 2 * nbytes,
-           "note": "b2_ntt_forward_host + b2_ntt_inverse_host on a [4][21][N] operand in pinned host memory; result verified below"}
+           "note": "b2_ntt_forward_host + b2_ntt_inverse_host on the [20][21][N] operand in pinned host memory (chunked: H2D, transform and D2H overlap); result verified below"}
     assert torch.equal(hb, x0[:e2e_pc].cpu()), "e2e round trip mismatch"
 
     # ---- extra: relinearize / rotate ops/s on the same parameter set (keyswitch core, data resident)

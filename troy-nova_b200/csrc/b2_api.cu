@@ -35,6 +35,16 @@ b2_status ensure_stage(b2_ctx *ctx, size_t bytes) {
     ctx->stage_bytes = bytes;
     return B2_OK;
 }
+b2_status ensure_copy_pipeline(b2_ctx *ctx, size_t n_events) {
+    if (!ctx->s_in) B2_CUDA(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    if (!ctx->s_out) B2_CUDA(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    while (ctx->events.size() < n_events) {
+        cudaEvent_t e;
+        B2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->events.push_back(e);
+    }
+    return B2_OK;
+}
 b2_status ensure_sync(b2_ctx *ctx, size_t limbs, cudaStream_t stream) {
     if (ctx->d_sync && ctx->sync_limbs >= limbs) return B2_OK;
     if (ctx->d_sync) { B2_CUDA(cudaDeviceSynchronize()); B2_CUDA(cudaFree(ctx->d_sync)); ctx->d_sync = nullptr; ctx->sync_limbs = 0; }

@@ -86,6 +86,8 @@ static b2_status ensure_behz(b2_ctx *ctx) {
     }
     for (size_t a = 0; a < A; a++) { mods[a].tw = bz->d_tw + a * n; mods[a].itw = bz->d_itw + a * n; }
     ctx->behz = bz;
+    ctx->h_mods.resize(K);                                   // host copies: run_ntt reads the arithmetic path of every table from h_mods
+    ctx->h_mods.insert(ctx->h_mods.end(), mods.begin(), mods.end());
     B2_CUDA(cudaMemcpy(bz->d_tw, tw.data(), A * n * sizeof(Tw), cudaMemcpyHostToDevice));
     B2_CUDA(cudaMemcpy(bz->d_itw, itw.data(), A * n * sizeof(Tw), cudaMemcpyHostToDevice));
     B2_CUDA(cudaMemcpy(ctx->d_mods + K, mods.data(), A * sizeof(ModInfo), cudaMemcpyHostToDevice));

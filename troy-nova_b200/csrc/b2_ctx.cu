@@ -121,5 +121,8 @@ extern "C" void b2_ctx_destroy(b2_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaFree(c->d_tw); cudaFree(c->d_itw); cudaFree(c->d_twd); cudaFree(c->d_itwd); cudaFree(c->d_mods); b2::behz_release(c); cudaFree(c->d_inv); cudaFree(c->d_inv_mod_t); cudaFree(c->d_galois); cudaFree(c->ws); cudaFree(c->stage); cudaFree(c->d_sync);
+    for (cudaEvent_t e : c->events) cudaEventDestroy(e);
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
     delete c;
 }

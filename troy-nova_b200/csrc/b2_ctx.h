@@ -29,6 +29,8 @@ struct b2_ctx {
     void *ws = nullptr; size_t ws_bytes = 0;
     // host-buffer staging for the *_host entry points
     void *stage = nullptr; size_t stage_bytes = 0;
+    cudaStream_t s_in = nullptr, s_out = nullptr;     // copy streams of the pipelined *_host entry points
+    std::vector<cudaEvent_t> events;
     // persistent-NTT work queue + per-limb completion counters (zero between launches; the kernel resets them)
     unsigned *d_sync = nullptr; size_t sync_limbs = 0;
     int sm_count = 148;
@@ -44,6 +46,7 @@ void set_error(const char *fmt, ...);
 b2_status cuda_fail(cudaError_t e, const char *what);
 b2_status ensure_ws(b2_ctx *ctx, size_t bytes);
 b2_status ensure_stage(b2_ctx *ctx, size_t bytes);
+b2_status ensure_copy_pipeline(b2_ctx *ctx, size_t n_events);
 b2_status ensure_sync(b2_ctx *ctx, size_t limbs, cudaStream_t stream);
 int build_modulus_tables(uint64_t p, unsigned logn, Tw *T, Tw *IT, double *TD, double *ITD, ModInfo &M, uint64_t &psi_out);
 void behz_release(b2_ctx *ctx);

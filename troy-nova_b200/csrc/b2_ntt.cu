@@ -71,19 +71,50 @@ b2_status b2_ntt_inverse_ptrs(b2_ctx *ctx, const uint64_t *const *in, uint64_t *
     return ntt_ptrs(ctx, false, in, out, batch, pcount, ncomp, mode, table_base, decomp, stream);
 }
 
+// Host-buffer transform, pipelined: the operand is cut into chunks of whole limbs (~4 MiB); chunk c+1 travels host->device
+// on a copy stream while chunk c is transformed on `stream` and chunk c-1 travels device->host on a second copy stream, so
+// both PCIe directions and the SMs are busy at the same time.  Synchronised on return (the caller's buffers are plain
+// host memory; pinned memory gives full-rate DMA).
 static b2_status ntt_host(b2_ctx *ctx, bool fwd, const uint64_t *in, uint64_t *out, size_t batch, size_t pcount, size_t ncomp,
                           int mode, size_t table_base, size_t decomp, void *stream) {
     B2_REQUIRE(ctx && in && out, "null argument");
-    const size_t bytes = batch * pcount * ncomp * ctx->n * 8;
+    const size_t n = ctx->n, K = ctx->K, limbs = batch * pcount * ncomp, bytes = limbs * n * 8;
     if (bytes == 0) return B2_OK;
+    b2_status st = check_ntt_args(ctx, batch, pcount, ncomp, mode, table_base, decomp);
+    if (st != B2_OK) return st;
     B2_CUDA(cudaSetDevice(ctx->device));
-    b2_status st = ensure_stage(ctx, bytes);
+    st = ensure_stage(ctx, bytes);
     if (st != B2_OK) return st;
-    cudaStream_t s = (cudaStream_t)stream;
-    B2_CUDA(cudaMemcpyAsync(ctx->stage, in, bytes, cudaMemcpyHostToDevice, s));
-    st = ntt_launch(ctx, fwd, (const uint64_t *)ctx->stage, (uint64_t *)ctx->stage, batch, pcount, ncomp, mode, table_base, decomp, s);
+    const size_t chunk = std::max<size_t>(1, std::min<size_t>((size_t)NTT_MAX_GROUPS, ((size_t)4 << 20) / (n * 8)));
+    const size_t nchunks = (limbs + chunk - 1) / chunk;
+    st = ensure_copy_pipeline(ctx, 2 * nchunks + 2);
     if (st != B2_OK) return st;
-    B2_CUDA(cudaMemcpyAsync(out, ctx->stage, bytes, cudaMemcpyDeviceToHost, s));
+    cudaStream_t s = (cudaStream_t)stream, s_in = ctx->s_in, s_out = ctx->s_out;
+    cudaEvent_t *ev = ctx->events.data();
+    u64 *dev = (u64 *)ctx->stage;
+    B2_CUDA(cudaEventRecord(ev[0], s));                 // copies start after the caller's earlier work on `stream`
+    B2_CUDA(cudaStreamWaitEvent(s_in, ev[0], 0));
+    std::vector<LimbGroup> groups;
+    for (size_t c = 0; c < nchunks; c++) {
+        const size_t l0 = c * chunk, l1 = std::min(limbs, l0 + chunk), cb = (l1 - l0) * n * 8;
+        B2_CUDA(cudaMemcpyAsync(dev + l0 * n, in + l0 * n, cb, cudaMemcpyHostToDevice, s_in));
+        B2_CUDA(cudaEventRecord(ev[2 + 2 * c], s_in));
+        B2_CUDA(cudaStreamWaitEvent(s, ev[2 + 2 * c], 0));
+        groups.clear();
+        for (size_t l = l0; l < l1; l++) {      // one single-limb group per limb; table as NTTTableIndexer::get picks it
+            const size_t j = l % ncomp, k = (l / ncomp) % pcount;
+            const u32 table = mode == B2_TABLES_COMPONENTWISE ? (u32)(table_base + j)
+                            : mode == B2_TABLES_KS_SET_PRODUCTS ? (u32)(k == decomp ? K - 1 : k) : (u32)(j == decomp ? K - 1 : j);
+            groups.push_back(LimbGroup{table, 1u, (u64)(l * n), 0});
+        }
+        st = run_ntt(ctx, fwd, groups, dev, PlainLoad{dev}, PlainStore{dev}, s);
+        if (st != B2_OK) return st;
+        B2_CUDA(cudaEventRecord(ev[3 + 2 * c], s));
+        B2_CUDA(cudaStreamWaitEvent(s_out, ev[3 + 2 * c], 0));
+        B2_CUDA(cudaMemcpyAsync(out + l0 * n, dev + l0 * n, cb, cudaMemcpyDeviceToHost, s_out));
+    }
+    B2_CUDA(cudaEventRecord(ev[1], s_out));
+    B2_CUDA(cudaStreamWaitEvent(s, ev[1], 0));
     B2_CUDA(cudaStreamSynchronize(s));
     return B2_OK;
 }

@@ -83,6 +83,7 @@ template <bool LAZY>
 struct ArithInt {
     typedef u64 T;
     typedef Tw TwT;
+    static constexpr bool PREFETCH = false;     // 16-byte twiddles: prefetching a layer ahead of the barrier costs too many registers
     u64 p, p2, ratio;
     Tw inv_n, inv_n_w;
     const Tw *ftab, *itab;
@@ -122,6 +123,7 @@ struct ArithInt {
 struct ArithF64 {
     typedef double T;
     typedef double TwT;
+    static constexpr bool PREFETCH = true;
     double p, pinv, inv_n, inv_n_w;
     const double *ftab, *itab;
     __device__ __forceinline__ explicit ArithF64(const ModInfo &M)
@@ -161,28 +163,58 @@ struct ArithF64 {
 };
 
 // ---- radix-16 rounds ------------------------------------------------------------------------------
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+
+// Twiddles of the first layers of a round, fetched BEFORE the barrier that precedes the round so that their L2 latency
+// overlaps the barrier wait and the shared-memory reads (forward: layers 0 and 1 = 1 + 2 entries; inverse: layer 0 = 8).
+template <int NL, int XLO, bool FWD, bool LAST, class AR>
+struct RoundTw {
+    static constexpr int PF = !AR::PREFETCH ? 0 : (FWD ? (NL < 2 ? NL : 2) : ((LAST && NL == 1) ? 0 : 1));
+    typename AR::TwT w[PF > 0 ? PF : 1][8];
+    __device__ __forceinline__ void load(const AR &ar, u32 xt, int logn) {
+#pragma unroll
+        for (int s = 0; s < PF; s++) {
+            if (FWD) {
+                const int j = NL - 1 - s;
+                const int l = logn - 1 - (XLO + j);
+                ar.ldtw_n(ar.ftab, (1u << l) + (xt >> (XLO + j + 1)), 16 >> (j + 1), w[s]);
+            } else {
+                const int j = (4 - NL) + s;
+                const int l = XLO + j;
+                const u32 n = 1u << logn;
+                ar.ldtw_n(ar.itab, n - (n >> l) + (xt >> (l + 1)), 16 >> (j + 1), w[s]);
+            }
+        }
+    }
+};
+
 // Forward (Cooley-Tukey) network on the low NL window bits (free window bits above them).
 // xt: limb-local position of register 0 (window bits clear); XLO: limb-local position of window bit 0.
-template <int NL, int XLO, class AR>
-__device__ __forceinline__ void fwd_round(const AR &ar, typename AR::T (&v)[16], u32 xt, int logn) {
+// `mid` runs once, about half way through the round (thread 0 uses it to advance the work-queue bookkeeping).
+template <int NL, int XLO, class AR, class RT, class Mid>
+__device__ __forceinline__ void fwd_round(const AR &ar, typename AR::T (&v)[16], u32 xt, int logn, const RT &rt, const Mid &mid) {
 #pragma unroll
     for (int s = 0; s < NL; s++) {
         const int j = NL - 1 - s;
         const int l = logn - 1 - (XLO + j);
         const u32 tb = (1u << l) + (xt >> (XLO + j + 1));
         typename AR::TwT w[8];
-        ar.ldtw_n(ar.ftab, tb, 16 >> (j + 1), w);
+        if (s < RT::PF) {
+#pragma unroll
+            for (int a = 0; a < 8; a++) if (a < (16 >> (j + 1))) w[a] = rt.w[s < RT::PF ? s : 0][a];
+        } else ar.ldtw_n(ar.ftab, tb, 16 >> (j + 1), w);
 #pragma unroll
         for (int k = 0; k < 16; k++) {
             if (k & (1 << j)) continue;
             ar.bf_fwd(v[k], v[k | (1 << j)], w[k >> (j + 1)]);
         }
+        if (s == (NL >= 2 ? 1 : NL - 1)) mid();
     }
 }
 
 // Inverse (Gentleman-Sande) network on the high NL window bits (free window bits below them).
-template <int NL, int XLO, bool LAST, class AR>
-__device__ __forceinline__ void inv_round(const AR &ar, typename AR::T (&v)[16], u32 xt, int logn) {
+template <int NL, int XLO, bool LAST, class AR, class RT, class Mid>
+__device__ __forceinline__ void inv_round(const AR &ar, typename AR::T (&v)[16], u32 xt, int logn, const RT &rt, const Mid &mid) {
     constexpr int OFF = 4 - NL;
     const u32 n = 1u << logn;
 #pragma unroll
@@ -198,13 +230,17 @@ __device__ __forceinline__ void inv_round(const AR &ar, typename AR::T (&v)[16],
         } else {
             const u32 tb = n - (n >> l) + (xt >> (l + 1));     // device table = inv_root_powers shifted down by one
             typename AR::TwT w[8];
-            ar.ldtw_n(ar.itab, tb, 16 >> (j + 1), w);
+            if (s < RT::PF) {
+#pragma unroll
+                for (int a = 0; a < 8; a++) if (a < (16 >> (j + 1))) w[a] = rt.w[s < RT::PF ? s : 0][a];
+            } else ar.ldtw_n(ar.itab, tb, 16 >> (j + 1), w);
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 if (k & (1 << j)) continue;
                 ar.bf_inv(v[k], v[k | (1 << j)], w[k >> (j + 1)], l);
             }
         }
+        if (s == (NL >= 2 ? 1 : NL - 1)) mid();
     }
 }
 
@@ -246,11 +282,6 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
-__device__ __forceinline__ u32 ld_acquire(const u32 *p) {
-    u32 v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 
 // Stage one tile of a limb (N contiguous words at `limb`) into `stage`: 2048 16-byte chunks, 8 per thread.
 template <int A, bool COL>
@@ -266,10 +297,16 @@ __device__ __forceinline__ void stage_tile(u64 *stage, const u64 *limb, int tile
 // One pass = one to three radix-16 rounds over a staged tile.  (LOr, NLr) per round; NLr == 0: round absent.
 //   FIRST: the pass reads external data (xf -> from_ext); otherwise it reads the raw intermediate
 //   FINAL: the pass writes canonical results; otherwise it writes the raw intermediate
+// Hooks (the persistent loop's bookkeeping, woven into the pass so that none of it sits between two barriers):
+//   hk.sync_stage()    after the modulus constants and the first twiddles have been requested: waits for the staged tile
+//                      (cp.async group + CTA barrier); thread 0 then signals the previous item and claims the next one
+//   hk.mid()           half way through round 0: thread 0 decodes the claimed item and requests its dependency counter
+//   hk.pre_exchange()  before the barrier that ends round 0: thread 0 posts (next item, ready) to shared memory
+//   hk.stage_free()    after that barrier: the stage buffer is free -> the next item's tile is staged
 template <int A, bool COL, bool FWD, bool FIRST, bool FINAL, class AR, int LO0, int NL0, int LO1, int NL1, int LO2, int NL2,
-          class Load, class Store, class Hook>
+          class Load, class Store, class Hooks>
 __device__ __forceinline__ void pass_body(const u64 *stage, u64 *sm, const ModInfo &M, int tile, int g, int c, u64 off, int logn,
-                                          const Load &ld, const Store &st, const Hook &stage_free) {
+                                          const Load &ld, const Store &st, Hooks &hk) {
     using G = Geo<A, COL>;
     typedef typename AR::T T;
     const AR ar(M);
@@ -278,11 +315,17 @@ __device__ __forceinline__ void pass_body(const u64 *stage, u64 *sm, const ModIn
     constexpr int NR = NL2 > 0 ? 3 : (NL1 > 0 ? 2 : 1);
     constexpr int LOL = NR == 3 ? LO2 : (NR == 2 ? LO1 : LO0);
     constexpr bool LASTL = FINAL && !FWD;    // the pass contains the last inverse layer
+    constexpr int N1 = NL1 > 0 ? NL1 : 1, N2 = NL2 > 0 ? NL2 : 1;
+    const NoHook nohook;
 
+    RoundTw<N1, G::xbit(LO1), FWD, LASTL && NR == 2, AR> tw1;
     {   // ---- round 0: from the stage buffer
         const int it = round_base<LO0>(t);
         const u32 xt = G::pos(tile, it);
         const int sb = swz16(it);
+        RoundTw<NL0, G::xbit(LO0), FWD, LASTL && NR == 1, AR> tw0;
+        tw0.load(ar, xt, logn);
+        hk.sync_stage();
         u64 raw[16];
         if (LO0 == 0) {
 #pragma unroll
@@ -297,27 +340,31 @@ __device__ __forceinline__ void pass_body(const u64 *stage, u64 *sm, const ModIn
 #pragma unroll
         for (int k = 0; k < 16; k++)
             v[k] = FIRST ? ar.from_ext(ld.xf(g, c, xt + ((u32)k << G::xbit(LO0)), raw[k])) : ar.from_raw(raw[k]);
-        if (FWD) fwd_round<NL0, G::xbit(LO0)>(ar, v, xt, logn);
-        else inv_round<NL0, G::xbit(LO0), LASTL && NR == 1>(ar, v, xt, logn);
+        if (FWD) fwd_round<NL0, G::xbit(LO0)>(ar, v, xt, logn, tw0, hk.mid);
+        else inv_round<NL0, G::xbit(LO0), LASTL && NR == 1>(ar, v, xt, logn, tw0, hk.mid);
         if (NR > 1) {
             const int xb = swz(it);
 #pragma unroll
             for (int k = 0; k < 16; k++) sm[xb ^ swz(k << LO0)] = ar.to_raw(v[k]);
+            tw1.load(ar, G::pos(tile, round_base<LO1>(t)), logn);
         }
     }
+    hk.pre_exchange();
     __syncthreads();   // every thread has consumed the stage buffer (and, for NR > 1, written the exchange buffer)
-    stage_free();      // -> the next item's tile is staged while this one is computed
+    hk.stage_free();   // -> the next item's tile is staged while this one is computed
+    RoundTw<N2, G::xbit(LO2), FWD, LASTL && NR == 3, AR> tw2;
     if (NR > 1) {   // ---- round 1
         const int it = round_base<LO1>(t);
         const u32 xt = G::pos(tile, it);
         const int sb = swz(it);
 #pragma unroll
         for (int k = 0; k < 16; k++) v[k] = ar.from_raw(sm[sb ^ swz(k << LO1)]);
-        if (FWD) fwd_round<(NL1 > 0 ? NL1 : 1), G::xbit(LO1)>(ar, v, xt, logn);
-        else inv_round<(NL1 > 0 ? NL1 : 1), G::xbit(LO1), LASTL && NR == 2>(ar, v, xt, logn);
+        if (FWD) fwd_round<N1, G::xbit(LO1)>(ar, v, xt, logn, tw1, nohook);
+        else inv_round<N1, G::xbit(LO1), LASTL && NR == 2>(ar, v, xt, logn, tw1, nohook);
         if (NR > 2) {     // each thread overwrites exactly the slots it has just read
 #pragma unroll
             for (int k = 0; k < 16; k++) sm[sb ^ swz(k << LO1)] = ar.to_raw(v[k]);
+            tw2.load(ar, G::pos(tile, round_base<LO2>(t)), logn);
         }
     }
     if (NR > 2) {   // ---- round 2
@@ -327,8 +374,8 @@ __device__ __forceinline__ void pass_body(const u64 *stage, u64 *sm, const ModIn
         const int sb = swz(it);
 #pragma unroll
         for (int k = 0; k < 16; k++) v[k] = ar.from_raw(sm[sb ^ swz(k << LO2)]);
-        if (FWD) fwd_round<(NL2 > 0 ? NL2 : 1), G::xbit(LO2)>(ar, v, xt, logn);
-        else inv_round<(NL2 > 0 ? NL2 : 1), G::xbit(LO2), LASTL>(ar, v, xt, logn);
+        if (FWD) fwd_round<N2, G::xbit(LO2)>(ar, v, xt, logn, tw2, nohook);
+        else inv_round<N2, G::xbit(LO2), LASTL>(ar, v, xt, logn, tw2, nohook);
     }
     {   // ---- to global memory
         const int it = round_base<LOL>(t);
@@ -388,21 +435,53 @@ __device__ __forceinline__ NttItem ntt_decode(const NttJob &J, u32 item) {
     return r;
 }
 
-template <int A, bool COL, bool FWD, bool FIRST, bool FINAL, int LO0, int NL0, int LO1, int NL1, int LO2, int NL2, class Load, class Store, class Hook>
-__device__ __forceinline__ void pass_dispatch(const u64 *stage, u64 *xch, const ModInfo &M, int tile, int g, int c, u64 off, int logn,
-                                              const Load &ld, const Store &st, const Hook &hk) {
-    const int path = M.use_f64 ? 2 : ((FWD ? M.fwd_lazy : M.inv_lazy) ? 1 : 0);
-    if (path == 2)
+// arithmetic path of a limb group, decided on the host (run_ntt) and carried in the upper half of LimbGroup::table so that
+// the kernel does not wait on a ModInfo load before it can branch
+constexpr u32 PATH_INT = 0, PATH_INT_LAZY = 1, PATH_F64 = 2;
+__host__ __device__ __forceinline__ u32 group_table(u32 tagged) { return tagged & 0xffffu; }
+__host__ __device__ __forceinline__ u32 group_path(u32 tagged, bool fwd) { return (tagged >> (fwd ? 16 : 20)) & 0xfu; }
+__host__ __device__ __forceinline__ u32 tag_table(u32 table, u32 fwd_path, u32 inv_path) { return table | (fwd_path << 16) | (inv_path << 20); }
+
+template <int A, bool COL, bool FWD, bool FIRST, bool FINAL, int LO0, int NL0, int LO1, int NL1, int LO2, int NL2, class Load, class Store, class Hooks>
+__device__ __forceinline__ void pass_dispatch(u32 path, const u64 *stage, u64 *xch, const ModInfo &M, int tile, int g, int c, u64 off, int logn,
+                                              const Load &ld, const Store &st, Hooks &hk) {
+    if (path == PATH_F64)
         pass_body<A, COL, FWD, FIRST, FINAL, ArithF64, LO0, NL0, LO1, NL1, LO2, NL2>(stage, xch, M, tile, g, c, off, logn, ld, st, hk);
-    else if (path == 1)
+    else if (path == PATH_INT_LAZY)
         pass_body<A, COL, FWD, FIRST, FINAL, ArithInt<true>, LO0, NL0, LO1, NL1, LO2, NL2>(stage, xch, M, tile, g, c, off, logn, ld, st, hk);
     else
         pass_body<A, COL, FWD, FIRST, FINAL, ArithInt<false>, LO0, NL0, LO1, NL1, LO2, NL2>(stage, xch, M, tile, g, c, off, logn, ld, st, hk);
 }
 
+__device__ __forceinline__ u32 ld_relaxed(const u32 *p) {      // L2 load, no L1 invalidation (cf. ld.acquire -> CCTL.IVALL)
+    u32 v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release(u32 *p) {          // MEMBAR.ALL.GPU + REDG: orders the CTA's stores (seen through the barrier) before the signal
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(p) : "memory");
+}
+__device__ __forceinline__ u32 claim(u32 *queue) {
+    u32 v;
+    asm volatile("atom.relaxed.gpu.global.add.u32 %0, [%1], 1;\n" : "=r"(v) : "l"(queue) : "memory");
+    return v;
+}
+
+template <class F0, class F1, class F2, class F3>
+struct PassHooks { F0 sync_stage; F1 mid; F2 pre_exchange; F3 stage_free; };
+template <class F0, class F1, class F2, class F3>
+__device__ __forceinline__ PassHooks<F0, F1, F2, F3> make_hooks(F0 a, F1 b, F2 c, F3 d) { return PassHooks<F0, F1, F2, F3>{a, b, c, d}; }
+
 // The persistent transform kernel.  FWD: first pass = column pass (reads the operand through `ld`), second
 // pass = row pass (writes through `st`); inverse: first pass = row pass, second pass = column pass.
 // OCC = resident CTAs per SM the register allocation is held to.
+//
+// Synchronisation between CTAs: done[l] counts the finished first-pass tiles of limb l.  A producer signals with
+// red.release after a CTA barrier; a consumer polls with a relaxed L2 load, passes a CTA barrier and then reads the
+// intermediate with cp.async.cg (L2, never L1), so no L1 invalidation is needed (ld.acquire would flush the SM's L1 — and
+// with it the twiddles — once per item).
+// Per item there are two CTA barriers (tile staged / exchange) and the queue bookkeeping of thread 0 is spread over the
+// item: claim after the first barrier, dependency load in the middle of round 0, hand-over at the second barrier.
 template <int A, bool FWD, int OCC, class Load, class Store>
 __global__ void __launch_bounds__(NTT_THREADS, OCC) ntt_persistent_kernel(const __grid_constant__ NttJob J, Load ld, Store st) {
     extern __shared__ __align__(128) u64 smem[];
@@ -428,68 +507,81 @@ __global__ void __launch_bounds__(NTT_THREADS, OCC) ntt_persistent_kernel(const 
         }
         cp_async_commit();
     };
-    auto compute_item = [&](const NttItem &it, const auto &hook) {
-        const u32 c = it.limb / (u32)J.n_groups, g = it.limb - c * (u32)J.n_groups;
-        const LimbGroup &grp = J.groups[g];
-        const u64 off = grp.base + (u64)c * grp.stride;
-        const ModInfo &M = J.mods[grp.table];
-        const int ga = J.g_base + (int)g;
-        if (FWD) {
-            using Pl = FwdColPlan<A>;
-            if (it.phase == 0)
-                pass_dispatch<A, true, true, true, false, Pl::LO0, Pl::NL0, Pl::LO1, Pl::NL1, Pl::LO2, Pl::NL2>(stage, xch, M, (int)it.tile, ga, (int)c, off, J.logn, ld, mid_st, hook);
-            else
-                pass_dispatch<8, false, true, false, true, 4, 4, 0, 4, 0, 0>(stage, xch, M, (int)it.tile, ga, (int)c, off, J.logn, mid_ld, st, hook);
-        } else {
-            using Pl = InvColPlan<A>;
-            if (it.phase == 0)
-                pass_dispatch<8, false, false, true, false, 0, 4, 4, 4, 0, 0>(stage, xch, M, (int)it.tile, ga, (int)c, off, J.logn, ld, mid_st, hook);
-            else
-                pass_dispatch<A, true, false, false, true, Pl::LO0, Pl::NL0, Pl::LO1, Pl::NL1, Pl::LO2, Pl::NL2>(stage, xch, M, (int)it.tile, ga, (int)c, off, J.logn, mid_ld, st, hook);
-        }
-    };
 
     // ---- prologue: claim the first item and stage it (blocking on its dependency)
     if (t == 0) {
-        const u32 i0 = atomicAdd(queue, 1u);
+        const u32 i0 = claim(queue);
         s_item = i0;
         if (i0 < total) {
             const NttItem it = ntt_decode(J, i0);
-            if (it.phase) while (ld_acquire(done + it.limb) < tiles) __nanosleep(100);
+            if (it.phase) while (ld_relaxed(done + it.limb) < tiles) __nanosleep(100);
         }
     }
     __syncthreads();
-    u32 cur_id = s_item;
-    if (cur_id < total) {
-        NttItem cur = ntt_decode(J, cur_id);
+    const u32 first_id = s_item;
+    if (first_id < total) {
+        NttItem cur = ntt_decode(J, first_id), nxt = cur;
         stage_item(cur);
+        __syncthreads();              // s_item has been read by everyone before thread 0 posts the next one
+        // thread-0 bookkeeping registers
         bool publish = false; u32 publish_limb = 0;       // a finished first-pass item whose completion is not yet signalled
-        while (true) {
-            __syncthreads();          // previous item's stores and exchange reads are complete CTA-wide
-            if (t == 0) {
-                if (publish) { __threadfence(); atomicAdd(done + publish_limb, 1u); }
-                const u32 nx = atomicAdd(queue, 1u);
-                u32 ready = 0;
-                if (nx < total) {
-                    const NttItem ni = ntt_decode(J, nx);
-                    ready = (ni.phase == 0 || ld_acquire(done + ni.limb) >= tiles) ? 1u : 0u;
+        u32 nx = 0, dep = 0; bool has_dep = false;
+        u32 nxt_id = 0; bool pre = false;
+        auto hooks = make_hooks(
+            [&]() {   // sync_stage
+                cp_async_wait_all();
+                __syncthreads();      // tile staged and visible; the previous item's stores and exchange reads are complete CTA-wide
+                if (t == 0) {
+                    if (publish) red_release(done + publish_limb);
+                    nx = claim(queue);
                 }
-                s_item = nx; s_ready = ready;
+            },
+            [&]() {   // mid
+                if (t == 0) {
+                    has_dep = false;
+                    if (nx < total) {
+                        const NttItem ni = ntt_decode(J, nx);
+                        if (ni.phase) { has_dep = true; dep = ld_relaxed(done + ni.limb); }
+                    }
+                }
+            },
+            [&]() {   // pre_exchange
+                if (t == 0) { s_item = nx; s_ready = (nx < total && (!has_dep || dep >= tiles)) ? 1u : 0u; }
+            },
+            [&]() {   // stage_free
+                nxt_id = s_item; pre = s_ready != 0;
+                if (nxt_id < total) nxt = ntt_decode(J, nxt_id);
+                if (pre) stage_item(nxt);
+            });
+        while (true) {
+            {
+                const u32 c = cur.limb / (u32)J.n_groups, g = cur.limb - c * (u32)J.n_groups;
+                const LimbGroup &grp = J.groups[g];
+                const u64 off = grp.base + (u64)c * grp.stride;
+                const ModInfo &M = J.mods[group_table(grp.table)];
+                const u32 path = group_path(grp.table, FWD);
+                const int ga = J.g_base + (int)g;
+                if (FWD) {
+                    using Pl = FwdColPlan<A>;
+                    if (cur.phase == 0)
+                        pass_dispatch<A, true, true, true, false, Pl::LO0, Pl::NL0, Pl::LO1, Pl::NL1, Pl::LO2, Pl::NL2>(path, stage, xch, M, (int)cur.tile, ga, (int)c, off, J.logn, ld, mid_st, hooks);
+                    else
+                        pass_dispatch<8, false, true, false, true, 4, 4, 0, 4, 0, 0>(path, stage, xch, M, (int)cur.tile, ga, (int)c, off, J.logn, mid_ld, st, hooks);
+                } else {
+                    using Pl = InvColPlan<A>;
+                    if (cur.phase == 0)
+                        pass_dispatch<8, false, false, true, false, 0, 4, 4, 4, 0, 0>(path, stage, xch, M, (int)cur.tile, ga, (int)c, off, J.logn, ld, mid_st, hooks);
+                    else
+                        pass_dispatch<A, true, false, false, true, Pl::LO0, Pl::NL0, Pl::LO1, Pl::NL1, Pl::LO2, Pl::NL2>(path, stage, xch, M, (int)cur.tile, ga, (int)c, off, J.logn, mid_ld, st, hooks);
+                }
             }
-            cp_async_wait_all();
-            __syncthreads();          // stage complete and visible; next item known
-            const u32 nxt_id = s_item;
-            const bool pre = s_ready != 0;
-            NttItem nxt = cur;
-            if (nxt_id < total) nxt = ntt_decode(J, nxt_id);
-            compute_item(cur, [&]() { if (pre) stage_item(nxt); });
             publish = cur.phase == 0; publish_limb = cur.limb;
             if (nxt_id >= total) break;
             if (!pre) {               // dependency not met at prefetch time: signal our own completion, then wait
                 __syncthreads();
                 if (t == 0) {
-                    if (publish) { __threadfence(); atomicAdd(done + publish_limb, 1u); }
-                    while (ld_acquire(done + nxt.limb) < tiles) __nanosleep(100);
+                    if (publish) red_release(done + publish_limb);
+                    while (ld_relaxed(done + nxt.limb) < tiles) __nanosleep(100);
                 }
                 publish = false;
                 __syncthreads();
@@ -498,7 +590,7 @@ __global__ void __launch_bounds__(NTT_THREADS, OCC) ntt_persistent_kernel(const 
             cur = nxt;
         }
         __syncthreads();
-        if (t == 0 && publish) { __threadfence(); atomicAdd(done + publish_limb, 1u); }
+        if (t == 0 && publish) red_release(done + publish_limb);
     }
     // ---- teardown: the last CTA to finish resets the queue and the counters for the next launch
     if (t == 0) {

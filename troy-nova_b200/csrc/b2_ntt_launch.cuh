@@ -15,7 +15,7 @@ __global__ void ntt_small_kernel(const __grid_constant__ NttJob P, Load ld, Stor
     const LimbGroup &grp = P.groups[blockIdx.y];
     const int c = blockIdx.x;
     if (c >= (int)grp.count) return;
-    const ModInfo M = P.mods[grp.table];
+    const ModInfo M = P.mods[group_table(grp.table)];
     const u64 off = grp.base + (u64)c * grp.stride;
     const int logn = P.logn, n = 1 << logn, half = n >> 1;
     const int g = P.g_base + (int)blockIdx.y;
@@ -53,8 +53,9 @@ __global__ void ntt_small_kernel(const __grid_constant__ NttJob P, Load ld, Stor
 }
 
 // second-pass items trail first-pass items by this many limbs: at N = 2^16 the in-flight intermediate is
-// NTT_LAG x 512 KiB = 16 MiB, far inside the 126 MB L2, and ~600 items (2 per resident CTA) are ~19 limbs.
-static constexpr u32 NTT_LAG = 32;
+// NTT_LAG x 512 KiB = 24 MiB, far inside the 126 MB L2; 888 items in flight (one being computed + one prefetched per
+// resident CTA) are ~28 limbs, so a lag of 32 left 29 % of the second-pass items waiting on their dependency (ncu, r01c).
+static constexpr u32 NTT_LAG = 48;
 
 #ifndef B2_NTT_OCC
 #define B2_NTT_OCC 3
@@ -91,7 +92,12 @@ static b2_status run_ntt(b2_ctx *ctx, bool forward, const std::vector<LimbGroup>
         const size_t ng = std::min(groups.size() - g0, (size_t)NTT_MAX_GROUPS);
         P.g_base = (int)g0;
         P.n_groups = (int)ng;
-        for (size_t g = 0; g < ng; g++) P.groups[g] = groups[g0 + g];
+        for (size_t g = 0; g < ng; g++) {
+            P.groups[g] = groups[g0 + g];
+            const ModInfo &M = ctx->h_mods[groups[g0 + g].table];
+            P.groups[g].table = tag_table(groups[g0 + g].table, M.use_f64 ? PATH_F64 : (M.fwd_lazy ? PATH_INT_LAZY : PATH_INT),
+                                          M.use_f64 ? PATH_F64 : (M.inv_lazy ? PATH_INT_LAZY : PATH_INT));
+        }
         if (logn <= 11) {
             const int threads = (int)std::max<size_t>(32, std::min<size_t>(n / 2, 1024));
             dim3 grid(P.count, (unsigned)ng);
