@@ -92,28 +92,6 @@ extern "C" b2_status b2_ctx_create(int device, const b2_params *prm, b2_ctx **ou
     B2_CUDA(cudaMemcpy(c->d_itw, itw.data(), K * n * sizeof(Tw), cudaMemcpyHostToDevice));
     B2_CUDA(cudaMemcpy(c->d_twd, twd.data(), K * n * sizeof(double), cudaMemcpyHostToDevice));
     B2_CUDA(cudaMemcpy(c->d_itwd, itwd.data(), K * n * sizeof(double), cudaMemcpyHostToDevice));
-    if (logn >= 8) {    // row-major copies of the FP64 tables (ModInfo::twrow / itwrow): the 255 twiddles a 256-coefficient row needs, contiguous
-        std::vector<double> twrow(K * n, 0.0), itwrow(K * n, 0.0);
-        const size_t rows = n >> 8; const unsigned A = logn - 8;
-        for (size_t i = 0; i < K; i++) {
-            const double *TD = &twd[i * n], *ITD = &itwd[i * n];
-            double *TR = &twrow[i * n], *ITR = &itwrow[i * n];
-            for (size_t r = 0; r < rows; r++)
-                for (unsigned s = 0; s < 8; s++)
-                    for (size_t a = 0; a < ((size_t)1 << s); a++) {
-                        TR[r * 256 + ((size_t)1 << s) + a] = TD[((size_t)1 << (A + s)) + r * ((size_t)1 << s) + a];
-                        const unsigned l = 7 - s;       // inverse layer l has 2^(7-l) = 2^s twiddles per row
-                        ITR[r * 256 + ((size_t)1 << s) + a] = ITD[n - (n >> l) + r * ((size_t)1 << s) + a];
-                    }
-        }
-        if ((ce = cudaMalloc(&c->d_twrow, K * n * sizeof(double))) != cudaSuccess || (ce = cudaMalloc(&c->d_itwrow, K * n * sizeof(double))) != cudaSuccess) {
-            b2_ctx_destroy(c);
-            return cuda_fail(ce, "cudaMalloc(row tables)");
-        }
-        B2_CUDA(cudaMemcpy(c->d_twrow, twrow.data(), K * n * sizeof(double), cudaMemcpyHostToDevice));
-        B2_CUDA(cudaMemcpy(c->d_itwrow, itwrow.data(), K * n * sizeof(double), cudaMemcpyHostToDevice));
-        for (size_t i = 0; i < K; i++) { c->h_mods[i].twrow = c->d_twrow + i * n; c->h_mods[i].itwrow = c->d_itwrow + i * n; }
-    }
     B2_CUDA(cudaMemcpy(c->d_mods, c->h_mods.data(), K * sizeof(ModInfo), cudaMemcpyHostToDevice));
     // cross-modulus inverses used by mod-down / rescale (reference: RNSTool::inv_q_last_mod_q, inv_q_last_mod_t,
     // src/utils/rns_tool.cu:214-231 — one RNSTool per level there, one K x K table here)
@@ -142,7 +120,7 @@ extern "C" b2_status b2_ctx_create(int device, const b2_params *prm, b2_ctx **ou
 extern "C" void b2_ctx_destroy(b2_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaFree(c->d_tw); cudaFree(c->d_itw); cudaFree(c->d_twd); cudaFree(c->d_itwd); cudaFree(c->d_twrow); cudaFree(c->d_itwrow); cudaFree(c->d_mods); b2::behz_release(c); cudaFree(c->d_inv); cudaFree(c->d_inv_mod_t); cudaFree(c->d_galois); cudaFree(c->ws); cudaFree(c->stage); cudaFree(c->d_sync);
+    cudaFree(c->d_tw); cudaFree(c->d_itw); cudaFree(c->d_twd); cudaFree(c->d_itwd); cudaFree(c->d_mods); b2::behz_release(c); cudaFree(c->d_inv); cudaFree(c->d_inv_mod_t); cudaFree(c->d_galois); cudaFree(c->ws); cudaFree(c->stage); cudaFree(c->d_sync);
     for (cudaEvent_t e : c->events) cudaEventDestroy(e);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);

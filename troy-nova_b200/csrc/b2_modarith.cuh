@@ -109,10 +109,7 @@ struct ModInfo {
     const double *twd, *itwd;
     double pd, pinv, inv_n_d, inv_n_w_d;
     u32 use_f64, bits;
-    // row-major copies of the FP64 tables for the row pass of the warp kernel (b2_ntt_warp.cuh), R = N / 256 rows of
-    // 256 entries: twrow[r][2^s + i] = twd[2^(logN-8+s) + r 2^s + i], itwrow[r][2^(7-l) + i] = itwd[N - (N >> l) + r 2^(7-l) + i]
-    const double *twrow, *itwrow;
-    u64 pad[12];
+    u64 pad[14];
 };
 static_assert(sizeof(ModInfo) == 256, "ModInfo must be 256 bytes");
 

@@ -2,11 +2,9 @@
 // Included by every translation unit that launches a transform (b2_ntt.cu, b2_keyswitch.cu, b2_rescale.cu).
 #pragma once
 #include <algorithm>
-#include <cstdlib>
 #include <vector>
 #include "b2_ctx.h"
 #include "b2_ntt.cuh"
-#include "b2_ntt_warp.cuh"
 
 namespace b2 {
 
@@ -76,24 +74,6 @@ static cudaError_t launch_persistent(const NttJob &J, unsigned grid, cudaStream_
     return cudaGetLastError();
 }
 
-// N = 2^16: warp-autonomous kernel (b2_ntt_warp.cuh), one persistent CTA of 16 warps per SM
-template <bool FWD, class Load, class Store>
-static cudaError_t launch_warp(const NttJob &J, unsigned grid, cudaStream_t s, Load ld, Store st) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(ntt_warp_kernel<FWD, Load, Store>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    ntt_warp_kernel<FWD, Load, Store><<<grid, W_THREADS, W_SMEM_BYTES, s>>>(J, ld, st);
-    return cudaGetLastError();
-}
-// developer switch: B2_NTT_TILE=1 forces the CTA-tile kernel at N = 2^16 (A/B timing); never set in production
-static inline bool use_warp_kernel(unsigned logn) {
-    static const bool force_tile = getenv("B2_NTT_TILE") != nullptr;
-    return logn == 16 && !force_tile;
-}
-
 // groups' base/stride address the intermediate buffer `mid` (raw values between the passes); the
 // functors map (group, limb) to wherever the external operands live.  All groups must have the same count.
 template <class Load, class Store>
@@ -125,20 +105,6 @@ static b2_status run_ntt(b2_ctx *ctx, bool forward, const std::vector<LimbGroup>
             else ntt_small_kernel<false><<<grid, threads, n * 8, stream>>>(P, ld, st);
             count_launches(1);
             B2_CUDA(cudaGetLastError());
-            continue;
-        }
-        if (use_warp_kernel(logn)) {
-            P.tile_shift = W_ITEM_SHIFT;
-            P.n_limbs = (u32)(ng * P.count);
-            P.lag = std::min<u32>(NTT_LAG, P.n_limbs);
-            P.total_items = (P.n_limbs << P.tile_shift) * 2;
-            b2_status s = ensure_sync(ctx, P.n_limbs, stream);
-            if (s != B2_OK) return s;
-            P.sync = ctx->d_sync;
-            const unsigned grid = std::min<unsigned>((P.total_items + W_WARPS - 1) / W_WARPS, (unsigned)ctx->sm_count);
-            cudaError_t e = forward ? launch_warp<true>(P, grid, stream, ld, st) : launch_warp<false>(P, grid, stream, ld, st);
-            count_launches(1);
-            B2_CUDA(e);
             continue;
         }
         const int A = (int)logn - 8;
