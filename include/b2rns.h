@@ -127,6 +127,21 @@ b2_status b2_keyswitch(b2_ctx *ctx, const uint64_t *target, size_t decomp, int i
 b2_status b2_keyswitch_batched(b2_ctx *ctx, const uint64_t *const *targets, uint64_t *const *dests, size_t batch, size_t decomp, int is_ntt,
                                const b2_kswitch_key *key, int assign, void *stream);
 
+/* ---- limb-sharded keyswitch across the GPUs of one box (no counterpart in the reference, which only
+ * replicates whole contexts per device).  The decomp + 1 output moduli of Evaluator::switch_key_internal
+ * (src/evaluator_keyswitching_core.cu:757-1052) are partitioned over `world` ranks; each rank keeps only its moduli's
+ * ciphertext limbs ([poly][owned limbs][N]) and key rows.  Per keyswitch: prepare -> all-gather (caller, NCCL) ->
+ * products -> broadcast of u from the special prime's owner (caller) -> finish.  Bit-identical to b2_keyswitch. */
+b2_status b2_limb_partition(size_t n_out_moduli, int world, int rank, size_t *first, size_t *count);
+b2_status b2_kswitch_key_shard(b2_ctx *ctx, const b2_kswitch_key *full, size_t decomp, size_t first, size_t count, b2_kswitch_key **out);
+b2_status b2_keyswitch_shard_prepare(b2_ctx *ctx, const uint64_t *target_local /* [owned ct limbs][N] */, size_t decomp, int is_ntt,
+                                     size_t first, size_t count, uint64_t *send /* [pad][N] */, void *stream);
+b2_status b2_keyswitch_shard_products(b2_ctx *ctx, const uint64_t *gathered /* [world][pad][N] */, int world, size_t pad, size_t decomp,
+                                      size_t first, size_t count, const b2_kswitch_key *shard, uint64_t *u /* [2][N] */, void *stream);
+b2_status b2_keyswitch_shard_finish(b2_ctx *ctx, const uint64_t *u /* [2][N] */, size_t decomp, int is_ntt, size_t first, size_t count,
+                                    uint64_t *dest_local /* [2][owned ct limbs][N] */, int assign, void *stream);
+
+
 /* ---- R1-R4: mod_switch_to_next / rescale_to_next (src/evaluator_modswitch.cu:14-149,445-461).
  *      in [count][nl][N] -> out [count][nl-1][N]; kind is a b2_modswitch_kind. ---- */
 b2_status b2_mod_switch_to_next(b2_ctx *ctx, const uint64_t *in, uint64_t *out, size_t count, size_t nl, int kind, void *stream);

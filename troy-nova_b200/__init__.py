@@ -63,6 +63,11 @@ _SIGS.update({
     "b2_kswitch_key_destroy": (None, [vp]),
     "b2_keyswitch": (C.c_int, [vp, vp, C.c_size_t, C.c_int, vp, vp, C.c_int, vp]),
     "b2_keyswitch_batched": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.c_size_t, C.c_size_t, C.c_int, vp, C.c_int, vp]),
+    "b2_limb_partition": (C.c_int, [C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "b2_kswitch_key_shard": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(vp)]),
+    "b2_keyswitch_shard_prepare": (C.c_int, [vp, vp, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t, vp, vp]),
+    "b2_keyswitch_shard_products": (C.c_int, [vp, vp, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, vp, vp, vp]),
+    "b2_keyswitch_shard_finish": (C.c_int, [vp, vp, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t, vp, C.c_int, vp]),
     "b2_mod_switch_to_next": (C.c_int, [vp, vp, vp, C.c_size_t, C.c_size_t, C.c_int, vp]),
     "b2_add": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp]),
     "b2_sub": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp]),
@@ -116,6 +121,13 @@ def coeff_modulus_create(n, bits):
     out = (C.c_uint64 * len(bits))()
     _chk(lib().b2_coeff_modulus_create(n, (C.c_uint32 * len(bits))(*bits), len(bits), out))
     return [int(x) for x in out]
+
+
+def limb_partition(n_out_moduli, world, rank):
+    """(first, count) of the output moduli 0..n_out_moduli-1 owned by `rank` (host-only; b2_limb_partition)."""
+    f, c = C.c_size_t(), C.c_size_t()
+    _chk(lib().b2_limb_partition(n_out_moduli, world, rank, C.byref(f), C.byref(c)))
+    return int(f.value), int(c.value)
 
 
 def _dptr(x):
@@ -199,6 +211,21 @@ class Context:
         tp = (vp * nb)(*[_dptr(t) for t in targets]); dp = (vp * nb)(*[_dptr(d) for d in dests])
         _chk(self.L.b2_keyswitch_batched(self.h, tp, dp, nb, decomp, int(is_ntt), key.h, assign, self._stream(stream)))
         return dests
+
+    # limb-sharded keyswitch stages (multi-GPU, see troy-nova_b200/sharded.py) -------------------
+    def kswitch_key_shard(self, full_key, decomp, first, count):
+        h = vp()
+        _chk(self.L.b2_kswitch_key_shard(self.h, full_key.h, decomp, first, count, C.byref(h)))
+        return KSwitchKey(self, h, None)
+
+    def keyswitch_shard_prepare(self, target_local, decomp, is_ntt, first, count, send, stream=None):
+        _chk(self.L.b2_keyswitch_shard_prepare(self.h, _dptr(target_local), decomp, int(is_ntt), first, count, _dptr(send), self._stream(stream)))
+
+    def keyswitch_shard_products(self, gathered, world, pad, decomp, first, count, shard, u, stream=None):
+        _chk(self.L.b2_keyswitch_shard_products(self.h, _dptr(gathered), world, pad, decomp, first, count, shard.h, _dptr(u), self._stream(stream)))
+
+    def keyswitch_shard_finish(self, u, decomp, is_ntt, first, count, dest_local, assign=ASSIGN_OVERWRITE, stream=None):
+        _chk(self.L.b2_keyswitch_shard_finish(self.h, _dptr(u), decomp, int(is_ntt), first, count, _dptr(dest_local), assign, self._stream(stream)))
 
     # R1-R4 -------------------------------------------------------------------------------------
     def mod_switch_to_next(self, src, dst, count, nl, kind, stream=None):

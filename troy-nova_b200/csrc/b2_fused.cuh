@@ -34,8 +34,9 @@ struct ModDownTerm {
 };
 struct ModDownLoad {      // NTT-form path: the transform's input IS the term
     ModDownTerm T;
+    u32 jbase = 0;        // modulus index of group 0 (limb-sharded calls transform a sub-range of the moduli)
     __device__ __forceinline__ const u64 *src(int, int c, u64) const { return T.u + (u64)c * T.n; }
-    __device__ __forceinline__ u64 xf(int g, int, u32, u64 raw) const { return T.term_of(g, raw); }
+    __device__ __forceinline__ u64 xf(int g, int, u32, u64 raw) const { return T.term_of(g + (int)jbase, raw); }
 };
 // batches are passed to the kernels BY VALUE as small pointer tables (no per-call device upload of pointer arrays,
 // cf. the reference's construct_batch, src/utils/box_batch.h:222-247); larger batches are processed in chunks
@@ -52,6 +53,9 @@ struct ModDownStore {
     PtrTabW dest;         // per ciphertext: [2][decomp][N]
     u32 decomp, assign;
     int t_from_transform; // 1: transformed value is t (NTT-form ciphertext); 0: transformed value is s, t computed here
+    // geometry (defaults = the whole modulus range on one GPU): group g is modulus jbase + g, row g of the prod_rows rows
+    // of each polynomial of `prod` and row g of the dest_rows rows of each polynomial of the destination
+    u32 jbase, prod_rows, dest_rows;
     __device__ __forceinline__ u64 one(int j, u64 q, u64 s, u64 v, u64 uv, u64 d, bool add) const {
         u64 t;
         if (t_from_transform) t = v;
@@ -59,23 +63,25 @@ struct ModDownStore {
         const u64 r = shoup(submod(s, t, q), pinv[j], q);
         return add ? addmod(d, r, q) : r;
     }
-    __device__ __forceinline__ void operator()(int j, int c, u64, u32 x, u64 v) const {
+    __device__ __forceinline__ void operator()(int g, int c, u64, u32 x, u64 v) const {
+        const int j = g + (int)jbase;
         const u64 q = T.mods[j].p, n = T.n;
         const int k = c & 1;
         const bool add = assign == B2_ASSIGN_ADD_INPLACE || (k == 0 && assign == B2_ASSIGN_OVERWRITE_EXCEPT_FIRST);
-        u64 *d = dest.p[c >> 1] + ((u64)k * decomp + j) * n + x;
-        const u64 s = t_from_transform ? prod[((u64)c * (decomp + 1) + j) * n + x] : 0;
+        u64 *d = dest.p[c >> 1] + ((u64)k * dest_rows + g) * n + x;
+        const u64 s = t_from_transform ? prod[((u64)c * prod_rows + g) * n + x] : 0;
         const u64 uv = t_from_transform ? 0 : T.u[(u64)c * n + x];
         *d = one(j, q, s, v, uv, add ? *d : 0, add);
     }
     // two adjacent coefficients: 16-byte accesses to prod / u / dest
-    __device__ __forceinline__ void st2(int j, int c, u64, u32 x, u64 v0, u64 v1) const {
+    __device__ __forceinline__ void st2(int g, int c, u64, u32 x, u64 v0, u64 v1) const {
+        const int j = g + (int)jbase;
         const u64 q = T.mods[j].p, n = T.n;
         const int k = c & 1;
         const bool add = assign == B2_ASSIGN_ADD_INPLACE || (k == 0 && assign == B2_ASSIGN_OVERWRITE_EXCEPT_FIRST);
-        ulonglong2 *d = reinterpret_cast<ulonglong2 *>(dest.p[c >> 1] + ((u64)k * decomp + j) * n + x);
+        ulonglong2 *d = reinterpret_cast<ulonglong2 *>(dest.p[c >> 1] + ((u64)k * dest_rows + g) * n + x);
         ulonglong2 s = make_ulonglong2(0, 0), uv = make_ulonglong2(0, 0), dv = make_ulonglong2(0, 0);
-        if (t_from_transform) s = *reinterpret_cast<const ulonglong2 *>(prod + ((u64)c * (decomp + 1) + j) * n + x);
+        if (t_from_transform) s = *reinterpret_cast<const ulonglong2 *>(prod + ((u64)c * prod_rows + g) * n + x);
         else uv = *reinterpret_cast<const ulonglong2 *>(T.u + (u64)c * n + x);
         if (add) dv = *d;
         *d = make_ulonglong2(one(j, q, s.x, v0, uv.x, dv.x, add), one(j, q, s.y, v1, uv.y, dv.y, add));

@@ -17,15 +17,20 @@
 //      For coefficient-form (BFV) ciphertexts the same happens around INTT(prod[k][j]).
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 #include "b2_ntt_launch.cuh"
 #include "b2_fused.cuh"
 
 using namespace b2;
 
 struct b2_kswitch_key {
-    const uint64_t **d_ptrs = nullptr;   // device array of D digit base pointers, each [2][K][N] NTT form
+    const uint64_t **d_ptrs = nullptr;   // device array of D digit base pointers, each [2][rows][N] NTT form
+    std::vector<const uint64_t *> h_ptrs; // host copy of the same pointers
     size_t digits = 0;
     int device = 0;
+    // limb shard (b2_kswitch_key_shard): rows first .. first+count-1 of the output moduli 0..decomp only, owned storage
+    uint64_t *own = nullptr;
+    size_t rows = 0, first = 0, decomp = 0;   // rows == 0: a full key ([2][K][N] per digit)
 };
 
 namespace b2 {
@@ -43,12 +48,14 @@ struct ModUpLoad {
     PtrTab tc;
     const ModInfo *mods;
     u32 decomp, K, n;
+    u32 g0;          // output modulus of group 0 (limb-sharded calls transform a sub-range of the output moduli)
     __device__ __forceinline__ const u64 *src(int, int c, u64) const {
         const u32 b = (u32)c / decomp, j = (u32)c - b * decomp;
         return tc.p[b] + (u64)j * n;
     }
     __device__ __forceinline__ u64 xf(int g, int c, u32, u64 v) const {
-        const u32 ki = (u32)g == decomp ? K - 1 : (u32)g;
+        const u32 i = (u32)g + g0;
+        const u32 ki = i == decomp ? K - 1 : i;
         const u32 j = (u32)c % decomp;
         const u64 m = mods[ki].p;
         // q_j <= m_i: already canonical modulo m_i
@@ -62,10 +69,12 @@ struct ModUpLoad {
 // rows are co-scheduled and all but the first hit in L2.
 __global__ void __launch_bounds__(256) ks_inner_product_kernel(const u64 *__restrict__ temp, const u64 *const *__restrict__ keys,
                                                                  u64 *__restrict__ prod, const ModInfo *__restrict__ mods,
-                                                                 u32 decomp, u32 K, u32 n) {
+                                                                 u32 decomp, u32 K, u32 n, u32 i0, u32 key_rows) {
     const u32 b = blockIdx.x, nb = gridDim.x;
-    const u32 i = blockIdx.z;                       // output modulus index 0..decomp
-    const u32 ki = i == decomp ? K - 1 : i;
+    const u32 il = blockIdx.z;                      // local output modulus index; the modulus is i0 + il in 0..decomp
+    const u32 i = il;
+    const u32 ki = i0 + il == decomp ? K - 1 : i0 + il;
+    const u32 krow = key_rows == K ? ki : il;       // full key: row of the key-level modulus; limb shard: local row
     const u32 x = (blockIdx.y * blockDim.x + threadIdx.x) * 2;
     if (x >= n) return;
     const ModInfo &M = mods[ki];
@@ -74,10 +83,10 @@ __global__ void __launch_bounds__(256) ks_inner_product_kernel(const u64 *__rest
     const u64 *tp = temp + (((u64)i * nb + b) * decomp) * n + x;
     for (u32 j = 0; j < decomp; j++) {
         const ulonglong2 d = __ldcs(reinterpret_cast<const ulonglong2 *>(tp + (u64)j * n));   // streamed once: evict-first
-        const u64 *kp = keys[j] + (u64)ki * n + x;
+        const u64 *kp = keys[j] + (u64)krow * n + x;
         ulonglong2 k0, k1;
-        if (nb == 1) { k0 = __ldcs(reinterpret_cast<const ulonglong2 *>(kp)); k1 = __ldcs(reinterpret_cast<const ulonglong2 *>(kp + (u64)K * n)); }
-        else { k0 = __ldg(reinterpret_cast<const ulonglong2 *>(kp)); k1 = __ldg(reinterpret_cast<const ulonglong2 *>(kp + (u64)K * n)); }
+        if (nb == 1) { k0 = __ldcs(reinterpret_cast<const ulonglong2 *>(kp)); k1 = __ldcs(reinterpret_cast<const ulonglong2 *>(kp + (u64)key_rows * n)); }
+        else { k0 = __ldg(reinterpret_cast<const ulonglong2 *>(kp)); k1 = __ldg(reinterpret_cast<const ulonglong2 *>(kp + (u64)key_rows * n)); }
         mac128(a0l, a0h, d.x, k0.x); mac128(a1l, a1h, d.y, k0.y);
         mac128(b0l, b0h, d.x, k1.x); mac128(b1l, b1h, d.y, k1.y);
         if ((j & 7) == 7) {     // keep the lazy 128-bit sums below 2^125 (8 products of 61-bit residues)
@@ -85,7 +94,7 @@ __global__ void __launch_bounds__(256) ks_inner_product_kernel(const u64 *__rest
             b0l = barrett128(b0l, b0h, p, r0, r1); b0h = 0; b1l = barrett128(b1l, b1h, p, r0, r1); b1h = 0;
         }
     }
-    const u32 R = decomp + 1;
+    const u32 R = gridDim.z;
     ulonglong2 o0, o1;
     o0.x = barrett128(a0l, a0h, p, r0, r1); o0.y = barrett128(a1l, a1h, p, r0, r1);
     o1.x = barrett128(b0l, b0h, p, r0, r1); o1.y = barrett128(b1l, b1h, p, r0, r1);
@@ -93,14 +102,14 @@ __global__ void __launch_bounds__(256) ks_inner_product_kernel(const u64 *__rest
     *reinterpret_cast<ulonglong2 *>(prod + (((u64)b * 2 + 1) * R + i) * n + x) = o1;
 }
 
-struct SpecialLoad {      // step 4: the special-prime limb of prod[b][k], c = 2 b + k
+struct SpecialLoad {      // step 4: the special-prime limb of prod[b][k], c = 2 b + k (row `decomp` of R rows)
     const u64 *prod; u32 R, decomp, n;
     __device__ __forceinline__ const u64 *src(int, int c, u64) const { return prod + ((u64)c * R + decomp) * n; }
     __device__ __forceinline__ u64 xf(int, int, u32, u64 raw) const { return raw; }
 };
-struct ProdLoad {         // coefficient-form path: transform prod[b][k][j] itself (inverse NTT)
-    const u64 *prod; u32 decomp, n;
-    __device__ __forceinline__ const u64 *src(int j, int c, u64) const { return prod + ((u64)c * (decomp + 1) + j) * n; }
+struct ProdLoad {         // coefficient-form path: transform prod[b][k][j] itself (inverse NTT); `rows` rows per polynomial
+    const u64 *prod; u32 rows, n;
+    __device__ __forceinline__ const u64 *src(int j, int c, u64) const { return prod + ((u64)c * rows + j) * n; }
     __device__ __forceinline__ u64 xf(int, int, u32, u64 raw) const { return raw; }
 };
 
@@ -113,6 +122,7 @@ b2_status b2_kswitch_key_create(b2_ctx *ctx, const uint64_t *const *digit_ptrs, 
     B2_CUDA(cudaSetDevice(ctx->device));
     b2_kswitch_key *k = new b2_kswitch_key();
     k->digits = digits; k->device = ctx->device;
+    k->h_ptrs.assign(digit_ptrs, digit_ptrs + digits);
     cudaError_t e = cudaMalloc((void **)&k->d_ptrs, digits * sizeof(uint64_t *));
     if (e != cudaSuccess) { delete k; return cuda_fail(e, "cudaMalloc(key ptrs)"); }
     e = cudaMemcpy((void *)k->d_ptrs, digit_ptrs, digits * sizeof(uint64_t *), cudaMemcpyHostToDevice);
@@ -130,6 +140,7 @@ void b2_kswitch_key_destroy(b2_kswitch_key *k) {
     if (!k) return;
     cudaSetDevice(k->device);
     cudaFree((void *)k->d_ptrs);
+    cudaFree(k->own);
     delete k;
 }
 
@@ -166,7 +177,7 @@ static b2_status keyswitch_chunk(b2_ctx *ctx, const uint64_t *const *targets, ui
     {
         std::vector<LimbGroup> groups;
         for (size_t i = 0; i < R; i++) groups.push_back(LimbGroup{(u32)(i == decomp ? K - 1 : i), (u32)(nb * decomp), (u64)(i * nb * decomp * n), (u64)n});
-        ModUpLoad ld{coef, ctx->d_mods, (u32)decomp, (u32)K, (u32)n};
+        ModUpLoad ld{coef, ctx->d_mods, (u32)decomp, (u32)K, (u32)n, 0u};
         st = run_ntt(ctx, true, groups, temp, ld, PlainStore{temp}, stream);
         if (st != B2_OK) return st;
     }
@@ -174,7 +185,7 @@ static b2_status keyswitch_chunk(b2_ctx *ctx, const uint64_t *const *targets, ui
     // 3. key inner product
     {
         dim3 grid((unsigned)nb, (unsigned)((n / 2 + 255) / 256), (unsigned)R);
-        ks_inner_product_kernel<<<grid, 256, 0, stream>>>(temp, (const u64 *const *)key->d_ptrs, prod, ctx->d_mods, (u32)decomp, (u32)K, (u32)n);
+        ks_inner_product_kernel<<<grid, 256, 0, stream>>>(temp, (const u64 *const *)key->d_ptrs, prod, ctx->d_mods, (u32)decomp, (u32)K, (u32)n, 0u, (u32)K);
         count_launches(1);
         B2_CUDA(cudaGetLastError());
     }
@@ -195,9 +206,9 @@ static b2_status keyswitch_chunk(b2_ctx *ctx, const uint64_t *const *targets, ui
                       ctx->h_inv_mod_t[K - 1]};
         PtrTabW dp;
         for (size_t b = 0; b < (size_t)KS_MAXB; b++) dp.p[b] = b < nb ? (u64 *)dests[b] : nullptr;
-        ModDownStore sst{T, prod, ctx->d_inv + (K - 1) * K, dp, (u32)decomp, (u32)assign, is_ntt ? 1 : 0};
+        ModDownStore sst{T, prod, ctx->d_inv + (K - 1) * K, dp, (u32)decomp, (u32)assign, is_ntt ? 1 : 0, 0u, (u32)R, (u32)decomp};
         if (is_ntt) st = run_ntt(ctx, true, groups, mid, ModDownLoad{T}, sst, stream);
-        else st = run_ntt(ctx, false, groups, mid, ProdLoad{prod, (u32)decomp, (u32)n}, sst, stream);
+        else st = run_ntt(ctx, false, groups, mid, ProdLoad{prod, (u32)R, (u32)n}, sst, stream);
         if (st != B2_OK) return st;
     }
     mark();
@@ -218,6 +229,7 @@ b2_status b2_keyswitch_batched(b2_ctx *ctx, const uint64_t *const *targets, uint
     B2_REQUIRE(ctx && key && (batch == 0 || (targets && dests)), "null argument");
     B2_REQUIRE(decomp >= 1 && decomp + 1 <= ctx->K, "decomp must be in [1, K-1] (keyswitching needs a special prime)");
     B2_REQUIRE(key->digits >= decomp, "keyswitching key has fewer digits than the ciphertext has limbs");
+    B2_REQUIRE(key->rows == 0, "a limb-sharded key can only be used with the b2_keyswitch_shard_* entry points");
     B2_REQUIRE(assign >= 0 && assign <= 2, "unknown assign method");
     B2_REQUIRE(ctx->scheme != B2_SCHEME_BGV || is_ntt, "BGV ciphertexts are NTT-form");
     B2_REQUIRE(ctx->scheme != B2_SCHEME_BGV || ctx->t > 1, "BGV needs a plain modulus");
@@ -240,6 +252,147 @@ b2_status b2_keyswitch(b2_ctx *ctx, const uint64_t *target, size_t decomp, int i
                        uint64_t *dest, int assign, void *stream_) {
     B2_REQUIRE(ctx && target && key && dest, "null argument");
     return b2_keyswitch_batched(ctx, &target, &dest, 1, decomp, is_ntt, key, assign, stream_);
+}
+
+
+// ---- limb-sharded keyswitch: the decomp + 1 output moduli are partitioned over the ranks ----------------
+// Rank r owns the contiguous range [first, first + count) of the output moduli 0 .. decomp (decomp = the special prime)
+// and holds the ciphertext limbs and the key rows of those moduli only.  One keyswitch is three local stages around
+// two collectives that the caller (one process per GPU) issues between them:
+//   prepare   c_j = INTT(target_j) for the owned ciphertext limbs        -> ALL-GATHER of the coefficient-form target
+//   products  temp[i][j] = NTT_{m_i}(c_j mod m_i), prod[k][i] = sum_j temp[i][j] o key_j[k][i] for the owned i;
+//             the owner of the special prime also computes u_k = INTT_P(prod[k][decomp])   -> BROADCAST of u (2 N words)
+//   finish    mod-down of the owned ciphertext limbs into the local destination
+// The per-rank work and key traffic are 1 / world of the single-GPU keyswitch; results are bit-identical to it.
+
+b2_status b2_limb_partition(size_t n_out_moduli, int world, int rank, size_t *first, size_t *count) {
+    B2_REQUIRE(first && count && world >= 1 && rank >= 0 && rank < world && n_out_moduli >= 1, "bad arguments");
+    const size_t base = n_out_moduli / (size_t)world, rem = n_out_moduli % (size_t)world, r = (size_t)rank;
+    *count = base + (r < rem ? 1 : 0);
+    *first = r * base + std::min(r, rem);
+    return B2_OK;
+}
+
+b2_status b2_kswitch_key_shard(b2_ctx *ctx, const b2_kswitch_key *full, size_t decomp, size_t first, size_t count, b2_kswitch_key **out) {
+    B2_REQUIRE(ctx && full && out, "null argument");
+    B2_REQUIRE(full->rows == 0, "the source must be a full key");
+    B2_REQUIRE(decomp >= 1 && decomp + 1 <= ctx->K && full->digits >= decomp, "bad decomp");
+    B2_REQUIRE(count >= 1 && first + count <= decomp + 1, "modulus range out of bounds");
+    B2_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = ctx->n, K = ctx->K;
+    b2_kswitch_key *k = new b2_kswitch_key();
+    k->digits = decomp; k->device = ctx->device; k->rows = count; k->first = first; k->decomp = decomp;
+    cudaError_t e = cudaMalloc((void **)&k->own, decomp * 2 * count * n * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&k->d_ptrs, decomp * sizeof(uint64_t *));
+    if (e != cudaSuccess) { cudaFree(k->own); delete k; return cuda_fail(e, "cudaMalloc(key shard)"); }
+    for (size_t j = 0; j < decomp && e == cudaSuccess; j++) {
+        k->h_ptrs.push_back(k->own + j * 2 * count * n);
+        for (size_t p = 0; p < 2 && e == cudaSuccess; p++)
+            for (size_t il = 0; il < count && e == cudaSuccess; il++) {
+                const size_t i = first + il, ki = i == decomp ? K - 1 : i;
+                e = cudaMemcpy(k->own + ((j * 2 + p) * count + il) * n, full->h_ptrs[j] + (p * K + ki) * n, n * 8, cudaMemcpyDeviceToDevice);
+            }
+    }
+    if (e == cudaSuccess) e = cudaMemcpy((void *)k->d_ptrs, k->h_ptrs.data(), decomp * sizeof(uint64_t *), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { b2_kswitch_key_destroy(k); return cuda_fail(e, "cudaMemcpy(key shard)"); }
+    *out = k;
+    return B2_OK;
+}
+
+static inline size_t owned_ct_limbs(size_t decomp, size_t first, size_t count) {
+    return first >= decomp ? 0 : std::min(first + count, decomp) - first;
+}
+
+b2_status b2_keyswitch_shard_prepare(b2_ctx *ctx, const uint64_t *target_local, size_t decomp, int is_ntt, size_t first, size_t count,
+                                     uint64_t *send, void *stream_) {
+    B2_REQUIRE(ctx && decomp >= 1 && decomp + 1 <= ctx->K && count >= 1 && first + count <= decomp + 1, "bad arguments");
+    const size_t n = ctx->n, nct = owned_ct_limbs(decomp, first, count);
+    if (nct == 0) return B2_OK;
+    B2_REQUIRE(target_local && send && (((uintptr_t)target_local | (uintptr_t)send) & 15) == 0, "operands must be non-null and 16-byte aligned");
+    B2_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!is_ntt) { B2_CUDA(cudaMemcpyAsync(send, target_local, nct * n * 8, cudaMemcpyDeviceToDevice, stream)); return B2_OK; }
+    std::vector<LimbGroup> groups;
+    for (size_t jl = 0; jl < nct; jl++) groups.push_back(LimbGroup{(u32)(first + jl), 1u, (u64)(jl * n), 0});
+    PtrTab coef;
+    for (int b = 0; b < KS_MAXB; b++) coef.p[b] = b == 0 ? (const u64 *)target_local : nullptr;
+    return run_ntt(ctx, false, groups, (u64 *)send, TargetLoad{coef, (u32)n}, PlainStore{(u64 *)send}, stream);
+}
+
+// workspace of the sharded stages: prod [2][count][N] | mid [2][nct][N] | tc [decomp][N] | temp [count][decomp][N];
+// prod survives from `products` to `finish` (no other call on this context in between)
+b2_status b2_keyswitch_shard_products(b2_ctx *ctx, const uint64_t *gathered, int world, size_t pad, size_t decomp, size_t first, size_t count,
+                                      const b2_kswitch_key *shard, uint64_t *u, void *stream_) {
+    B2_REQUIRE(ctx && gathered && shard && world >= 1, "null argument");
+    B2_REQUIRE(decomp >= 1 && decomp + 1 <= ctx->K && count >= 1 && first + count <= decomp + 1, "bad modulus range");
+    B2_REQUIRE(shard->rows == count && shard->first == first && shard->decomp == decomp, "key shard does not match the modulus range");
+    B2_REQUIRE((((uintptr_t)gathered | (uintptr_t)u) & 15) == 0, "operands must be 16-byte aligned");
+    const bool owns_special = first + count == decomp + 1;
+    B2_REQUIRE(!owns_special || u, "the owner of the special prime needs the u buffer");
+    B2_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t n = ctx->n, K = ctx->K, nct = owned_ct_limbs(decomp, first, count);
+    b2_status st = ensure_ws(ctx, (2 * count + 2 * nct + decomp + count * decomp) * n * 8);
+    if (st != B2_OK) return st;
+    u64 *prod = (u64 *)ctx->ws, *tc = prod + (2 * count + 2 * nct) * n, *temp = tc + decomp * n;
+    // the all-gather delivered [world][pad][N]: rank r's owned ciphertext limbs first_r .. ; compact to tc[decomp][N]
+    for (int r = 0; r < world; r++) {
+        size_t f = 0, c = 0;
+        b2_limb_partition(decomp + 1, world, r, &f, &c);
+        const size_t m = owned_ct_limbs(decomp, f, c);
+        B2_REQUIRE(m <= pad, "pad is smaller than a rank's share of the ciphertext limbs");
+        if (m) B2_CUDA(cudaMemcpyAsync(tc + f * n, gathered + (size_t)r * pad * n, m * n * 8, cudaMemcpyDeviceToDevice, stream));
+    }
+    PtrTab coef;
+    for (int b = 0; b < KS_MAXB; b++) coef.p[b] = b == 0 ? tc : nullptr;
+    {
+        std::vector<LimbGroup> groups;
+        for (size_t il = 0; il < count; il++) {
+            const size_t i = first + il;
+            groups.push_back(LimbGroup{(u32)(i == decomp ? K - 1 : i), (u32)decomp, (u64)(il * decomp * n), (u64)n});
+        }
+        ModUpLoad ld{coef, ctx->d_mods, (u32)decomp, (u32)K, (u32)n, (u32)first};
+        st = run_ntt(ctx, true, groups, temp, ld, PlainStore{temp}, stream);
+        if (st != B2_OK) return st;
+    }
+    {
+        dim3 grid(1, (unsigned)((n / 2 + 255) / 256), (unsigned)count);
+        ks_inner_product_kernel<<<grid, 256, 0, stream>>>(temp, (const u64 *const *)shard->d_ptrs, prod, ctx->d_mods, (u32)decomp, (u32)K, (u32)n,
+                                                          (u32)first, (u32)count);
+        count_launches(1);
+        B2_CUDA(cudaGetLastError());
+    }
+    if (owns_special) {
+        std::vector<LimbGroup> groups{LimbGroup{(u32)(K - 1), 2u, 0, (u64)n}};
+        SpecialLoad ld{prod, (u32)count, (u32)(count - 1), (u32)n};
+        st = run_ntt(ctx, false, groups, (u64 *)u, ld, PlainStore{(u64 *)u}, stream);
+        if (st != B2_OK) return st;
+    }
+    return B2_OK;
+}
+
+b2_status b2_keyswitch_shard_finish(b2_ctx *ctx, const uint64_t *u, size_t decomp, int is_ntt, size_t first, size_t count,
+                                    uint64_t *dest_local, int assign, void *stream_) {
+    B2_REQUIRE(ctx && u, "null argument");
+    B2_REQUIRE(decomp >= 1 && decomp + 1 <= ctx->K && count >= 1 && first + count <= decomp + 1, "bad modulus range");
+    B2_REQUIRE(assign >= 0 && assign <= 2, "unknown assign method");
+    B2_REQUIRE(ctx->scheme != B2_SCHEME_BGV || (is_ntt && ctx->t > 1), "BGV ciphertexts are NTT-form and need a plain modulus");
+    const size_t n = ctx->n, K = ctx->K, nct = owned_ct_limbs(decomp, first, count);
+    if (nct == 0) return B2_OK;
+    B2_REQUIRE(dest_local && (((uintptr_t)dest_local | (uintptr_t)u) & 15) == 0, "operands must be non-null and 16-byte aligned");
+    B2_REQUIRE(ctx->ws && ctx->ws_bytes >= (2 * count + 2 * nct) * n * 8, "b2_keyswitch_shard_products must run first");
+    B2_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    u64 *prod = (u64 *)ctx->ws, *mid = prod + 2 * count * n;
+    std::vector<LimbGroup> groups;
+    for (size_t jl = 0; jl < nct; jl++) groups.push_back(LimbGroup{(u32)(first + jl), 2u, (u64)(jl * n), (u64)(nct * n)});
+    ModDownTerm T{(const u64 *)u, ctx->d_mods, (u32)(K - 1), (u32)n, ctx->scheme == B2_SCHEME_BGV ? 1 : 0, ctx->t, ctx->t_ratio, ctx->t_r0, ctx->t_r1,
+                  ctx->h_inv_mod_t[K - 1]};
+    PtrTabW dp;
+    for (int b = 0; b < KS_MAXB; b++) dp.p[b] = b == 0 ? (u64 *)dest_local : nullptr;
+    ModDownStore sst{T, prod, ctx->d_inv + (K - 1) * K, dp, (u32)decomp, (u32)assign, is_ntt ? 1 : 0, (u32)first, (u32)count, (u32)nct};
+    if (is_ntt) return run_ntt(ctx, true, groups, mid, ModDownLoad{T, (u32)first}, sst, stream);
+    return run_ntt(ctx, false, groups, mid, ProdLoad{prod, (u32)count, (u32)n}, sst, stream);
 }
 
 }  // extern "C"
