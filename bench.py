@@ -41,6 +41,16 @@ METRIC = "ntt_limbs_per_s_n65536"
 UNIT = "limbs/s"
 
 
+def measured_traffic():
+    """dram__bytes_read + dram__bytes_write of one forward launch of the workload (ncu --set full capture of the same
+    command, committed under profiles/): {"bytes_per_launch": ..., "source": ...} or None."""
+    p = os.path.join(ROOT, "profiles", "ntt_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -222,7 +232,9 @@ def main():
     fwd_s = ef0.elapsed_time(ef1) * 1e-3 / reps
     peak, peak_src = measured_peaks()
     achieved = limbs * n * 16 / fwd_s / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    tr = measured_traffic()
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": tr["bytes_per_launch"] if tr else None, "traffic_source": tr["source"] if tr else None,
                 "kernel": "ntt_persistent_kernel (one launch = one b2_ntt_forward over 420 limbs, both passes)",
                 "algorithmic_bytes_per_call": limbs * n * 16, "call_ms": fwd_s * 1e3, "peak_source": peak_src}
 
@@ -283,6 +295,46 @@ def main():
             extra[name + "_us"] = s / k * 1e6
         extra["keyswitch_compulsory_bytes"] = 8 * n * (L + 2 * L * (L + 1) + 4 * L)
         extra["keyswitch_hbm_frac"] = extra["keyswitch_compulsory_bytes"] / (extra["relinearize_us"] * 1e-6) / 1e9 / peak
+        extra["note"] = "relinearize/rotate ops/s above: one independent ciphertext stream per GPU (batch sharding, whole-job aggregate)"
+        if world > 1:
+            # ONE relinearize cut over all GPUs by RNS limb: all-gather of the coefficient-form target and
+            # broadcast of the special limb over NCCL, everything else local to the modulus owner
+            sh = importlib.import_module("troy-nova_b200.sharded")
+            gs = torch.Generator(device="cuda"); gs.manual_seed(4242)          # the SAME ciphertext and key on every rank
+            for i in range(NCOMP):
+                key[:, :, i, :] = torch.randint(0, moduli[i], (L, 2, n), dtype=torch.int64, device="cuda", generator=gs)
+            cts = torch.empty((3, L, n), dtype=torch.int64, device="cuda")
+            for j in range(L):
+                cts[:, j, :] = torch.randint(0, moduli[j], (3, n), dtype=torch.int64, device="cuda", generator=gs)
+            want = cts[:2].clone()
+            ctx.keyswitch(cts[2], L, True, kh, want, b2.ASSIGN_ADD_INPLACE)     # single-GPU result: the checker
+            ks = sh.LimbShardedKeyswitch(sh.DeviceStages(ctx), L)
+            f, c, nct = ks.first, ks.count, ks.nct
+            shard = ctx.kswitch_key_shard(kh, L, f, c) if c else None
+            tl = cts[2, f:f + nct].contiguous() if nct else torch.zeros(2, dtype=torch.int64, device="cuda")
+            dl0 = cts[:2, f:f + nct].contiguous() if nct else torch.zeros(2, dtype=torch.int64, device="cuda")
+            dl = dl0.clone()
+
+            def relin_sharded():
+                dl.copy_(dl0)
+                ks(tl, True, shard, dl, b2.ASSIGN_ADD_INPLACE)
+            relin_sharded()
+            ok = 1 if (nct == 0 or torch.equal(dl, want[:, f:f + nct])) else 0
+            for _ in range(3):
+                relin_sharded()
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k = max(5, args.steps)
+            a0.record()
+            for _ in range(k):
+                relin_sharded()
+            a1.record(); barrier()
+            s = max_over_ranks(a0.elapsed_time(a1) * 1e-3)
+            extra["relinearize_limb_sharded_us"] = s / k * 1e6
+            extra["relinearize_limb_sharded_ops_per_s"] = k / s
+            extra["relinearize_limb_sharded_speedup_vs_1gpu"] = extra["relinearize_us"] / (s / k * 1e6)
+            extra["relinearize_limb_sharded_bit_exact"] = bool(max_over_ranks(1.0 - ok) == 0.0)
+            extra["limb_partition"] = [sh.partition(L + 1, world, r)[1] for r in range(world)]
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -16,7 +16,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > "$OUT/bench_under_ncu.log" 2>&1
 python tools/summarize_launches.py "$OUT/launches.csv" > "$OUT/launches_summary.txt" 2>&1; cat "$OUT/launches_summary.txt"
 echo "== ncu full"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'ntt_persistent' -s 4 -c 2 -f -o "$OUT/prof_ntt" python tools/prof_ntt.py > "$OUT/prof_ntt.log" 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:ntt_persistent -s 4 -c 2 -f -o "$OUT/prof_ntt" python tools/prof_ntt.py > "$OUT/prof_ntt.log" 2>&1
 tail -2 "$OUT/prof_ntt.log"
 ncu -i "$OUT/prof_ntt.ncu-rep" --page raw --csv > "$OUT/prof_ntt_raw.csv" 2>/dev/null
 ncu -i "$OUT/prof_ntt.ncu-rep" --page source --csv > "$OUT/prof_ntt_source.csv" 2>/dev/null
