@@ -83,6 +83,7 @@ b2_status b2_malloc_host(size_t bytes, void **hptr);       /* pinned */
 b2_status b2_free_host(void *hptr);
 b2_status b2_memcpy_h2d(b2_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream);
 b2_status b2_memcpy_d2h(b2_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream);
+b2_status b2_memcpy_d2d(b2_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream);
 b2_status b2_stream_sync(b2_ctx *ctx, void *stream);
 
 /* ---- N1/N2: utils::ntt_transfer_to_rev / ntt_transfer_from_rev (+_inplace when in == out)

@@ -50,6 +50,7 @@ _SIGS = {
     "b2_free_host": (C.c_int, [vp]),
     "b2_memcpy_h2d": (C.c_int, [vp, vp, vp, C.c_size_t, vp]),
     "b2_memcpy_d2h": (C.c_int, [vp, vp, vp, C.c_size_t, vp]),
+    "b2_memcpy_d2d": (C.c_int, [vp, vp, vp, C.c_size_t, vp]),
     "b2_stream_sync": (C.c_int, [vp, vp]),
 }
 _NTT_ARGS = [vp, vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t, vp]

@@ -114,6 +114,12 @@ b2_status b2_memcpy_d2h(b2_ctx *ctx, void *dst, const void *src, size_t bytes, v
     B2_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return B2_OK;
 }
+b2_status b2_memcpy_d2d(b2_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream) {
+    B2_REQUIRE(ctx, "null ctx");
+    B2_CUDA(cudaSetDevice(ctx->device));
+    B2_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return B2_OK;
+}
 b2_status b2_stream_sync(b2_ctx *ctx, void *stream) {
     B2_REQUIRE(ctx, "null ctx");
     B2_CUDA(cudaSetDevice(ctx->device));

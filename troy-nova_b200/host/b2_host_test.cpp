@@ -1,0 +1,100 @@
+// b2_host_test.cpp — scripted driver of the C++ host mirror (b2_evaluator.h) for tests/test_host_mirror_gpu.py.
+//   b2_host_test <input.bin> <output.bin>
+// input  (uint64 words): scheme, log_n, K, t, G, galois_element[G], moduli[K], relin key [L][2][K][N],
+//                        galois keys G x [L][2][K][N], ct a [2][L][N], ct b [2][L][N], plain [L][N] (NTT form)
+// output (uint64 words): the result ciphertexts of the script below, concatenated, then one word per error-behaviour probe.
+// The python test recomputes every result with the CPU oracle and compares bit for bit.
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+
+#include "b2_evaluator.h"
+
+using namespace b2troy;
+
+static std::vector<uint64_t> read_all(const char *path) {
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
+    if (!f) { std::fprintf(stderr, "cannot open %s\n", path); std::exit(2); }
+    const size_t bytes = (size_t)f.tellg();
+    std::vector<uint64_t> v(bytes / 8);
+    f.seekg(0);
+    f.read((char *)v.data(), (std::streamsize)(v.size() * 8));
+    return v;
+}
+
+int main(int argc, char **argv) {
+    if (argc != 3) { std::fprintf(stderr, "usage: %s in.bin out.bin\n", argv[0]); return 2; }
+    const std::vector<uint64_t> in = read_all(argv[1]);
+    size_t pos = 0;
+    auto take = [&](size_t n) { const uint64_t *p = in.data() + pos; pos += n; if (pos > in.size()) { std::fprintf(stderr, "input truncated\n"); std::exit(2); } return p; };
+    const uint64_t *hdr = take(5);
+    const SchemeType scheme = (SchemeType)hdr[0];
+    const size_t log_n = hdr[1], K = hdr[2], G = hdr[4], n = (size_t)1 << log_n, L = K - 1;
+    const uint64_t t = hdr[3];
+    const uint64_t *gelts = take(G);
+    const uint64_t *moduli = take(K);
+    const size_t key_words = L * 2 * K * n;
+    std::vector<uint64_t> out;
+    auto emit = [&](const Ciphertext &c) { const std::vector<uint64_t> h = c.to_host(); out.insert(out.end(), h.begin(), h.end()); };
+    try {
+        HeContextPointer ctx = HeContext::create(scheme, n, std::vector<uint64_t>(moduli, moduli + K), t, 0);
+        RelinKeys rk(ctx);
+        rk.set_key(RelinKeys::get_index(2), take(key_words), L);
+        GaloisKeys gk(ctx);
+        for (size_t i = 0; i < G; i++) gk.set_galois_key((size_t)gelts[i], take(key_words), L);
+        const bool ntt = scheme != SchemeType::BFV;
+        const double scale = scheme == SchemeType::CKKS ? 1048576.0 : 1.0;
+        Ciphertext a = Ciphertext::from_host(ctx, take(2 * L * n), 2, L, ntt, scale);
+        Ciphertext b = Ciphertext::from_host(ctx, take(2 * L * n), 2, L, ntt, scale);
+        Plaintext plain = Plaintext::from_host(ctx, take(L * n), L, true);
+        Evaluator ev(ctx);
+
+        Ciphertext m = ev.multiply_new(a, b);                     emit(m);        // 1
+        Ciphertext r = ev.relinearize_new(m, rk);                 emit(r);        // 2
+        Ciphertext rot1, rot3, conj;
+        if (scheme == SchemeType::CKKS) { ev.rotate_vector(r, 1, gk, rot1); ev.rotate_vector(r, 3, gk, rot3); ev.complex_conjugate(r, gk, conj); }
+        else { ev.rotate_rows(r, 1, gk, rot1); ev.rotate_rows(r, 3, gk, rot3); ev.rotate_columns(r, gk, conj); }
+        emit(rot1); emit(rot3); emit(conj);                                       // 3, 4 (NAF: -1 then 4), 5
+        Ciphertext down = scheme == SchemeType::CKKS ? ev.rescale_to_next_new(r) : ev.mod_switch_to_next_new(r);
+        emit(down);                                                               // 6
+        Ciphertext sq = ev.square_new(a);                         emit(sq);       // 7
+        emit(ev.add_new(a, b)); emit(ev.sub_new(a, b)); emit(ev.negate_new(a));   // 8, 9, 10
+        {                                                                         // 11: multiply_plain on NTT-form operands
+            Ciphertext an = a.clone();
+            if (!ntt) ev.transform_to_ntt_inplace(an);
+            Ciphertext mp; ev.multiply_plain(an, plain, mp);
+            if (!ntt) ev.transform_from_ntt_inplace(mp);
+            emit(mp);
+        }
+        {                                                                         // 12, 13: relinearize_batched
+            Ciphertext o0, o1;
+            ev.relinearize_batched({&m, &sq}, rk, {&o0, &o1});
+            emit(o0); emit(o1);
+        }
+        {                                                                         // 14, 15: rotate batched (direct key), 16, 17: NAF path
+            Ciphertext o0, o1, p0, p1;
+            if (scheme == SchemeType::CKKS) { ev.rotate_vector_batched({&r, &rot1}, 1, gk, {&o0, &o1}); ev.rotate_vector_batched({&r, &rot1}, 3, gk, {&p0, &p1}); }
+            else { ev.rotate_rows_batched({&r, &rot1}, 1, gk, {&o0, &o1}); ev.rotate_rows_batched({&r, &rot1}, 3, gk, {&p0, &p1}); }
+            emit(o0); emit(o1); emit(p0); emit(p1);
+        }
+        {                                                                         // 18: apply_keyswitching with the relin key as a plain kswitch key
+            Ciphertext ks; ev.apply_keyswitching(r, rk, ks); emit(ks);
+        }
+        // error behaviour probes: 1 = std::invalid_argument thrown as the reference does
+        auto probe = [&](auto &&fn) { try { fn(); out.push_back(0); } catch (const std::invalid_argument &) { out.push_back(1); } };
+        probe([&] { Ciphertext d; ev.relinearize(m, RelinKeys(ctx), d); });                       // key not present
+        probe([&] { Ciphertext d; if (scheme == SchemeType::CKKS) ev.rotate_vector(r, 5, gk, d); else ev.rotate_rows(r, 5, gk, d); });   // NAF needs a missing key (4 + 1 ok? 5 = 1 + 4: present) -> expect 0
+        probe([&] { Ciphertext d; if (scheme == SchemeType::CKKS) ev.rotate_vector(r, 2, gk, d); else ev.rotate_rows(r, 2, gk, d); });   // single-term NAF, key missing -> 1
+        probe([&] { Ciphertext d; ev.add(a, down, d); });                                          // level mismatch
+        probe([&] { Ciphertext d; if (scheme == SchemeType::CKKS) ev.rotate_rows(r, 1, gk, d); else ev.rotate_vector(r, 1, gk, d); });   // wrong scheme
+        probe([&] { Ciphertext c3 = m.clone(); Ciphertext d; ev.apply_galois(c3, (size_t)gelts[0], gk, d); });                           // size-3 ciphertext
+        ctx->synchronize();
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "b2_host_test: %s\n", e.what());
+        return 1;
+    }
+    std::ofstream f(argv[2], std::ios::binary);
+    f.write((const char *)out.data(), (std::streamsize)(out.size() * 8));
+    return 0;
+}
