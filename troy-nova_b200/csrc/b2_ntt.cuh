@@ -284,51 +284,25 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // Stage one tile of a limb (N contiguous words at `limb`) into `stage`: 2048 16-byte chunks, 8 per thread.
-// WARP-PRIVATE: a thread copies exactly chunks that its own warp reads in round 0 of the pass (window low bit LO0), so
-// "tile staged" is a per-warp condition (cp.async.wait_group + bar.warp.sync) and a warp may refill its part of the
-// stage buffer as soon as it has read it, without a CTA barrier.  For LO0 > 0 the 16 words of a thread are 2^LO0 apart
-// and the 16-byte chunks are shared by the thread pair (t, t ^ 1): the even thread copies registers 0..7, the odd one 8..15.
-template <int A, bool COL, int LO0>
+template <int A, bool COL>
 __device__ __forceinline__ void stage_tile(u64 *stage, const u64 *limb, int tile) {
     using G = Geo<A, COL>;
-    const int t = (int)threadIdx.x;
 #pragma unroll
     for (int m = 0; m < 8; m++) {
-        // LO0 <= 5: the warp's round-0 words are the contiguous block [512 w, 512 w + 512) of the tile -> consecutive lanes copy
-        // consecutive chunks; otherwise (LO0 = 8) the lane pair's own chunks, 16 consecutive chunks per half-warp
-        const int idx = LO0 <= 5 ? 512 * (t >> 5) + 2 * ((t & 31) + 32 * m) : round_base<LO0>(t & ~1) + ((m + 8 * (t & 1)) << LO0);
+        const int idx = 2 * ((int)threadIdx.x + NTT_THREADS * m);
         cp_async16(stage + swz16(idx), limb + G::pos(tile, idx));
     }
-}
-
-// shared-memory barrier object, used split-phase: a warp ARRIVES when it has finished reading the exchange buffer of an
-// item and WAITS (normally without blocking) just before it overwrites the buffer in the next item
-__device__ __forceinline__ void mbar_init(u64 *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(u64 *bar) {
-    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u64 *bar, unsigned parity) {
-    asm volatile(
-        "{\n.reg .pred p;\nWAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
 }
 
 // One pass = one to three radix-16 rounds over a staged tile.  (LOr, NLr) per round; NLr == 0: round absent.
 //   FIRST: the pass reads external data (xf -> from_ext); otherwise it reads the raw intermediate
 //   FINAL: the pass writes canonical results; otherwise it writes the raw intermediate
 // Hooks (the persistent loop's bookkeeping, woven into the pass so that none of it sits between two barriers):
-//   hk.sync_stage()    after the modulus constants and the first twiddles have been requested: waits for the warp's part of
-//                      the staged tile (cp.async group + bar.warp.sync, no CTA barrier); thread 0 claims the next item
+//   hk.sync_stage()    after the modulus constants and the first twiddles have been requested: waits for the staged tile
+//                      (cp.async group + CTA barrier); thread 0 then signals the previous item and claims the next one
 //   hk.mid()           half way through round 0: thread 0 decodes the claimed item and requests its dependency counter
-//   hk.xch_wait()      before the exchange buffer is overwritten: every warp has finished reading it in the previous item
-//                      (split-phase mbarrier, normally already complete)
 //   hk.pre_exchange()  before the barrier that ends round 0: thread 0 posts (next item, ready) to shared memory
-//   hk.stage_free()    after that barrier (the ONE CTA barrier of an item): the next item's tile is staged; thread 0 signals
-//                      the completion of the previous item (all of its stores precede this barrier)
-//   hk.xch_done()      after the warp's last read of the exchange buffer: arrives on the mbarrier
+//   hk.stage_free()    after that barrier: the stage buffer is free -> the next item's tile is staged
 template <int A, bool COL, bool FWD, bool FIRST, bool FINAL, class AR, int LO0, int NL0, int LO1, int NL1, int LO2, int NL2,
           class Load, class Store, class Hooks>
 __device__ __forceinline__ void pass_body(const u64 *stage, u64 *sm, const ModInfo &M, int tile, int g, int c, u64 off, int logn,
@@ -368,7 +342,6 @@ __device__ __forceinline__ void pass_body(const u64 *stage, u64 *sm, const ModIn
             v[k] = FIRST ? ar.from_ext(ld.xf(g, c, xt + ((u32)k << G::xbit(LO0)), raw[k])) : ar.from_raw(raw[k]);
         if (FWD) fwd_round<NL0, G::xbit(LO0)>(ar, v, xt, logn, tw0, hk.mid);
         else inv_round<NL0, G::xbit(LO0), LASTL && NR == 1>(ar, v, xt, logn, tw0, hk.mid);
-        hk.xch_wait();
         if (NR > 1) {
             const int xb = swz(it);
 #pragma unroll
@@ -377,17 +350,15 @@ __device__ __forceinline__ void pass_body(const u64 *stage, u64 *sm, const ModIn
         }
     }
     hk.pre_exchange();
-    __syncthreads();   // the exchange buffer is written (NR > 1); every warp has consumed its part of the stage buffer
+    __syncthreads();   // every thread has consumed the stage buffer (and, for NR > 1, written the exchange buffer)
     hk.stage_free();   // -> the next item's tile is staged while this one is computed
     RoundTw<N2, G::xbit(LO2), FWD, LASTL && NR == 3, AR> tw2;
-    if (NR == 1) hk.xch_done();
     if (NR > 1) {   // ---- round 1
         const int it = round_base<LO1>(t);
         const u32 xt = G::pos(tile, it);
         const int sb = swz(it);
 #pragma unroll
         for (int k = 0; k < 16; k++) v[k] = ar.from_raw(sm[sb ^ swz(k << LO1)]);
-        if (NR == 2) hk.xch_done();
         if (FWD) fwd_round<N1, G::xbit(LO1)>(ar, v, xt, logn, tw1, nohook);
         else inv_round<N1, G::xbit(LO1), LASTL && NR == 2>(ar, v, xt, logn, tw1, nohook);
         if (NR > 2) {     // each thread overwrites exactly the slots it has just read
@@ -403,7 +374,6 @@ __device__ __forceinline__ void pass_body(const u64 *stage, u64 *sm, const ModIn
         const int sb = swz(it);
 #pragma unroll
         for (int k = 0; k < 16; k++) v[k] = ar.from_raw(sm[sb ^ swz(k << LO2)]);
-        hk.xch_done();
         if (FWD) fwd_round<N2, G::xbit(LO2)>(ar, v, xt, logn, tw2, nohook);
         else inv_round<N2, G::xbit(LO2), LASTL>(ar, v, xt, logn, tw2, nohook);
     }
@@ -497,12 +467,10 @@ __device__ __forceinline__ u32 claim(u32 *queue) {
     return v;
 }
 
-template <class F0, class F1, class F2, class F3, class F4, class F5>
-struct PassHooks { F0 sync_stage; F1 mid; F2 pre_exchange; F3 stage_free; F4 xch_wait; F5 xch_done; };
-template <class F0, class F1, class F2, class F3, class F4, class F5>
-__device__ __forceinline__ PassHooks<F0, F1, F2, F3, F4, F5> make_hooks(F0 a, F1 b, F2 c, F3 d, F4 e, F5 f) {
-    return PassHooks<F0, F1, F2, F3, F4, F5>{a, b, c, d, e, f};
-}
+template <class F0, class F1, class F2, class F3>
+struct PassHooks { F0 sync_stage; F1 mid; F2 pre_exchange; F3 stage_free; };
+template <class F0, class F1, class F2, class F3>
+__device__ __forceinline__ PassHooks<F0, F1, F2, F3> make_hooks(F0 a, F1 b, F2 c, F3 d) { return PassHooks<F0, F1, F2, F3>{a, b, c, d}; }
 
 // The persistent transform kernel.  FWD: first pass = column pass (reads the operand through `ld`), second
 // pass = row pass (writes through `st`); inverse: first pass = row pass, second pass = column pass.
@@ -512,25 +480,18 @@ __device__ __forceinline__ PassHooks<F0, F1, F2, F3, F4, F5> make_hooks(F0 a, F1
 // red.release after a CTA barrier; a consumer polls with a relaxed L2 load, passes a CTA barrier and then reads the
 // intermediate with cp.async.cg (L2, never L1), so no L1 invalidation is needed (ld.acquire would flush the SM's L1 — and
 // with it the twiddles — once per item).
-// Inside a CTA an item costs ONE CTA barrier (between writing and reading the exchange buffer).  The tile is staged
-// warp-privately (each warp copies what it reads in round 0 and waits for its own copies only), the exchange buffer is
-// protected across items by a split-phase mbarrier (arrive after the last read, wait before the next write), and the
-// queue bookkeeping of thread 0 is spread over the item: claim at the start, dependency load in the middle of round 0,
-// hand-over at the barrier, completion signal of the previous item after it.  (r01f ncu of the two-barrier version:
-// 20 % of the stall samples were waits at the tile-staged barrier.)
+// Per item there are two CTA barriers (tile staged / exchange) and the queue bookkeeping of thread 0 is spread over the
+// item: claim after the first barrier, dependency load in the middle of round 0, hand-over at the second barrier.
 template <int A, bool FWD, int OCC, class Load, class Store>
 __global__ void __launch_bounds__(NTT_THREADS, OCC) ntt_persistent_kernel(const __grid_constant__ NttJob J, Load ld, Store st) {
     extern __shared__ __align__(128) u64 smem[];
-    __shared__ u32 s_item[2], s_ready[2];
-    __shared__ __align__(8) u64 s_xch_bar;
+    __shared__ u32 s_item, s_ready;
     u64 *const stage = smem, *const xch = smem + NTT_TILE;
     const int t = threadIdx.x;
     const u32 total = J.total_items, tiles = 1u << J.tile_shift;
     u32 *const queue = J.sync, *const finished = J.sync + 1, *const done = J.sync + 2;
     const PlainLoad mid_ld{J.mid};
     const PlainStore mid_st{J.mid};
-    constexpr int LO_P0 = FWD ? 8 : 0;                               // window low bit of round 0 of the first pass
-    constexpr int LO_P1 = FWD ? 4 : InvColPlan<A>::LO0;              // ... and of the second pass
 
     // limb l -> (group, limb in group): consecutive limbs cycle through the groups, so CTAs working on FP64-pipe
     // moduli and on integer-pipe moduli are resident on an SM at the same time and the two pipes overlap
@@ -540,38 +501,40 @@ __global__ void __launch_bounds__(NTT_THREADS, OCC) ntt_persistent_kernel(const 
         const u64 off = grp.base + (u64)c * grp.stride;
         if (it.phase == 0) {
             const u64 *src = ld.src(J.g_base + (int)g, (int)c, off);
-            stage_tile<A, FWD, LO_P0>(stage, src, (int)it.tile);          // forward: column tile; inverse: row tile
+            stage_tile<A, FWD>(stage, src, (int)it.tile);          // forward: column tile; inverse: row tile
         } else {
-            stage_tile<A, !FWD, LO_P1>(stage, J.mid + off, (int)it.tile);
+            stage_tile<A, !FWD>(stage, J.mid + off, (int)it.tile);
         }
         cp_async_commit();
     };
 
     // ---- prologue: claim the first item and stage it (blocking on its dependency)
     if (t == 0) {
-        mbar_init(&s_xch_bar, NTT_THREADS / 32);
         const u32 i0 = claim(queue);
-        s_item[0] = i0;
+        s_item = i0;
         if (i0 < total) {
             const NttItem it = ntt_decode(J, i0);
             if (it.phase) while (ld_relaxed(done + it.limb) < tiles) __nanosleep(100);
         }
     }
     __syncthreads();
-    const u32 first_id = s_item[0];
+    const u32 first_id = s_item;
     if (first_id < total) {
         NttItem cur = ntt_decode(J, first_id), nxt = cur;
         stage_item(cur);
-        u32 m = 0;                    // items this CTA has started (uniform): parity of the exchange-buffer mbarrier, slot of s_item
+        __syncthreads();              // s_item has been read by everyone before thread 0 posts the next one
         // thread-0 bookkeeping registers
         bool publish = false; u32 publish_limb = 0;       // a finished first-pass item whose completion is not yet signalled
         u32 nx = 0, dep = 0; bool has_dep = false;
         u32 nxt_id = 0; bool pre = false;
         auto hooks = make_hooks(
             [&]() {   // sync_stage
-                if (t == 0) nx = claim(queue);
                 cp_async_wait_all();
-                __syncwarp();         // the warp's part of the tile is staged and visible to the warp
+                __syncthreads();      // tile staged and visible; the previous item's stores and exchange reads are complete CTA-wide
+                if (t == 0) {
+                    if (publish) red_release(done + publish_limb);
+                    nx = claim(queue);
+                }
             },
             [&]() {   // mid
                 if (t == 0) {
@@ -583,20 +546,12 @@ __global__ void __launch_bounds__(NTT_THREADS, OCC) ntt_persistent_kernel(const 
                 }
             },
             [&]() {   // pre_exchange
-                if (t == 0) { s_item[(m + 1) & 1] = nx; s_ready[(m + 1) & 1] = (nx < total && (!has_dep || dep >= tiles)) ? 1u : 0u; }
+                if (t == 0) { s_item = nx; s_ready = (nx < total && (!has_dep || dep >= tiles)) ? 1u : 0u; }
             },
-            [&]() {   // stage_free (after the item's CTA barrier)
-                if (t == 0 && publish) { red_release(done + publish_limb); publish = false; }
-                nxt_id = s_item[(m + 1) & 1]; pre = s_ready[(m + 1) & 1] != 0;
+            [&]() {   // stage_free
+                nxt_id = s_item; pre = s_ready != 0;
                 if (nxt_id < total) nxt = ntt_decode(J, nxt_id);
                 if (pre) stage_item(nxt);
-            },
-            [&]() {   // xch_wait: all warps have finished reading the exchange buffer in the previous item
-                if (m > 0) mbar_wait(&s_xch_bar, (m - 1) & 1u);
-            },
-            [&]() {   // xch_done
-                __syncwarp();
-                if ((t & 31) == 0) mbar_arrive(&s_xch_bar);
             });
         while (true) {
             {
@@ -620,16 +575,15 @@ __global__ void __launch_bounds__(NTT_THREADS, OCC) ntt_persistent_kernel(const 
                         pass_dispatch<A, true, false, false, true, Pl::LO0, Pl::NL0, Pl::LO1, Pl::NL1, Pl::LO2, Pl::NL2>(path, stage, xch, M, (int)cur.tile, ga, (int)c, off, J.logn, mid_ld, st, hooks);
                 }
             }
-            // thread 0: the item just finished is signalled after the NEXT CTA barrier (stage_free of the next item, or below)
-            if (t == 0 && cur.phase == 0) { publish = true; publish_limb = cur.limb; }
-            m++;
+            publish = cur.phase == 0; publish_limb = cur.limb;
             if (nxt_id >= total) break;
             if (!pre) {               // dependency not met at prefetch time: signal our own completion, then wait
                 __syncthreads();
                 if (t == 0) {
-                    if (publish) { red_release(done + publish_limb); publish = false; }
+                    if (publish) red_release(done + publish_limb);
                     while (ld_relaxed(done + nxt.limb) < tiles) __nanosleep(100);
                 }
+                publish = false;
                 __syncthreads();
                 stage_item(nxt);
             }
@@ -641,10 +595,10 @@ __global__ void __launch_bounds__(NTT_THREADS, OCC) ntt_persistent_kernel(const 
     // ---- teardown: the last CTA to finish resets the queue and the counters for the next launch
     if (t == 0) {
         __threadfence();
-        s_ready[0] = (atomicAdd(finished, 1u) == gridDim.x - 1) ? 1u : 0u;
+        s_ready = (atomicAdd(finished, 1u) == gridDim.x - 1) ? 1u : 0u;
     }
     __syncthreads();
-    if (s_ready[0]) {
+    if (s_ready) {
         for (u32 i = t; i < J.n_limbs; i += NTT_THREADS) done[i] = 0;
         if (t == 0) { *queue = 0; *finished = 0; }
     }
