@@ -148,6 +148,69 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def _rand_limbs(torch, moduli, shape_prefix, n, gen):
+    """uniform residues [*shape_prefix][len(moduli)][n]"""
+    x = torch.empty(tuple(shape_prefix) + (len(moduli), n), dtype=torch.int64, device="cuda")
+    for j, q in enumerate(moduli):
+        x[..., j, :] = torch.randint(0, q, tuple(shape_prefix) + (n,), dtype=torch.int64, device="cuda", generator=gen)
+    return x
+
+
+def bench_c2(b2, torch, timed, local, world):
+    """BASELINE config 2: BFV N=16384, q={60,40,40}+special 60, 256 ciphertexts: batched NTT / INTT, multiply_plain
+    (NTT form), rotate_rows (Galois automorphism + batched keyswitch, 16 ciphertexts per launch set)."""
+    log_n, n, B = 14, 1 << 14, 256
+    moduli = b2.coeff_modulus_create(n, [60, 40, 40, 60]); K = len(moduli); L = K - 1
+    ctx = b2.Context(log_n, moduli, 786433, b2.BFV, device=local)   # t = 3 * 2^18 + 1 = 1 mod 2N
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    cts = _rand_limbs(torch, moduli[:L], (B, 2), n, g)
+    plain = _rand_limbs(torch, moduli[:L], (B,), n, g)          # one plaintext per ciphertext (multiply_plain_batched)
+    key = torch.empty((L, 2, K, n), dtype=torch.int64, device="cuda")
+    for i in range(K):
+        key[:, :, i, :] = torch.randint(0, moduli[i], (L, 2, n), dtype=torch.int64, device="cuda", generator=g)
+    kh = ctx.kswitch_key(key)
+    out = torch.empty_like(cts); rot = torch.empty_like(cts)
+    r = {}
+    t = timed(lambda: ctx.ntt_forward(cts, batch=B, pcount=2, ncomp=L), 5); r["ntt_batched_limbs_per_s"] = world * B * 2 * L / t
+    t = timed(lambda: ctx.ntt_inverse(cts, batch=B, pcount=2, ncomp=L), 5); r["intt_batched_limbs_per_s"] = world * B * 2 * L / t
+    t = timed(lambda: ctx.dyadic_broadcast_batched(cts, plain, out, B, 2, L), 5); r["multiply_plain_ops_per_s"] = world * B / t
+    gal = 3
+
+    def rotate_rows():
+        ctx.galois(cts, gal, rot, 2 * B, L, False)          # coefficient-form automorphism of all 2 B polynomials
+        ctx.keyswitch_batched([rot[b, 1] for b in range(B)], L, False, kh, [rot[b] for b in range(B)], b2.ASSIGN_OVERWRITE_EXCEPT_FIRST)
+    t = timed(rotate_rows, 3); r["rotate_rows_ops_per_s"] = world * B / t; r["rotate_rows_us_per_op"] = t / B * 1e6
+    return r
+
+
+def bench_c4(b2, torch, timed, local, world):
+    """BASELINE config 4: BGV N=32768, q={60,40x7}+special 60: multiply + relinearize, then the mod-switch chain to the last level."""
+    log_n, n = 15, 1 << 15
+    moduli = b2.coeff_modulus_create(n, [60] + [40] * 7 + [60]); K = len(moduli); L = K - 1
+    ctx = b2.Context(log_n, moduli, 786433, b2.BGV, device=local)
+    g = torch.Generator(device="cuda"); g.manual_seed(9)
+    a = _rand_limbs(torch, moduli[:L], (2,), n, g); b = _rand_limbs(torch, moduli[:L], (2,), n, g)
+    key = torch.empty((L, 2, K, n), dtype=torch.int64, device="cuda")
+    for i in range(K):
+        key[:, :, i, :] = torch.randint(0, moduli[i], (L, 2, n), dtype=torch.int64, device="cuda", generator=g)
+    kh = ctx.kswitch_key(key)
+    m = torch.empty((3, L, n), dtype=torch.int64, device="cuda"); d = torch.empty((2, L, n), dtype=torch.int64, device="cuda")
+    r = {}
+    t = timed(lambda: ctx.dyadic_convolute(a, 2, b, 2, m, L), 10); r["multiply_ops_per_s"] = world / t
+
+    def relin():
+        d.copy_(m[:2]); ctx.keyswitch(m[2], L, True, kh, d, b2.ASSIGN_ADD_INPLACE)
+    t = timed(relin, 10); r["relinearize_ops_per_s"] = world / t; r["relinearize_us"] = t * 1e6
+    bufs = [torch.empty((2, l, n), dtype=torch.int64, device="cuda") for l in range(L, 0, -1)]
+    bufs[0].copy_(d)
+
+    def chain():
+        for i in range(L - 1):
+            ctx.mod_switch_to_next(bufs[i], bufs[i + 1], 2, L - i, b2.MODSWITCH_BGV)
+    t = timed(chain, 5); r["modswitch_chain_8_to_1_us"] = t * 1e6
+    return r
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -260,6 +323,24 @@ def main():
     e2e = {"value": world * e2e_steps * 2 * e2e_pc * NCOMP / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": 2 * nbytes,
            "note": "b2_ntt_forward_host + b2_ntt_inverse_host on the [20][21][N] operand in pinned host memory (chunked: H2D, transform and D2H overlap); result verified below"}
     assert torch.equal(hb, x0[:e2e_pc].cpu()), "e2e round trip mismatch"
+    # what the host link can do at best: the same pinned buffer copied in both directions at once (plain cudaMemcpyAsync)
+    try:
+        hb2 = torch.empty_like(hb).pin_memory(); dA = torch.empty_like(x0[:e2e_pc]); dB = x0[:e2e_pc].clone()
+        sA, sB = torch.cuda.Stream(), torch.cuda.Stream()
+        best = 0.0
+        for _ in range(3):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            with torch.cuda.stream(sA):
+                dA.copy_(hb, non_blocking=True)
+            with torch.cuda.stream(sB):
+                hb2.copy_(dB, non_blocking=True)
+            torch.cuda.synchronize()
+            best = max(best, nbytes / (time.perf_counter() - t0) / 1e9)
+        e2e["host_link_duplex_gbs_per_direction"] = best
+        e2e["host_link_frac"] = (e2e["value"] / world) * n * 8 / 1e9 / best
+        del hb2, dA, dB
+    except Exception as ex:        # measurement aid only
+        e2e["host_link_duplex_gbs_per_direction"] = None; e2e["host_link_note"] = str(ex)[:80]
 
     # ---- extra: relinearize / rotate ops/s on the same parameter set (keyswitch core, data resident)
     extra = {}
@@ -296,6 +377,29 @@ def main():
         extra["keyswitch_compulsory_bytes"] = 8 * n * (L + 2 * L * (L + 1) + 4 * L)
         extra["keyswitch_hbm_frac"] = extra["keyswitch_compulsory_bytes"] / (extra["relinearize_us"] * 1e-6) / 1e9 / peak
         extra["note"] = "relinearize/rotate ops/s above: one independent ciphertext stream per GPU (batch sharding, whole-job aggregate)"
+
+        def timed(fn, k):
+            for _ in range(2):
+                fn()
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(k):
+                fn()
+            a1.record(); barrier()
+            return max_over_ranks(a0.elapsed_time(a1) * 1e-3) / k
+
+        # C3, batch 8: eight relinearizes sharing the key in one batched call (Evaluator::switch_key_internal_batched, K5)
+        nb = 8
+        cb = [x0[:3, :L, :].clone() for _ in range(nb)]
+        db = [c[:2].clone() for c in cb]
+        s8 = timed(lambda: ctx.keyswitch_batched([c[2] for c in cb], L, True, kh, db, b2.ASSIGN_ADD_INPLACE), max(3, args.steps // 4))
+        extra["relinearize_batch8_ops_per_s"] = world * nb / s8
+        extra["relinearize_batch8_us_per_op"] = s8 / nb * 1e6
+        del cb, db
+        # the other named parameter sets (BASELINE.json configs 2 and 4), data resident, per GPU x world
+        extra["c2_bfv_n16384_batch256"] = bench_c2(b2, torch, timed, local, world)
+        extra["c4_bgv_n32768"] = bench_c4(b2, torch, timed, local, world)
         if world > 1:
             # ONE relinearize cut over all GPUs by RNS limb: all-gather of the coefficient-form target and
             # broadcast of the special limb over NCCL, everything else local to the modulus owner

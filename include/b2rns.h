@@ -159,6 +159,10 @@ b2_status b2_dyadic_square(b2_ctx *ctx, const uint64_t *a, uint64_t *out, size_t
 /* fgk::dyadic_convolute::dyadic_broadcast_product(_accumulate)_ps (src/fgk/dyadic_convolute.cu:151-292):
  * out[k] (+)= a[k] o plain, k < pcount; plain [ncomp][N] */
 b2_status b2_dyadic_broadcast(b2_ctx *ctx, const uint64_t *a, const uint64_t *plain, uint64_t *out, size_t pcount, size_t ncomp, int accumulate, void *stream);
+/* ... _bps (src/fgk/dyadic_convolute.cu:223-292), Evaluator::multiply_plain_batched on contiguous batches:
+ * a, out [batch][pcount][ncomp][N], plain [batch][ncomp][N]; ciphertext b is multiplied by plaintext b, one launch */
+b2_status b2_dyadic_broadcast_batched(b2_ctx *ctx, const uint64_t *a, const uint64_t *plain, uint64_t *out, size_t batch, size_t pcount, size_t ncomp,
+                                      int accumulate, void *stream);
 /* Evaluator::bfv_multiply / bfv_square device branch (src/evaluator.cu:29-116,199-282) = BEHZ RNS multiplication:
  * RNSTool::fast_b_conv_m_tilde_sm_mrq + NTT + dyadic convolution + INTT + RNSTool::fast_floor_fast_b_conv_sk
  * (src/fgk/rns_tool.cu:7-343).  a, b [batch][2][nl][N] coefficient form -> out [batch][3][nl][N] coefficient form.

@@ -153,6 +153,18 @@ def test_elementwise(b2, po, log_n):
     assert np.array_equal(to_np(ctx.dyadic_broadcast(da, to_dev(pl), out, 2, nc)), o.dyadic_broadcast(a, pl, 2, nc))
     acc = o.random_poly(rng, 2, nc); dacc = to_dev(acc)
     assert np.array_equal(to_np(ctx.dyadic_broadcast(da, to_dev(pl), dacc, 2, nc, accumulate=True)), o.dyadic_broadcast(a, pl, 2, nc, acc_into=acc))
+    # batched multiply_plain (one plaintext per ciphertext) == per-item, with and without accumulation
+    Bp = 3
+    ap = np.concatenate([o.random_poly(rng, 2, nc) for _ in range(Bp)]); pp = np.concatenate([o.random_poly(rng, 1, nc) for _ in range(Bp)])
+    accp = np.concatenate([o.random_poly(rng, 2, nc) for _ in range(Bp)])
+    per_ct, per_pt = 2 * nc * o.n, nc * o.n
+    outp = to_dev(np.zeros_like(ap)); daccp = to_dev(accp)
+    ctx.dyadic_broadcast_batched(to_dev(ap), to_dev(pp), outp, Bp, 2, nc)
+    ctx.dyadic_broadcast_batched(to_dev(ap), to_dev(pp), daccp, Bp, 2, nc, accumulate=True)
+    for i in range(Bp):
+        ai, pi = ap[i * per_ct:(i + 1) * per_ct], pp[i * per_pt:(i + 1) * per_pt]
+        assert np.array_equal(to_np(outp)[i * per_ct:(i + 1) * per_ct], o.dyadic_broadcast(ai, pi, 2, nc))
+        assert np.array_equal(to_np(daccp)[i * per_ct:(i + 1) * per_ct], o.dyadic_broadcast(ai, pi, 2, nc, acc_into=accp[i * per_ct:(i + 1) * per_ct]))
     # batched convolution == per-item
     B = 3
     ab = np.concatenate([o.random_poly(rng, 2, nc) for _ in range(B)]); bb = np.concatenate([o.random_poly(rng, 2, nc) for _ in range(B)])

@@ -76,6 +76,7 @@ _SIGS.update({
     "b2_dyadic_convolute": (C.c_int, [vp, vp, C.c_size_t, vp, C.c_size_t, vp, C.c_size_t, C.c_size_t, vp]),
     "b2_dyadic_square": (C.c_int, [vp, vp, vp, C.c_size_t, C.c_size_t, vp]),
     "b2_dyadic_broadcast": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_size_t, C.c_int, vp]),
+    "b2_dyadic_broadcast_batched": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, vp]),
     "b2_negacyclic_shift": (C.c_int, [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp]),
     "b2_galois": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, vp]),
     "b2_bfv_multiply": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_size_t, vp]),
@@ -251,6 +252,9 @@ class Context:
 
     def dyadic_broadcast(self, a, plain, out, pcount, ncomp, accumulate=False, stream=None):
         _chk(self.L.b2_dyadic_broadcast(self.h, _dptr(a), _dptr(plain), _dptr(out), pcount, ncomp, int(accumulate), self._stream(stream))); return out
+
+    def dyadic_broadcast_batched(self, a, plain, out, batch, pcount, ncomp, accumulate=False, stream=None):
+        _chk(self.L.b2_dyadic_broadcast_batched(self.h, _dptr(a), _dptr(plain), _dptr(out), batch, pcount, ncomp, int(accumulate), self._stream(stream))); return out
 
     def bfv_multiply(self, a, b, out, nl, batch=1, stream=None):
         _chk(self.L.b2_bfv_multiply(self.h, _dptr(a), _dptr(b), _dptr(out), batch, nl, self._stream(stream))); return out

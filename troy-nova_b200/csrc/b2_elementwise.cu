@@ -16,6 +16,13 @@ __device__ __forceinline__ const ModInfo &ew_mod(const ModInfo *mods, const EwSh
     return mods[S.table_base + (u32)((v / S.n2) % S.ncomp)];
 }
 
+// canonical a * b mod p on the FP64 pipe for canonical a, b < p < 2^41 (6 DP instructions + conversions instead of the
+// ~40 integer-multiplier slots of a 128-bit Barrett reduction: the element-wise kernels stay HBM-bound).  Operands must be
+// canonical, as every stored output of the hot path is.
+__device__ __forceinline__ u64 mulmod_f64(u64 a, u64 b, double p, double pinv) {
+    return dd_to_canonical(mulmod_dd(u64_to_dd(a), u64_to_dd(b), p, pinv), p);
+}
+
 template <int OP>   // 0 add, 1 sub, 2 negate
 __global__ void __launch_bounds__(256) ew_addsub_kernel(const ulonglong2 *__restrict__ a, const ulonglong2 *__restrict__ b, ulonglong2 *__restrict__ o,
                                                           const ModInfo *__restrict__ mods, EwShape S) {
@@ -31,8 +38,11 @@ __global__ void __launch_bounds__(256) ew_addsub_kernel(const ulonglong2 *__rest
 }
 
 // out[b][pidx] = sum_{x+y=pidx} a[b][x] o b[b][y]     (kernel_dyadic_convolute, dyadic_convolute.cu:6-42)
-__global__ void __launch_bounds__(256) ew_convolute_kernel(const ulonglong2 *__restrict__ a, u32 na, const ulonglong2 *__restrict__ b, u32 nb,
+// NA, NB > 0: operand sizes known at compile time (operands stay in registers); 0: taken from na_, nb_
+template <int NA, int NB>
+__global__ void __launch_bounds__(256) ew_convolute_kernel(const ulonglong2 *__restrict__ a, u32 na_, const ulonglong2 *__restrict__ b, u32 nb_,
                                                              ulonglong2 *__restrict__ o, const ModInfo *__restrict__ mods, u32 ncomp, u32 n2, u32 batch) {
+    const u32 na = NA ? (u32)NA : na_, nb = NB ? (u32)NB : nb_;
     const u64 per = (u64)ncomp * n2;                      // vectors per polynomial
     const u64 total = (u64)batch * per;
     for (u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (u64)gridDim.x * blockDim.x) {
@@ -40,13 +50,41 @@ __global__ void __launch_bounds__(256) ew_convolute_kernel(const ulonglong2 *__r
         const ModInfo &M = mods[(u32)(r / n2)];
         const u64 p = M.p, r0 = M.r0, r1 = M.r1;
         ulonglong2 av[3], bv[3];
-        for (u32 x = 0; x < na; x++) av[x] = a[(bi * na + x) * per + r];
-        for (u32 y = 0; y < nb; y++) bv[y] = b[(bi * nb + y) * per + r];
+#pragma unroll
+        for (u32 x = 0; x < 3; x++) if (x < na) av[x] = a[(bi * na + x) * per + r];
+#pragma unroll
+        for (u32 y = 0; y < 3; y++) if (y < nb) bv[y] = b[(bi * nb + y) * per + r];
         const u32 no = na + nb - 1;
-        for (u32 pidx = 0; pidx < no; pidx++) {
+        if (M.use_f64) {        // p < 2^41: exact double-double products on the FP64 pipe, one reduction per output
+            const double pd = M.pd, pinv = M.pinv;
+            double ax[3], ay[3], bx[3], by[3];
+#pragma unroll
+            for (u32 x = 0; x < 3; x++) if (x < na) { ax[x] = u64_to_dd(av[x].x); ay[x] = u64_to_dd(av[x].y); }
+#pragma unroll
+            for (u32 y = 0; y < 3; y++) if (y < nb) { bx[y] = u64_to_dd(bv[y].x); by[y] = u64_to_dd(bv[y].y); }
+#pragma unroll
+            for (u32 pidx = 0; pidx < 5; pidx++) {
+                if (pidx >= no) continue;
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (u32 x = 0; x < 3; x++) {
+                    if (x >= na || pidx < x || pidx - x >= nb) continue;
+                    s0 += mulmod_dd(ax[x], bx[pidx - x], pd, pinv);
+                    s1 += mulmod_dd(ay[x], by[pidx - x], pd, pinv);
+                }
+                ulonglong2 res;
+                res.x = dd_to_canonical(reduce_dd(s0, pd, pinv), pd); res.y = dd_to_canonical(reduce_dd(s1, pd, pinv), pd);
+                o[(bi * no + pidx) * per + r] = res;
+            }
+            continue;
+        }
+#pragma unroll
+        for (u32 pidx = 0; pidx < 5; pidx++) {
+            if (pidx >= no) continue;
             u64 l0 = 0, h0 = 0, l1 = 0, h1 = 0;
-            for (u32 x = 0; x < na; x++) {
-                if (pidx < x || pidx - x >= nb) continue;
+#pragma unroll
+            for (u32 x = 0; x < 3; x++) {
+                if (x >= na || pidx < x || pidx - x >= nb) continue;
                 mac128(l0, h0, av[x].x, bv[pidx - x].x);
                 mac128(l1, h1, av[x].y, bv[pidx - x].y);
             }
@@ -67,6 +105,16 @@ __global__ void __launch_bounds__(256) ew_square_kernel(const ulonglong2 *__rest
         const u64 p = M.p, r0 = M.r0, r1 = M.r1;
         const ulonglong2 c0 = a[(bi * 2) * per + r], c1 = a[(bi * 2 + 1) * per + r];
         ulonglong2 o0, o1, o2;
+        if (M.use_f64) {
+            const double pd = M.pd, pinv = M.pinv;
+            const double a0 = u64_to_dd(c0.x), a1 = u64_to_dd(c0.y), b0 = u64_to_dd(c1.x), b1 = u64_to_dd(c1.y);
+            o0.x = dd_to_canonical(mulmod_dd(a0, a0, pd, pinv), pd); o0.y = dd_to_canonical(mulmod_dd(a1, a1, pd, pinv), pd);
+            const double t0 = mulmod_dd(a0, b0, pd, pinv), t1 = mulmod_dd(a1, b1, pd, pinv);
+            o1.x = dd_to_canonical(reduce_dd(t0 + t0, pd, pinv), pd); o1.y = dd_to_canonical(reduce_dd(t1 + t1, pd, pinv), pd);
+            o2.x = dd_to_canonical(mulmod_dd(b0, b0, pd, pinv), pd); o2.y = dd_to_canonical(mulmod_dd(b1, b1, pd, pinv), pd);
+            o[(bi * 3) * per + r] = o0; o[(bi * 3 + 1) * per + r] = o1; o[(bi * 3 + 2) * per + r] = o2;
+            continue;
+        }
         o0.x = mulmod(c0.x, c0.x, p, r0, r1); o0.y = mulmod(c0.y, c0.y, p, r0, r1);
         u64 cx = mulmod(c0.x, c1.x, p, r0, r1), cy = mulmod(c0.y, c1.y, p, r0, r1);
         o1.x = addmod(cx, cx, p); o1.y = addmod(cy, cy, p);
@@ -78,14 +126,16 @@ __global__ void __launch_bounds__(256) ew_square_kernel(const ulonglong2 *__rest
 // out[k] (+)= a[k] o plain , k < pcount          (kernel_dyadic_broadcast_product_ps, dyadic_convolute.cu:151-170)
 template <bool ACC>
 __global__ void __launch_bounds__(256) ew_broadcast_kernel(const ulonglong2 *__restrict__ a, const ulonglong2 *__restrict__ pl, ulonglong2 *__restrict__ o,
-                                                             const ModInfo *__restrict__ mods, EwShape S) {
+                                                             const ModInfo *__restrict__ mods, EwShape S, u64 pstride) {
+    // pstride = vector units of one ciphertext (pcount * ncomp * n2): ciphertext v / pstride of a batch uses plaintext v / pstride
     const u64 per = (u64)S.ncomp * S.n2;
     for (u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x; v < S.total2; v += (u64)gridDim.x * blockDim.x) {
         const ModInfo &M = ew_mod(mods, S, v);
         const u64 p = M.p, r0 = M.r0, r1 = M.r1;
-        const ulonglong2 x = a[v], y = pl[v % per];
+        const ulonglong2 x = a[v], y = pl[(v / pstride) * per + v % per];
         ulonglong2 r;
-        r.x = mulmod(x.x, y.x, p, r0, r1); r.y = mulmod(x.y, y.y, p, r0, r1);
+        if (M.use_f64) { r.x = mulmod_f64(x.x, y.x, M.pd, M.pinv); r.y = mulmod_f64(x.y, y.y, M.pd, M.pinv); }
+        else { r.x = mulmod(x.x, y.x, p, r0, r1); r.y = mulmod(x.y, y.y, p, r0, r1); }
         if (ACC) { const ulonglong2 d = o[v]; r.x = addmod(d.x, r.x, p); r.y = addmod(d.y, r.y, p); }
         o[v] = r;
     }
@@ -181,7 +231,13 @@ b2_status b2_dyadic_convolute(b2_ctx *ctx, const uint64_t *a, size_t na, const u
     EW_PROLOG(a && b && out && na >= 1 && nb >= 1 && na <= 3 && nb <= 3 && ncomp <= ctx->K && ctx->n >= 2, "bad arguments (polynomial counts must be 1..3)");
     if (batch * ncomp == 0) return B2_OK;
     const u64 total = (u64)batch * ncomp * (n / 2);
-    ew_convolute_kernel<<<ew_grid(total), 256, 0, stream>>>((const ulonglong2 *)a, (u32)na, (const ulonglong2 *)b, (u32)nb, (ulonglong2 *)out, ctx->d_mods, (u32)ncomp, (u32)(n / 2), (u32)batch);
+#define B2_CONV(NA, NB) ew_convolute_kernel<NA, NB><<<ew_grid(total), 256, 0, stream>>>((const ulonglong2 *)a, (u32)na, (const ulonglong2 *)b, (u32)nb, (ulonglong2 *)out, ctx->d_mods, (u32)ncomp, (u32)(n / 2), (u32)batch)
+    if (na == 2 && nb == 2) B2_CONV(2, 2);
+    else if (na == 3 && nb == 2) B2_CONV(3, 2);
+    else if (na == 2 && nb == 3) B2_CONV(2, 3);
+    else if (na == 3 && nb == 3) B2_CONV(3, 3);
+    else B2_CONV(0, 0);
+#undef B2_CONV
     count_launches(1);
     B2_CUDA(cudaGetLastError());
     return B2_OK;
@@ -195,15 +251,20 @@ b2_status b2_dyadic_square(b2_ctx *ctx, const uint64_t *a, uint64_t *out, size_t
     B2_CUDA(cudaGetLastError());
     return B2_OK;
 }
-b2_status b2_dyadic_broadcast(b2_ctx *ctx, const uint64_t *a, const uint64_t *plain, uint64_t *out, size_t pcount, size_t ncomp, int accumulate, void *stream_) {
+b2_status b2_dyadic_broadcast_batched(b2_ctx *ctx, const uint64_t *a, const uint64_t *plain, uint64_t *out, size_t batch, size_t pcount, size_t ncomp,
+                                      int accumulate, void *stream_) {
     EW_PROLOG(a && plain && out && ncomp <= ctx->K && ctx->n >= 2, "bad arguments");
-    if (pcount * ncomp == 0) return B2_OK;
-    EwShape S{(u32)ncomp, (u32)(n / 2), 0u, (u64)pcount * ncomp * (n / 2)};
-    if (accumulate) ew_broadcast_kernel<true><<<ew_grid(S.total2), 256, 0, stream>>>((const ulonglong2 *)a, (const ulonglong2 *)plain, (ulonglong2 *)out, ctx->d_mods, S);
-    else ew_broadcast_kernel<false><<<ew_grid(S.total2), 256, 0, stream>>>((const ulonglong2 *)a, (const ulonglong2 *)plain, (ulonglong2 *)out, ctx->d_mods, S);
+    if (batch * pcount * ncomp == 0) return B2_OK;
+    EwShape S{(u32)ncomp, (u32)(n / 2), 0u, (u64)batch * pcount * ncomp * (n / 2)};
+    const u64 pstride = (u64)pcount * ncomp * (n / 2);
+    if (accumulate) ew_broadcast_kernel<true><<<ew_grid(S.total2), 256, 0, stream>>>((const ulonglong2 *)a, (const ulonglong2 *)plain, (ulonglong2 *)out, ctx->d_mods, S, pstride);
+    else ew_broadcast_kernel<false><<<ew_grid(S.total2), 256, 0, stream>>>((const ulonglong2 *)a, (const ulonglong2 *)plain, (ulonglong2 *)out, ctx->d_mods, S, pstride);
     count_launches(1);
     B2_CUDA(cudaGetLastError());
     return B2_OK;
+}
+b2_status b2_dyadic_broadcast(b2_ctx *ctx, const uint64_t *a, const uint64_t *plain, uint64_t *out, size_t pcount, size_t ncomp, int accumulate, void *stream_) {
+    return b2_dyadic_broadcast_batched(ctx, a, plain, out, 1, pcount, ncomp, accumulate, stream_);
 }
 b2_status b2_scale_inv_degree(b2_ctx *ctx, uint64_t *data, size_t count, size_t ncomp, size_t table_base, uint64_t scalar, void *stream_) {
     EW_PROLOG(data && table_base + ncomp <= ctx->K && ctx->n >= 2, "bad arguments");

@@ -102,6 +102,19 @@ __global__ void __launch_bounds__(256) ks_inner_product_kernel(const u64 *__rest
     *reinterpret_cast<ulonglong2 *>(prod + (((u64)b * 2 + 1) * R + i) * n + x) = o1;
 }
 
+// limb-sharded path: the all-gather delivers [world][pad][N] (rank r's owned ciphertext limbs in slot r); one launch
+// compacts it to tc[decomp][N].  Rank ranges as in b2_limb_partition: the first `rem` ranks own base + 1 output moduli.
+__global__ void __launch_bounds__(256) ks_compact_gathered_kernel(const u64 *__restrict__ gathered, u64 *__restrict__ tc, u32 n, u32 pad,
+                                                                    u32 base, u32 rem) {
+    const u32 j = blockIdx.y;                      // ciphertext limb
+    const u32 split = rem * (base + 1);
+    const u32 r = j < split ? j / (base + 1) : rem + (j - split) / base;
+    const u32 first = r * base + min(r, rem);
+    const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(gathered + ((u64)r * pad + (j - first)) * n);
+    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(tc + (u64)j * n);
+    for (u32 x = blockIdx.x * blockDim.x + threadIdx.x; x < n / 2; x += gridDim.x * blockDim.x) dst[x] = src[x];
+}
+
 struct SpecialLoad {      // step 4: the special-prime limb of prod[b][k], c = 2 b + k (row `decomp` of R rows)
     const u64 *prod; u32 R, decomp, n;
     __device__ __forceinline__ const u64 *src(int, int c, u64) const { return prod + ((u64)c * R + decomp) * n; }
@@ -336,12 +349,18 @@ b2_status b2_keyswitch_shard_products(b2_ctx *ctx, const uint64_t *gathered, int
     if (st != B2_OK) return st;
     u64 *prod = (u64 *)ctx->ws, *tc = prod + (2 * count + 2 * nct) * n, *temp = tc + decomp * n;
     // the all-gather delivered [world][pad][N]: rank r's owned ciphertext limbs first_r .. ; compact to tc[decomp][N]
-    for (int r = 0; r < world; r++) {
-        size_t f = 0, c = 0;
-        b2_limb_partition(decomp + 1, world, r, &f, &c);
-        const size_t m = owned_ct_limbs(decomp, f, c);
-        B2_REQUIRE(m <= pad, "pad is smaller than a rank's share of the ciphertext limbs");
-        if (m) B2_CUDA(cudaMemcpyAsync(tc + f * n, gathered + (size_t)r * pad * n, m * n * 8, cudaMemcpyDeviceToDevice, stream));
+    {
+        const size_t R = decomp + 1, base = R / (size_t)world, rem = R % (size_t)world;
+        B2_REQUIRE(pad >= std::min<size_t>(base + (rem ? 1 : 0), decomp), "pad is smaller than a rank's share of the ciphertext limbs");
+        if (base == 0) {    // more ranks than moduli: rank r < rem owns modulus r
+            for (size_t j = 0; j < decomp; j++)
+                B2_CUDA(cudaMemcpyAsync(tc + j * n, gathered + j * pad * n, n * 8, cudaMemcpyDeviceToDevice, stream));
+        } else {
+            dim3 grid((unsigned)std::min<size_t>(64, (n / 2 + 255) / 256), (unsigned)decomp);
+            ks_compact_gathered_kernel<<<grid, 256, 0, stream>>>((const u64 *)gathered, tc, (u32)n, (u32)pad, (u32)base, (u32)rem);
+            count_launches(1);
+            B2_CUDA(cudaGetLastError());
+        }
     }
     PtrTab coef;
     for (int b = 0; b < KS_MAXB; b++) coef.p[b] = b == 0 ? tc : nullptr;

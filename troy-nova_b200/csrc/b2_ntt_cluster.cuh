@@ -1,0 +1,83 @@
+// b2_ntt_cluster.cuh — low-latency N = 2^16 transform for SMALL launches: one thread-block cluster per limb, the
+// intermediate between the two passes lives in distributed shared memory (DSMEM) instead of L2.
+//
+// The persistent kernel (b2_ntt.cuh) is built for throughput: a launch over a few limbs (keyswitch: INTT of the target,
+// INTT of the special limb, the mod-down transform; every stage of the limb-sharded path) is bound by its serial chain
+// queue claim -> tile from HBM -> first pass -> completion counter -> second-pass tile from L2 -> store, ~19 us even
+// for one limb.  Here a limb is owned by a cluster of 16 CTAs (non-portable cluster size, 2 CTAs per SM -> 8 SMs):
+//   CTA r stages column tile r (32 KiB, cp.async), runs the first pass on it (same pass_body as the persistent kernel)
+//   and stores every intermediate word straight into the receive buffer of the CTA that owns it in the second pass
+//   (st.shared::cluster, already in the stage layout the second pass reads); one cluster barrier; CTA r runs the
+//   second pass on row tile r out of its receive buffer.  No work queue, no global counters, no L2 round trip.
+// Same load / store functor interface, same arithmetic back ends, bit-identical results.
+#pragma once
+#include "b2_ntt.cuh"
+
+namespace b2 {
+
+constexpr int CL_SIZE = 16;                               // CTAs per cluster = tiles per limb at N = 2^16
+constexpr int CL_SMEM_BYTES = 3 * NTT_TILE * 8;           // stage | exchange | receive = 96 KiB (2 CTAs per SM)
+
+__device__ __forceinline__ u32 cluster_ctarank() { u32 r; asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+// first-pass store: word at limb position x -> receive buffer of the CTA whose second-pass tile contains x
+//   forward (second pass = row tiles of 16 rows):    tile = x >> 12,          local index = x & 4095
+//   inverse (second pass = column tiles of 16 cols): tile = (x & 255) >> 4,  local index = (row << 4) | (col & 15)
+template <bool FWD>
+struct DsmemStore {
+    u32 recv;      // shared-window address of this CTA's receive buffer (identical offset in every CTA of the cluster)
+    __device__ __forceinline__ void operator()(int, int, u64, u32 x, u64 v) const {
+        const u32 tile = FWD ? x >> 12 : (x & 255u) >> 4;
+        const u32 idx = FWD ? x & 4095u : ((x >> 8) << 4) | (x & 15u);
+        u32 remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(remote) : "r"(recv + 8u * (u32)swz16((int)idx)), "r"(tile));
+        asm volatile("st.shared::cluster.u64 [%0], %1;\n" ::"r"(remote), "l"(v) : "memory");
+    }
+    __device__ __forceinline__ void st2(int g, int c, u64 off, u32 x, u64 v0, u64 v1) const { (*this)(g, c, off, x, v0); (*this)(g, c, off, x + 1, v1); }
+};
+
+struct ClusterHooks {
+    NoHook mid;
+    __device__ __forceinline__ void sync_stage() const { cp_async_wait_all(); __syncthreads(); }
+    __device__ __forceinline__ void pre_exchange() const {}
+    __device__ __forceinline__ void stage_free() const {}
+};
+
+template <bool FWD, class Load, class Store>
+__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_cluster_kernel(const __grid_constant__ NttJob J, Load ld, Store st) {
+    extern __shared__ __align__(128) u64 smem[];
+    u64 *const stage = smem, *const xch = smem + NTT_TILE, *const recv = smem + 2 * NTT_TILE;
+    const u32 r = cluster_ctarank();
+    const u32 limb = blockIdx.x / CL_SIZE;
+    const u32 c = limb / (u32)J.n_groups, g = limb - c * (u32)J.n_groups;
+    const LimbGroup &grp = J.groups[g];
+    const u64 off = grp.base + (u64)c * grp.stride;
+    const ModInfo &M = J.mods[group_table(grp.table)];
+    const u32 path = group_path(grp.table, FWD);
+    const int ga = J.g_base + (int)g;
+    // first-pass tile from the operand: forward = column tile r, inverse = row tile r
+    stage_tile<8, FWD>(stage, ld.src(ga, (int)c, off), (int)r);
+    cp_async_commit();
+    cluster_sync();            // every CTA of the cluster is resident before anyone writes into its shared memory
+    ClusterHooks hk;
+    const DsmemStore<FWD> xst{(u32)__cvta_generic_to_shared(recv)};
+    const PlainLoad none{nullptr};
+    if (FWD) {
+        using Pl = FwdColPlan<8>;
+        pass_dispatch<8, true, true, true, false, Pl::LO0, Pl::NL0, Pl::LO1, Pl::NL1, Pl::LO2, Pl::NL2>(path, stage, xch, M, (int)r, ga, (int)c, off, 16, ld, xst, hk);
+    } else {
+        pass_dispatch<8, false, false, true, false, 0, 4, 4, 4, 0, 0>(path, stage, xch, M, (int)r, ga, (int)c, off, 16, ld, xst, hk);
+    }
+    cluster_sync();            // all intermediates have landed in the receive buffers
+    if (FWD) {
+        pass_dispatch<8, false, true, false, true, 4, 4, 0, 4, 0, 0>(path, recv, xch, M, (int)r, ga, (int)c, off, 16, none, st, hk);
+    } else {
+        using Pl = InvColPlan<8>;
+        pass_dispatch<8, true, false, false, true, Pl::LO0, Pl::NL0, Pl::LO1, Pl::NL1, Pl::LO2, Pl::NL2>(path, recv, xch, M, (int)r, ga, (int)c, off, 16, none, st, hk);
+    }
+}
+
+}  // namespace b2

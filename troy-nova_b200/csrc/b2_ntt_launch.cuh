@@ -2,9 +2,11 @@
 // Included by every translation unit that launches a transform (b2_ntt.cu, b2_keyswitch.cu, b2_rescale.cu).
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 #include "b2_ctx.h"
 #include "b2_ntt.cuh"
+#include "b2_ntt_cluster.cuh"
 
 namespace b2 {
 
@@ -74,6 +76,33 @@ static cudaError_t launch_persistent(const NttJob &J, unsigned grid, cudaStream_
     return cudaGetLastError();
 }
 
+// N = 2^16, few limbs: one 16-CTA cluster per limb, intermediate in distributed shared memory (b2_ntt_cluster.cuh)
+template <bool FWD, class Load, class Store>
+static cudaError_t launch_cluster(const NttJob &J, cudaStream_t s, Load ld, Store st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(ntt_cluster_kernel<FWD, Load, Store>, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ntt_cluster_kernel<FWD, Load, Store>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(J.n_limbs * CL_SIZE, 1, 1);
+    cfg.blockDim = dim3(NTT_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = CL_SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL_SIZE; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, ntt_cluster_kernel<FWD, Load, Store>, J, ld, st);
+}
+// launches of at most this many limbs take the cluster kernel (latency-bound regime); B2_NTT_CLUSTER_MAX overrides (0 = never)
+static inline unsigned cluster_max_limbs() {
+    static const unsigned v = [] { const char *e = getenv("B2_NTT_CLUSTER_MAX"); return e ? (unsigned)atoi(e) : 32u; }();
+    return v;
+}
+
 // groups' base/stride address the intermediate buffer `mid` (raw values between the passes); the
 // functors map (group, limb) to wherever the external operands live.  All groups must have the same count.
 template <class Load, class Store>
@@ -110,6 +139,13 @@ static b2_status run_ntt(b2_ctx *ctx, bool forward, const std::vector<LimbGroup>
         const int A = (int)logn - 8;
         P.tile_shift = logn - NTT_TB;
         P.n_limbs = (u32)(ng * P.count);
+        if (logn == 16 && P.n_limbs <= cluster_max_limbs()) {
+            P.sync = nullptr; P.lag = 0; P.total_items = 0;
+            cudaError_t e = forward ? launch_cluster<true>(P, stream, ld, st) : launch_cluster<false>(P, stream, ld, st);
+            count_launches(1);
+            B2_CUDA(e);
+            continue;
+        }
         P.lag = std::min<u32>(NTT_LAG, P.n_limbs);
         P.total_items = (P.n_limbs << P.tile_shift) * 2;
         b2_status s = ensure_sync(ctx, P.n_limbs, stream);

@@ -459,6 +459,8 @@ void Evaluator::multiply_plain(const Ciphertext &e, const Plaintext &p, Cipherte
 }
 void Evaluator::multiply_plain_batched(const std::vector<const Ciphertext *> &es, const std::vector<const Plaintext *> &ps, const std::vector<Ciphertext *> &ds) const {
     if (es.size() != ps.size() || es.size() != ds.size()) throw std::invalid_argument("[Evaluator::multiply_plain_batched] Size mismatch.");
+    // the operands are separate allocations (the reference's vector<Ciphertext*>): one launch per item; callers that keep a
+    // batch contiguous use b2_dyadic_broadcast_batched directly (one launch for the whole batch)
     for (size_t i = 0; i < es.size(); i++) multiply_plain(*es[i], *ps[i], *ds[i]);
 }
 void Evaluator::multiply_plain_accumulate(const std::vector<const Ciphertext *> &es, const std::vector<const Plaintext *> &ps, Ciphertext &d, bool set_zero) const {
