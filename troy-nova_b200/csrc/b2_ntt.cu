@@ -71,7 +71,7 @@ b2_status b2_ntt_inverse_ptrs(b2_ctx *ctx, const uint64_t *const *in, uint64_t *
     return ntt_ptrs(ctx, false, in, out, batch, pcount, ncomp, mode, table_base, decomp, stream);
 }
 
-// Host-buffer transform, pipelined: the operand is cut into chunks of whole limbs (~4 MiB); chunk c+1 travels host->device
+// Host-buffer transform, pipelined: the operand is cut into chunks of whole limbs (~16 MiB: 1 / 2 / 4 / 8 / 16 / 32 MiB chunks measured 51 / 59 / 70 / 78 / 81 / 79 k limbs/s on B200, r01h); chunk c+1 travels host->device
 // on a copy stream while chunk c is transformed on `stream` and chunk c-1 travels device->host on a second copy stream, so
 // both PCIe directions and the SMs are busy at the same time.  Synchronised on return (the caller's buffers are plain
 // host memory; pinned memory gives full-rate DMA).
@@ -85,7 +85,10 @@ static b2_status ntt_host(b2_ctx *ctx, bool fwd, const uint64_t *in, uint64_t *o
     B2_CUDA(cudaSetDevice(ctx->device));
     st = ensure_stage(ctx, bytes);
     if (st != B2_OK) return st;
-    const size_t chunk = std::max<size_t>(1, std::min<size_t>((size_t)NTT_MAX_GROUPS, ((size_t)4 << 20) / (n * 8)));
+    // chunk size: large enough that a copy runs at link rate, small enough that filling / draining the three-stage pipeline
+    // stays a small part of the call (B2_HOST_CHUNK_MB: developer override for tuning)
+    static const size_t chunk_mb = [] { const char *e = getenv("B2_HOST_CHUNK_MB"); return e && atoi(e) > 0 ? (size_t)atoi(e) : (size_t)16; }();
+    const size_t chunk = std::max<size_t>(1, std::min<size_t>((size_t)NTT_MAX_GROUPS, (chunk_mb << 20) / (n * 8)));
     const size_t nchunks = (limbs + chunk - 1) / chunk;
     st = ensure_copy_pipeline(ctx, 2 * nchunks + 2);
     if (st != B2_OK) return st;
