@@ -57,9 +57,12 @@ struct ModUpLoad {
         const u32 i = (u32)g + g0;
         const u32 ki = i == decomp ? K - 1 : i;
         const u32 j = (u32)c % decomp;
-        const u64 m = mods[ki].p;
-        // q_j <= m_i: already canonical modulo m_i
-        return (mods[j].p <= m) ? v : barrett64(v, m, mods[ki].ratio);
+        const ModInfo &Mi = mods[ki];
+        const u64 m = Mi.p;
+        // q_j <= m_i: already canonical modulo m_i.  FP64-pipe moduli take lazy inputs (|x| < 2^10 m_i, b2_modarith.cuh), so a
+        // digit modulus at most 4 bits longer needs no reduction here either: the transform's first multiplication does it
+        if (mods[j].p <= m || (Mi.use_f64 && mods[j].bits <= Mi.bits + 4)) return v;
+        return barrett64(v, m, Mi.ratio);
     }
 };
 
@@ -69,7 +72,7 @@ struct ModUpLoad {
 // rows are co-scheduled and all but the first hit in L2.
 __global__ void __launch_bounds__(256) ks_inner_product_kernel(const u64 *__restrict__ temp, const u64 *const *__restrict__ keys,
                                                                  u64 *__restrict__ prod, const ModInfo *__restrict__ mods,
-                                                                 u32 decomp, u32 K, u32 n, u32 i0, u32 key_rows) {
+                                                                 u32 decomp, u32 K, u32 n, u32 i0, u32 key_rows, u32 prod_rows, u32 prod_row0) {
     const u32 b = blockIdx.x, nb = gridDim.x;
     const u32 il = blockIdx.z;                      // local output modulus index; the modulus is i0 + il in 0..decomp
     const u32 i = il;
@@ -94,12 +97,12 @@ __global__ void __launch_bounds__(256) ks_inner_product_kernel(const u64 *__rest
             b0l = barrett128(b0l, b0h, p, r0, r1); b0h = 0; b1l = barrett128(b1l, b1h, p, r0, r1); b1h = 0;
         }
     }
-    const u32 R = gridDim.z;
+    const u32 R = prod_rows, io = prod_row0 + il;       // row of this modulus in prod [B][2][prod_rows][N]
     ulonglong2 o0, o1;
     o0.x = barrett128(a0l, a0h, p, r0, r1); o0.y = barrett128(a1l, a1h, p, r0, r1);
     o1.x = barrett128(b0l, b0h, p, r0, r1); o1.y = barrett128(b1l, b1h, p, r0, r1);
-    *reinterpret_cast<ulonglong2 *>(prod + (((u64)b * 2 + 0) * R + i) * n + x) = o0;
-    *reinterpret_cast<ulonglong2 *>(prod + (((u64)b * 2 + 1) * R + i) * n + x) = o1;
+    *reinterpret_cast<ulonglong2 *>(prod + (((u64)b * 2 + 0) * R + io) * n + x) = o0;
+    *reinterpret_cast<ulonglong2 *>(prod + (((u64)b * 2 + 1) * R + io) * n + x) = o1;
 }
 
 // limb-sharded path: the all-gather delivers [world][pad][N] (rank r's owned ciphertext limbs in slot r); one launch
@@ -161,8 +164,14 @@ void b2_kswitch_key_destroy(b2_kswitch_key *k) {
 static b2_status keyswitch_chunk(b2_ctx *ctx, const uint64_t *const *targets, uint64_t *const *dests, size_t nb, size_t decomp, int is_ntt,
                                  const b2_kswitch_key *key, int assign, cudaStream_t stream) {
     const size_t n = ctx->n, K = ctx->K, R = decomp + 1;
-    // workspace: tc [B][decomp][N] | temp [R][B][decomp][N] | prod [B][2][R][N] | u [B][2][N] | mid [B][2][decomp][N]
-    const size_t w_tc = nb * decomp * n, w_temp = R * nb * decomp * n, w_prod = nb * 2 * R * n, w_u = nb * 2 * n, w_mid = nb * 2 * decomp * n;
+    // workspace: tc [B][decomp][N] | temp [blk][B][decomp][N] | prod [B][2][R][N] | u [B][2][N] | mid [B][2][decomp][N]
+    static const size_t blk_env = [] { const char *e = getenv("B2_KS_BLOCK"); return e && atoi(e) > 0 ? (size_t)atoi(e) : (size_t)0; }();
+    // output moduli per mod-up / inner-product block.  Default: all of them in one block.  Smaller blocks keep the block's temp
+    // slice L2-resident between the transform and the inner product, but the shorter transforms lose more to wave
+    // quantisation than the saved HBM traffic buys (C3 on B200, r01h: 21 / 11 / 7 / 5 / 3 moduli per block -> 545 / 570 / 593 /
+    // 646 / 672 us per keyswitch); B2_KS_BLOCK is the developer override the sweep used
+    const size_t blk = std::min(R, blk_env ? blk_env : R);
+    const size_t w_tc = nb * decomp * n, w_temp = blk * nb * decomp * n, w_prod = nb * 2 * R * n, w_u = nb * 2 * n, w_mid = nb * 2 * decomp * n;
     b2_status st = ensure_ws(ctx, (w_tc + w_temp + w_prod + w_u + w_mid) * 8);
     if (st != B2_OK) return st;
     u64 *tc = (u64 *)ctx->ws, *temp = tc + w_tc, *prod = temp + w_temp, *u = prod + w_prod, *mid = u + w_u;
@@ -186,19 +195,22 @@ static b2_status keyswitch_chunk(b2_ctx *ctx, const uint64_t *const *targets, ui
         for (size_t b = 0; b < nb; b++) coef.p[b] = tc + b * decomp * n;
     }
     mark();
-    // 2. mod-up + NTT: group i = output modulus, limbs c = (b, j); results temp[i][b][j]
-    {
+    // 2 + 3. mod-up NTT and key inner product, per block of `blk` output moduli (one block by default, see above)
+    //   group i = output modulus, limbs c = (b, j); temp[il][b][j], il = i - i0
+    for (size_t i0 = 0; i0 < R; i0 += blk) {
+        const size_t cnt = std::min(blk, R - i0);
         std::vector<LimbGroup> groups;
-        for (size_t i = 0; i < R; i++) groups.push_back(LimbGroup{(u32)(i == decomp ? K - 1 : i), (u32)(nb * decomp), (u64)(i * nb * decomp * n), (u64)n});
-        ModUpLoad ld{coef, ctx->d_mods, (u32)decomp, (u32)K, (u32)n, 0u};
+        for (size_t il = 0; il < cnt; il++) {
+            const size_t i = i0 + il;
+            groups.push_back(LimbGroup{(u32)(i == decomp ? K - 1 : i), (u32)(nb * decomp), (u64)(il * nb * decomp * n), (u64)n});
+        }
+        ModUpLoad ld{coef, ctx->d_mods, (u32)decomp, (u32)K, (u32)n, (u32)i0};
         st = run_ntt(ctx, true, groups, temp, ld, PlainStore{temp}, stream);
         if (st != B2_OK) return st;
-    }
-    mark();
-    // 3. key inner product
-    {
-        dim3 grid((unsigned)nb, (unsigned)((n / 2 + 255) / 256), (unsigned)R);
-        ks_inner_product_kernel<<<grid, 256, 0, stream>>>(temp, (const u64 *const *)key->d_ptrs, prod, ctx->d_mods, (u32)decomp, (u32)K, (u32)n, 0u, (u32)K);
+        if (i0 == 0) mark();
+        dim3 grid((unsigned)nb, (unsigned)((n / 2 + 255) / 256), (unsigned)cnt);
+        ks_inner_product_kernel<<<grid, 256, 0, stream>>>(temp, (const u64 *const *)key->d_ptrs, prod, ctx->d_mods, (u32)decomp, (u32)K, (u32)n,
+                                                          (u32)i0, (u32)K, (u32)R, (u32)i0);
         count_launches(1);
         B2_CUDA(cudaGetLastError());
     }
@@ -227,7 +239,7 @@ static b2_status keyswitch_chunk(b2_ctx *ctx, const uint64_t *const *targets, ui
     mark();
     if (timing) {
         cudaEventSynchronize(ev[nev - 1]);
-        static const char *names[] = {"intt(target)", "modup+ntt", "inner product", "intt(special)", "moddown+ntt"};
+        static const char *names[] = {"intt(target)", "modup+ntt (block 0)", "other blocks + inner products", "intt(special)", "moddown+ntt"};
         float tot = 0; cudaEventElapsedTime(&tot, ev[0], ev[nev - 1]);
         fprintf(stderr, "[b2 keyswitch x%zu] total %.1f us:", nb, tot * 1e3f);
         for (int i = 0; i + 1 < nev; i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); fprintf(stderr, " %s %.1f", names[i], ms * 1e3f); }
@@ -377,7 +389,7 @@ b2_status b2_keyswitch_shard_products(b2_ctx *ctx, const uint64_t *gathered, int
     {
         dim3 grid(1, (unsigned)((n / 2 + 255) / 256), (unsigned)count);
         ks_inner_product_kernel<<<grid, 256, 0, stream>>>(temp, (const u64 *const *)shard->d_ptrs, prod, ctx->d_mods, (u32)decomp, (u32)K, (u32)n,
-                                                          (u32)first, (u32)count);
+                                                          (u32)first, (u32)count, (u32)count, 0u);
         count_launches(1);
         B2_CUDA(cudaGetLastError());
     }
