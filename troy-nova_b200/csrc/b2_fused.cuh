@@ -69,9 +69,11 @@ struct ModDownStore {
         const int k = c & 1;
         const bool add = assign == B2_ASSIGN_ADD_INPLACE || (k == 0 && assign == B2_ASSIGN_OVERWRITE_EXCEPT_FIRST);
         u64 *d = dest.p[c >> 1] + ((u64)k * dest_rows + g) * n + x;
-        const u64 s = t_from_transform ? prod[((u64)c * prod_rows + g) * n + x] : 0;
-        const u64 uv = t_from_transform ? 0 : T.u[(u64)c * n + x];
-        *d = one(j, q, s, v, uv, add ? *d : 0, add);
+        // read-only-path loads (ld.global.nc): every word is read at most once, before this thread's own store to it, and by no
+        // other thread — and the compiler may hoist the loads of the following registers above this register's store
+        const u64 s = t_from_transform ? __ldg(prod + ((u64)c * prod_rows + g) * n + x) : 0;
+        const u64 uv = t_from_transform ? 0 : __ldg(T.u + (u64)c * n + x);
+        *d = one(j, q, s, v, uv, add ? __ldg(d) : 0, add);
     }
     // two adjacent coefficients: 16-byte accesses to prod / u / dest
     __device__ __forceinline__ void st2(int g, int c, u64, u32 x, u64 v0, u64 v1) const {
@@ -81,9 +83,9 @@ struct ModDownStore {
         const bool add = assign == B2_ASSIGN_ADD_INPLACE || (k == 0 && assign == B2_ASSIGN_OVERWRITE_EXCEPT_FIRST);
         ulonglong2 *d = reinterpret_cast<ulonglong2 *>(dest.p[c >> 1] + ((u64)k * dest_rows + g) * n + x);
         ulonglong2 s = make_ulonglong2(0, 0), uv = make_ulonglong2(0, 0), dv = make_ulonglong2(0, 0);
-        if (t_from_transform) s = *reinterpret_cast<const ulonglong2 *>(prod + ((u64)c * prod_rows + g) * n + x);
-        else uv = *reinterpret_cast<const ulonglong2 *>(T.u + (u64)c * n + x);
-        if (add) dv = *d;
+        if (t_from_transform) s = __ldg(reinterpret_cast<const ulonglong2 *>(prod + ((u64)c * prod_rows + g) * n + x));
+        else uv = __ldg(reinterpret_cast<const ulonglong2 *>(T.u + (u64)c * n + x));
+        if (add) dv = __ldg(d);
         *d = make_ulonglong2(one(j, q, s.x, v0, uv.x, dv.x, add), one(j, q, s.y, v1, uv.y, dv.y, add));
     }
 };
@@ -98,12 +100,12 @@ struct RescaleStore {
     u32 nl, n;
     __device__ __forceinline__ void operator()(int i, int p, u64, u32 x, u64 t) const {
         const u64 q = mods[i].p;
-        const u64 s = in[((u64)p * nl + i) * n + x];
+        const u64 s = __ldg(in + ((u64)p * nl + i) * n + x);
         out[((u64)p * (nl - 1) + i) * n + x] = shoup(submod(s, t, q), inv[i], q);
     }
     __device__ __forceinline__ void st2(int i, int p, u64, u32 x, u64 t0, u64 t1) const {
         const u64 q = mods[i].p;
-        const ulonglong2 s = *reinterpret_cast<const ulonglong2 *>(in + ((u64)p * nl + i) * n + x);
+        const ulonglong2 s = __ldg(reinterpret_cast<const ulonglong2 *>(in + ((u64)p * nl + i) * n + x));
         *reinterpret_cast<ulonglong2 *>(out + ((u64)p * (nl - 1) + i) * n + x) =
             make_ulonglong2(shoup(submod(s.x, t0, q), inv[i], q), shoup(submod(s.y, t1, q), inv[i], q));
     }

@@ -45,6 +45,7 @@ extern "C" b2_status b2_mod_switch_to_next(b2_ctx *ctx, const uint64_t *in, uint
     B2_REQUIRE((((uintptr_t)in | (uintptr_t)out) & 15) == 0, "operands must be 16-byte aligned");
     B2_REQUIRE(nl >= 2 && nl <= ctx->K, "need at least two limbs to drop one");
     B2_REQUIRE(kind >= 0 && kind <= 3, "unknown kind");
+    B2_REQUIRE(in != out, "in-place mod switch is not supported: the output has one limb less per polynomial (the reference writes a new ciphertext too)");
     if (count == 0) return B2_OK;
     B2_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t stream = (cudaStream_t)stream_;
