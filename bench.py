@@ -143,7 +143,8 @@ def run_reference_arm(args):
     cb = dict(vals[-1]); cb["value"] = v
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "C3 CKKS N=65536: forward+inverse negacyclic NTT, 60/40-bit primes, reference host branch, bounded sample per step"},
+            "config": {"workload": "C3 CKKS N=65536, q={60,40x19,60}: forward+inverse negacyclic NTT of a [20][21][N] operand (420 limbs, 210 MiB) per GPU per step",
+                       "sample": "reference host branch (utils::ntt_inplace_ps on host slices), %.1f s of [2][3][N] forward+inverse calls per step on every host thread, 60/40-bit primes" % per_step},
             "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 

@@ -284,7 +284,7 @@ struct BehzLoad {
         if ((u32)g < L) { const u32 bi = (u32)c >> 2, w = (u32)c & 3; return ((w < 2) ? a : b) + ((u64)(bi * 2 + (w & 1)) * L + g) * n; }
         return lifted + ((u64)c * S + ((u32)g - L)) * n;
     }
-    __device__ __forceinline__ u64 xf(int, int, u32, u64 raw) const { return raw; }
+    B2_IDENTITY_XF
 };
 
 }  // namespace b2
@@ -323,7 +323,7 @@ extern "C" b2_status b2_bfv_multiply(b2_ctx *ctx, const uint64_t *a, const uint6
         for (size_t j = 0; j < L; j++) groups.push_back(LimbGroup{(u32)j, (u32)(4 * batch), (u64)(j * n), (u64)(L * n)});
         for (size_t o = 0; o < S; o++) groups.push_back(LimbGroup{bsk_slot((u32)K, D.nB, (u32)o), (u32)(4 * batch), (u64)(w_q + o * n), (u64)(S * n)});
         BehzLoad ld{(const u64 *)a, (const u64 *)b, lifted, (u32)L, (u32)S, (u32)n};
-        st = run_ntt(ctx, true, groups, wq, ld, PlainStore{wq}, stream);
+        st = run_ntt_dir<true>(ctx, groups, wq, ld, PlainStore{wq}, stream);
         if (st != B2_OK) return st;
     }
     {   // (4)
@@ -337,7 +337,7 @@ extern "C" b2_status b2_bfv_multiply(b2_ctx *ctx, const uint64_t *a, const uint6
         std::vector<LimbGroup> groups;
         for (size_t j = 0; j < L; j++) groups.push_back(LimbGroup{(u32)j, (u32)(3 * batch), (u64)(j * n), (u64)(L * n)});
         for (size_t o = 0; o < S; o++) groups.push_back(LimbGroup{bsk_slot((u32)K, D.nB, (u32)o), (u32)(3 * batch), (u64)(w_pq + o * n), (u64)(S * n)});
-        st = run_ntt(ctx, false, groups, pq, PlainLoad{pq}, PlainStore{pq}, stream);
+        st = run_ntt_dir<false>(ctx, groups, pq, PlainLoad{pq}, PlainStore{pq}, stream);
         if (st != B2_OK) return st;
     }
     {   // (6)-(8)

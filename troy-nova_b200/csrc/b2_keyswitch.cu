@@ -39,7 +39,7 @@ namespace b2 {
 struct TargetLoad {
     PtrTab t; u32 n;
     __device__ __forceinline__ const u64 *src(int j, int b, u64) const { return t.p[b] + (u64)j * n; }
-    __device__ __forceinline__ u64 xf(int, int, u32, u64 raw) const { return raw; }
+    B2_IDENTITY_XF
 };
 
 // ---- step 2 loader: c_j re-reduced modulo the group's modulus (src/fgk/switch_key.cu:6-27) ----------
@@ -53,17 +53,20 @@ struct ModUpLoad {
         const u32 b = (u32)c / decomp, j = (u32)c - b * decomp;
         return tc.p[b] + (u64)j * n;
     }
-    __device__ __forceinline__ u64 xf(int g, int c, u32, u64 v) const {
+    struct Prep { u64 m, ratio; bool reduce; };
+    __device__ __forceinline__ Prep prep(int g, int c) const {
         const u32 i = (u32)g + g0;
         const u32 ki = i == decomp ? K - 1 : i;
         const u32 j = (u32)c % decomp;
         const ModInfo &Mi = mods[ki];
-        const u64 m = Mi.p;
+        Prep r;
+        r.m = Mi.p; r.ratio = Mi.ratio;
         // q_j <= m_i: already canonical modulo m_i.  FP64-pipe moduli take lazy inputs (|x| < 2^10 m_i, b2_modarith.cuh), so a
         // digit modulus at most 4 bits longer needs no reduction here either: the transform's first multiplication does it
-        if (mods[j].p <= m || (Mi.use_f64 && mods[j].bits <= Mi.bits + 4)) return v;
-        return barrett64(v, m, Mi.ratio);
+        r.reduce = !(mods[j].p <= r.m || (Mi.use_f64 && mods[j].bits <= Mi.bits + 4));
+        return r;
     }
+    __device__ __forceinline__ u64 xf(const Prep &pc, u32, u64 v) const { return pc.reduce ? barrett64(v, pc.m, pc.ratio) : v; }
 };
 
 // ---- step 3: key inner product (src/fgk/switch_key.cu:77-132) --------------------------------------
@@ -121,14 +124,38 @@ __global__ void __launch_bounds__(256) ks_compact_gathered_kernel(const u64 *__r
 struct SpecialLoad {      // step 4: the special-prime limb of prod[b][k], c = 2 b + k (row `decomp` of R rows)
     const u64 *prod; u32 R, decomp, n;
     __device__ __forceinline__ const u64 *src(int, int c, u64) const { return prod + ((u64)c * R + decomp) * n; }
-    __device__ __forceinline__ u64 xf(int, int, u32, u64 raw) const { return raw; }
+    B2_IDENTITY_XF
 };
 struct ProdLoad {         // coefficient-form path: transform prod[b][k][j] itself (inverse NTT); `rows` rows per polynomial
     const u64 *prod; u32 rows, n;
     __device__ __forceinline__ const u64 *src(int j, int c, u64) const { return prod + ((u64)c * rows + j) * n; }
-    __device__ __forceinline__ u64 xf(int, int, u32, u64 raw) const { return raw; }
+    B2_IDENTITY_XF
 };
 
+
+// step 5 launcher: the scheme (BGV or not) and the ciphertext form select one kernel instantiation each
+template <bool BGV>
+static b2_status mod_down_t(b2_ctx *ctx, const std::vector<LimbGroup> &groups, u64 *mid, const u64 *u, const u64 *prod, const PtrTabW &dp, size_t decomp,
+                            int assign, int is_ntt, size_t jbase, size_t prod_rows, size_t dest_rows, cudaStream_t stream) {
+    const size_t K = ctx->K, n = ctx->n;
+    ModDownTerm<BGV> T{u, ctx->d_mods, (u32)(K - 1), (u32)n, ctx->t, ctx->t_ratio, ctx->t_r0, ctx->t_r1, BGV ? ctx->h_inv_mod_t[K - 1] : 0};
+    if (is_ntt) {
+        ModDownStore<BGV, true> sst{T, prod, ctx->d_inv + (K - 1) * K, dp, (u32)decomp, (u32)assign, (u32)jbase, (u32)prod_rows, (u32)dest_rows};
+        return run_ntt_dir<true>(ctx, groups, mid, ModDownLoad<BGV>{T, (u32)jbase}, sst, stream);
+    }
+    ModDownStore<BGV, false> sst{T, prod, ctx->d_inv + (K - 1) * K, dp, (u32)decomp, (u32)assign, (u32)jbase, (u32)prod_rows, (u32)dest_rows};
+    return run_ntt_dir<false>(ctx, groups, mid, ProdLoad{prod, (u32)prod_rows, (u32)n}, sst, stream);
+}
+static b2_status mod_down(b2_ctx *ctx, const std::vector<LimbGroup> &groups, u64 *mid, const u64 *u, const u64 *prod, const PtrTabW &dp, size_t decomp,
+                          int assign, int is_ntt, size_t jbase, size_t prod_rows, size_t dest_rows, cudaStream_t stream) {
+    // BGV ciphertexts are always NTT-form (checked by the callers): the coefficient-form BGV kernel is never instantiated
+    if (ctx->scheme == B2_SCHEME_BGV) {
+        ModDownTerm<true> T{u, ctx->d_mods, (u32)(ctx->K - 1), (u32)ctx->n, ctx->t, ctx->t_ratio, ctx->t_r0, ctx->t_r1, ctx->h_inv_mod_t[ctx->K - 1]};
+        ModDownStore<true, true> sst{T, prod, ctx->d_inv + (ctx->K - 1) * ctx->K, dp, (u32)decomp, (u32)assign, (u32)jbase, (u32)prod_rows, (u32)dest_rows};
+        return run_ntt_dir<true>(ctx, groups, mid, ModDownLoad<true>{T, (u32)jbase}, sst, stream);
+    }
+    return mod_down_t<false>(ctx, groups, mid, u, prod, dp, decomp, assign, is_ntt, jbase, prod_rows, dest_rows, stream);
+}
 }  // namespace b2
 
 extern "C" {
@@ -190,7 +217,7 @@ static b2_status keyswitch_chunk(b2_ctx *ctx, const uint64_t *const *targets, ui
         std::vector<LimbGroup> groups;
         for (size_t j = 0; j < decomp; j++) groups.push_back(LimbGroup{(u32)j, (u32)nb, (u64)(j * n), (u64)(decomp * n)});
         TargetLoad ld{coef, (u32)n};
-        st = run_ntt(ctx, false, groups, tc, ld, PlainStore{tc}, stream);
+        st = run_ntt_dir<false>(ctx, groups, tc, ld, PlainStore{tc}, stream);
         if (st != B2_OK) return st;
         for (size_t b = 0; b < nb; b++) coef.p[b] = tc + b * decomp * n;
     }
@@ -205,7 +232,7 @@ static b2_status keyswitch_chunk(b2_ctx *ctx, const uint64_t *const *targets, ui
             groups.push_back(LimbGroup{(u32)(i == decomp ? K - 1 : i), (u32)(nb * decomp), (u64)(il * nb * decomp * n), (u64)n});
         }
         ModUpLoad ld{coef, ctx->d_mods, (u32)decomp, (u32)K, (u32)n, (u32)i0};
-        st = run_ntt(ctx, true, groups, temp, ld, PlainStore{temp}, stream);
+        st = run_ntt_dir<true>(ctx, groups, temp, ld, PlainStore{temp}, stream);
         if (st != B2_OK) return st;
         if (i0 == 0) mark();
         dim3 grid((unsigned)nb, (unsigned)((n / 2 + 255) / 256), (unsigned)cnt);
@@ -219,7 +246,7 @@ static b2_status keyswitch_chunk(b2_ctx *ctx, const uint64_t *const *targets, ui
     {
         std::vector<LimbGroup> groups{LimbGroup{(u32)(K - 1), (u32)(2 * nb), 0, (u64)n}};
         SpecialLoad ld{prod, (u32)R, (u32)decomp, (u32)n};
-        st = run_ntt(ctx, false, groups, u, ld, PlainStore{u}, stream);
+        st = run_ntt_dir<false>(ctx, groups, u, ld, PlainStore{u}, stream);
         if (st != B2_OK) return st;
     }
     mark();
@@ -227,13 +254,9 @@ static b2_status keyswitch_chunk(b2_ctx *ctx, const uint64_t *const *targets, ui
     {
         std::vector<LimbGroup> groups;
         for (size_t j = 0; j < decomp; j++) groups.push_back(LimbGroup{(u32)j, (u32)(2 * nb), (u64)(j * n), (u64)(decomp * n)});
-        ModDownTerm T{u, ctx->d_mods, (u32)(K - 1), (u32)n, ctx->scheme == B2_SCHEME_BGV ? 1 : 0, ctx->t, ctx->t_ratio, ctx->t_r0, ctx->t_r1,
-                      ctx->h_inv_mod_t[K - 1]};
         PtrTabW dp;
         for (size_t b = 0; b < (size_t)KS_MAXB; b++) dp.p[b] = b < nb ? (u64 *)dests[b] : nullptr;
-        ModDownStore sst{T, prod, ctx->d_inv + (K - 1) * K, dp, (u32)decomp, (u32)assign, is_ntt ? 1 : 0, 0u, (u32)R, (u32)decomp};
-        if (is_ntt) st = run_ntt(ctx, true, groups, mid, ModDownLoad{T}, sst, stream);
-        else st = run_ntt(ctx, false, groups, mid, ProdLoad{prod, (u32)R, (u32)n}, sst, stream);
+        st = mod_down(ctx, groups, mid, u, prod, dp, decomp, assign, is_ntt, 0, R, decomp, stream);
         if (st != B2_OK) return st;
     }
     mark();
@@ -341,7 +364,7 @@ b2_status b2_keyswitch_shard_prepare(b2_ctx *ctx, const uint64_t *target_local, 
     for (size_t jl = 0; jl < nct; jl++) groups.push_back(LimbGroup{(u32)(first + jl), 1u, (u64)(jl * n), 0});
     PtrTab coef;
     for (int b = 0; b < KS_MAXB; b++) coef.p[b] = b == 0 ? (const u64 *)target_local : nullptr;
-    return run_ntt(ctx, false, groups, (u64 *)send, TargetLoad{coef, (u32)n}, PlainStore{(u64 *)send}, stream);
+    return run_ntt_dir<false>(ctx, groups, (u64 *)send, TargetLoad{coef, (u32)n}, PlainStore{(u64 *)send}, stream);
 }
 
 // workspace of the sharded stages: prod [2][count][N] | mid [2][nct][N] | tc [decomp][N] | temp [count][decomp][N];
@@ -383,7 +406,7 @@ b2_status b2_keyswitch_shard_products(b2_ctx *ctx, const uint64_t *gathered, int
             groups.push_back(LimbGroup{(u32)(i == decomp ? K - 1 : i), (u32)decomp, (u64)(il * decomp * n), (u64)n});
         }
         ModUpLoad ld{coef, ctx->d_mods, (u32)decomp, (u32)K, (u32)n, (u32)first};
-        st = run_ntt(ctx, true, groups, temp, ld, PlainStore{temp}, stream);
+        st = run_ntt_dir<true>(ctx, groups, temp, ld, PlainStore{temp}, stream);
         if (st != B2_OK) return st;
     }
     {
@@ -396,7 +419,7 @@ b2_status b2_keyswitch_shard_products(b2_ctx *ctx, const uint64_t *gathered, int
     if (owns_special) {
         std::vector<LimbGroup> groups{LimbGroup{(u32)(K - 1), 2u, 0, (u64)n}};
         SpecialLoad ld{prod, (u32)count, (u32)(count - 1), (u32)n};
-        st = run_ntt(ctx, false, groups, (u64 *)u, ld, PlainStore{(u64 *)u}, stream);
+        st = run_ntt_dir<false>(ctx, groups, (u64 *)u, ld, PlainStore{(u64 *)u}, stream);
         if (st != B2_OK) return st;
     }
     return B2_OK;
@@ -417,13 +440,9 @@ b2_status b2_keyswitch_shard_finish(b2_ctx *ctx, const uint64_t *u, size_t decom
     u64 *prod = (u64 *)ctx->ws, *mid = prod + 2 * count * n;
     std::vector<LimbGroup> groups;
     for (size_t jl = 0; jl < nct; jl++) groups.push_back(LimbGroup{(u32)(first + jl), 2u, (u64)(jl * n), (u64)(nct * n)});
-    ModDownTerm T{(const u64 *)u, ctx->d_mods, (u32)(K - 1), (u32)n, ctx->scheme == B2_SCHEME_BGV ? 1 : 0, ctx->t, ctx->t_ratio, ctx->t_r0, ctx->t_r1,
-                  ctx->h_inv_mod_t[K - 1]};
     PtrTabW dp;
     for (int b = 0; b < KS_MAXB; b++) dp.p[b] = b == 0 ? (u64 *)dest_local : nullptr;
-    ModDownStore sst{T, prod, ctx->d_inv + (K - 1) * K, dp, (u32)decomp, (u32)assign, is_ntt ? 1 : 0, (u32)first, (u32)count, (u32)nct};
-    if (is_ntt) return run_ntt(ctx, true, groups, mid, ModDownLoad{T, (u32)first}, sst, stream);
-    return run_ntt(ctx, false, groups, mid, ProdLoad{prod, (u32)count, (u32)n}, sst, stream);
+    return mod_down(ctx, groups, mid, (const u64 *)u, prod, dp, decomp, assign, is_ntt, first, count, nct, stream);
 }
 
 }  // extern "C"

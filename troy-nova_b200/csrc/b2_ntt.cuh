@@ -246,21 +246,30 @@ __device__ __forceinline__ void inv_round(const AR &ar, typename AR::T (&v)[16],
 
 // ---- load / store functors -------------------------------------------------------------------------
 // A LOAD functor names, for limb c of group g, where the limb's N source words live (src) and an
-// element-wise transform applied when the staged word is read into registers (xf).  `off` is the limb's
-// element offset in the intermediate buffer (LimbGroup base + c * stride); plain transforms use it for
-// the operand as well.  Sources must be 16-byte aligned (cp.async).
+// element-wise transform applied when the staged word is read into registers: prep(g, c) is evaluated ONCE per
+// work item and returns whatever per-limb constants the transform needs, xf(prep, x, raw) is evaluated per word
+// (the per-limb part used to be re-evaluated per word — ptxas does not hoist it out of the unrolled loop — which made
+// the fused first passes 70 % - 400 % longer in instructions, r01h SASS).  `off` is the limb's element offset in the
+// intermediate buffer (LimbGroup base + c * stride); plain transforms use it for the operand as well.  Sources must be
+// 16-byte aligned (cp.async).
+#define B2_IDENTITY_XF                                                                   \
+    struct Prep {};                                                                      \
+    __device__ __forceinline__ Prep prep(int, int) const { return Prep{}; }              \
+    __device__ __forceinline__ u64 xf(const Prep &, u32, u64 raw) const { return raw; }
 struct PlainLoad {
     const u64 *base;
     __device__ __forceinline__ const u64 *src(int, int, u64 off) const { return base + off; }
-    __device__ __forceinline__ u64 xf(int, int, u32, u64 raw) const { return raw; }
+    B2_IDENTITY_XF
 };
-// A STORE functor receives canonical results: st(g, c, off, x, v) one word, st2 two adjacent words
-// (x even).  The default st2 is two st calls.
+// A STORE functor receives canonical results.  prep(g, c, off) is evaluated once per work item (row pointers, per-limb
+// constants), st(prep, x, v) stores one word at limb position x, st2(prep, x, v0, v1) two adjacent words (x even).
 struct PlainStore {
     u64 *base;
-    __device__ __forceinline__ void operator()(int, int, u64 off, u32 x, u64 v) const { base[off + x] = v; }
-    __device__ __forceinline__ void st2(int, int, u64 off, u32 x, u64 v0, u64 v1) const {
-        *reinterpret_cast<ulonglong2 *>(base + off + x) = make_ulonglong2(v0, v1);
+    struct Prep { u64 *p; };
+    __device__ __forceinline__ Prep prep(int, int, u64 off) const { return Prep{base + off}; }
+    __device__ __forceinline__ void operator()(const Prep &pc, u32 x, u64 v) const { pc.p[x] = v; }
+    __device__ __forceinline__ void st2(const Prep &pc, u32 x, u64 v0, u64 v1) const {
+        *reinterpret_cast<ulonglong2 *>(pc.p + x) = make_ulonglong2(v0, v1);
     }
 };
 
@@ -337,9 +346,14 @@ __device__ __forceinline__ void pass_body(const u64 *stage, u64 *sm, const ModIn
 #pragma unroll
             for (int k = 0; k < 16; k++) raw[k] = stage[sb ^ swz16(k << LO0)];
         }
+        if (FIRST) {
+            const auto lp = ld.prep(g, c);
 #pragma unroll
-        for (int k = 0; k < 16; k++)
-            v[k] = FIRST ? ar.from_ext(ld.xf(g, c, xt + ((u32)k << G::xbit(LO0)), raw[k])) : ar.from_raw(raw[k]);
+            for (int k = 0; k < 16; k++) v[k] = ar.from_ext(ld.xf(lp, xt + ((u32)k << G::xbit(LO0)), raw[k]));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; k++) v[k] = ar.from_raw(raw[k]);
+        }
         if (FWD) fwd_round<NL0, G::xbit(LO0)>(ar, v, xt, logn, tw0, hk.mid);
         else inv_round<NL0, G::xbit(LO0), LASTL && NR == 1>(ar, v, xt, logn, tw0, hk.mid);
         if (NR > 1) {
@@ -389,12 +403,13 @@ __device__ __forceinline__ void pass_body(const u64 *stage, u64 *sm, const ModIn
                 o[k] = ar.to_raw(v[k]);
             }
         }
+        const auto sp = st.prep(g, c, off);
         if (G::xbit(LOL) == 0) {     // 16 adjacent words per thread: 16-byte stores
 #pragma unroll
-            for (int k = 0; k < 16; k += 2) st.st2(g, c, off, xt + (u32)k, o[k], o[k + 1]);
+            for (int k = 0; k < 16; k += 2) st.st2(sp, xt + (u32)k, o[k], o[k + 1]);
         } else {
 #pragma unroll
-            for (int k = 0; k < 16; k++) st(g, c, off, xt + ((u32)k << G::xbit(LOL)), o[k]);
+            for (int k = 0; k < 16; k++) st(sp, xt + ((u32)k << G::xbit(LOL)), o[k]);
         }
     }
 }

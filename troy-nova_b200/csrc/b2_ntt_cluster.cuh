@@ -29,14 +29,16 @@ __device__ __forceinline__ void cluster_sync() {
 template <bool FWD>
 struct DsmemStore {
     u32 recv;      // shared-window address of this CTA's receive buffer (identical offset in every CTA of the cluster)
-    __device__ __forceinline__ void operator()(int, int, u64, u32 x, u64 v) const {
+    struct Prep {};
+    __device__ __forceinline__ Prep prep(int, int, u64) const { return Prep{}; }
+    __device__ __forceinline__ void operator()(const Prep &, u32 x, u64 v) const {
         const u32 tile = FWD ? x >> 12 : (x & 255u) >> 4;
         const u32 idx = FWD ? x & 4095u : ((x >> 8) << 4) | (x & 15u);
         u32 remote;
         asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(remote) : "r"(recv + 8u * (u32)swz16((int)idx)), "r"(tile));
         asm volatile("st.shared::cluster.u64 [%0], %1;\n" ::"r"(remote), "l"(v) : "memory");
     }
-    __device__ __forceinline__ void st2(int g, int c, u64 off, u32 x, u64 v0, u64 v1) const { (*this)(g, c, off, x, v0); (*this)(g, c, off, x + 1, v1); }
+    __device__ __forceinline__ void st2(const Prep &pc, u32 x, u64 v0, u64 v1) const { (*this)(pc, x, v0); (*this)(pc, x + 1, v1); }
 };
 
 struct ClusterHooks {

@@ -24,7 +24,8 @@ __global__ void ntt_small_kernel(const __grid_constant__ NttJob P, Load ld, Stor
     const u64 p = M.p, p2 = p << 1;
     const ArithInt<false> ar(M);
     const u64 *src = ld.src(g, c, off);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) sm[i] = ld.xf(g, c, (u32)i, src[i]);
+    const auto lp = ld.prep(g, c);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sm[i] = ld.xf(lp, (u32)i, src[i]);
     __syncthreads();
     for (int layer = 0; layer < logn; layer++) {
         for (int i = threadIdx.x; i < half; i += blockDim.x) {
@@ -51,7 +52,8 @@ __global__ void ntt_small_kernel(const __grid_constant__ NttJob P, Load ld, Stor
         }
         __syncthreads();
     }
-    for (int i = threadIdx.x; i < n; i += blockDim.x) st(g, c, off, (u32)i, FWD ? csub(csub(sm[i], p2), p) : sm[i]);
+    const auto sp = st.prep(g, c, off);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) st(sp, (u32)i, FWD ? csub(csub(sm[i], p2), p) : sm[i]);
 }
 
 // second-pass items trail first-pass items by this many limbs: at N = 2^16 the in-flight intermediate is
@@ -105,9 +107,9 @@ static inline unsigned cluster_max_limbs() {
 
 // groups' base/stride address the intermediate buffer `mid` (raw values between the passes); the
 // functors map (group, limb) to wherever the external operands live.  All groups must have the same count.
-template <class Load, class Store>
-static b2_status run_ntt(b2_ctx *ctx, bool forward, const std::vector<LimbGroup> &groups, u64 *mid, Load ld, Store st,
-                         cudaStream_t stream) {
+// The direction is a template parameter so that a call site instantiates only the kernels it launches.
+template <bool FWD, class Load, class Store>
+static b2_status run_ntt_dir(b2_ctx *ctx, const std::vector<LimbGroup> &groups, u64 *mid, Load ld, Store st, cudaStream_t stream) {
     const unsigned logn = ctx->logn;
     const size_t n = ctx->n;
     if (groups.empty() || groups[0].count == 0) return B2_OK;
@@ -130,8 +132,7 @@ static b2_status run_ntt(b2_ctx *ctx, bool forward, const std::vector<LimbGroup>
         if (logn <= 11) {
             const int threads = (int)std::max<size_t>(32, std::min<size_t>(n / 2, 1024));
             dim3 grid(P.count, (unsigned)ng);
-            if (forward) ntt_small_kernel<true><<<grid, threads, n * 8, stream>>>(P, ld, st);
-            else ntt_small_kernel<false><<<grid, threads, n * 8, stream>>>(P, ld, st);
+            ntt_small_kernel<FWD><<<grid, threads, n * 8, stream>>>(P, ld, st);
             count_launches(1);
             B2_CUDA(cudaGetLastError());
             continue;
@@ -141,7 +142,7 @@ static b2_status run_ntt(b2_ctx *ctx, bool forward, const std::vector<LimbGroup>
         P.n_limbs = (u32)(ng * P.count);
         if (logn == 16 && P.n_limbs <= cluster_max_limbs()) {
             P.sync = nullptr; P.lag = 0; P.total_items = 0;
-            cudaError_t e = forward ? launch_cluster<true>(P, stream, ld, st) : launch_cluster<false>(P, stream, ld, st);
+            cudaError_t e = launch_cluster<FWD>(P, stream, ld, st);
             count_launches(1);
             B2_CUDA(e);
             continue;
@@ -153,29 +154,24 @@ static b2_status run_ntt(b2_ctx *ctx, bool forward, const std::vector<LimbGroup>
         P.sync = ctx->d_sync;
         const unsigned grid = std::min<unsigned>(P.total_items, (unsigned)NTT_OCC * (unsigned)ctx->sm_count);
         cudaError_t e;
-        if (forward) {
-            switch (A) {
-            case 4: e = launch_persistent<4, true>(P, grid, stream, ld, st); break;
-            case 5: e = launch_persistent<5, true>(P, grid, stream, ld, st); break;
-            case 6: e = launch_persistent<6, true>(P, grid, stream, ld, st); break;
-            case 7: e = launch_persistent<7, true>(P, grid, stream, ld, st); break;
-            case 8: e = launch_persistent<8, true>(P, grid, stream, ld, st); break;
-            default: e = launch_persistent<9, true>(P, grid, stream, ld, st); break;
-            }
-        } else {
-            switch (A) {
-            case 4: e = launch_persistent<4, false>(P, grid, stream, ld, st); break;
-            case 5: e = launch_persistent<5, false>(P, grid, stream, ld, st); break;
-            case 6: e = launch_persistent<6, false>(P, grid, stream, ld, st); break;
-            case 7: e = launch_persistent<7, false>(P, grid, stream, ld, st); break;
-            case 8: e = launch_persistent<8, false>(P, grid, stream, ld, st); break;
-            default: e = launch_persistent<9, false>(P, grid, stream, ld, st); break;
-            }
+        switch (A) {
+        case 4: e = launch_persistent<4, FWD>(P, grid, stream, ld, st); break;
+        case 5: e = launch_persistent<5, FWD>(P, grid, stream, ld, st); break;
+        case 6: e = launch_persistent<6, FWD>(P, grid, stream, ld, st); break;
+        case 7: e = launch_persistent<7, FWD>(P, grid, stream, ld, st); break;
+        case 8: e = launch_persistent<8, FWD>(P, grid, stream, ld, st); break;
+        default: e = launch_persistent<9, FWD>(P, grid, stream, ld, st); break;
         }
         count_launches(1);
         B2_CUDA(e);
     }
     return B2_OK;
 }
+// run-time direction (the plain transforms of b2_ntt.cu)
+template <class Load, class Store>
+static b2_status run_ntt(b2_ctx *ctx, bool forward, const std::vector<LimbGroup> &groups, u64 *mid, Load ld, Store st, cudaStream_t stream) {
+    return forward ? run_ntt_dir<true>(ctx, groups, mid, ld, st, stream) : run_ntt_dir<false>(ctx, groups, mid, ld, st, stream);
+}
+
 
 }  // namespace b2

@@ -72,16 +72,20 @@ extern "C" b2_status b2_mod_switch_to_next(b2_ctx *ctx, const uint64_t *in, uint
     u64 *u = (u64 *)ctx->ws, *mid = u + count * n;
     {   // u_p = INTT_{q_last}(in[p][last])
         std::vector<LimbGroup> groups{LimbGroup{(u32)last, (u32)count, 0, (u64)n}};
-        st = run_ntt(ctx, false, groups, u, LastLimbLoad{(const u64 *)in, (u32)nl, (u32)n}, PlainStore{u}, stream);
+        st = run_ntt_dir<false>(ctx, groups, u, LastLimbLoad{(const u64 *)in, (u32)nl, (u32)n}, PlainStore{u}, stream);
         if (st != B2_OK) return st;
     }
     {   // NTT of the correction term, final store scales by q_last^-1
         std::vector<LimbGroup> groups;
         for (size_t i = 0; i + 1 < nl; i++) groups.push_back(LimbGroup{(u32)i, (u32)count, (u64)(i * n), (u64)((nl - 1) * n)});
-        ModDownTerm T{u, ctx->d_mods, (u32)last, (u32)n, kind == B2_MODSWITCH_BGV ? 1 : 0, ctx->t, ctx->t_ratio, ctx->t_r0, ctx->t_r1,
-                      ctx->t > 1 ? ctx->h_inv_mod_t[last] : 0};
         RescaleStore sst{(const u64 *)in, (u64 *)out, ctx->d_mods, ctx->d_inv + last * K, (u32)nl, (u32)n};
-        st = run_ntt(ctx, true, groups, mid, ModDownLoad{T}, sst, stream);
+        if (kind == B2_MODSWITCH_BGV) {
+            ModDownTerm<true> T{u, ctx->d_mods, (u32)last, (u32)n, ctx->t, ctx->t_ratio, ctx->t_r0, ctx->t_r1, ctx->h_inv_mod_t[last]};
+            st = run_ntt_dir<true>(ctx, groups, mid, ModDownLoad<true>{T}, sst, stream);
+        } else {
+            ModDownTerm<false> T{u, ctx->d_mods, (u32)last, (u32)n, ctx->t, ctx->t_ratio, ctx->t_r0, ctx->t_r1, 0};
+            st = run_ntt_dir<true>(ctx, groups, mid, ModDownLoad<false>{T}, sst, stream);
+        }
         if (st != B2_OK) return st;
     }
     return B2_OK;
