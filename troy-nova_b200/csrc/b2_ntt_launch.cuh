@@ -140,12 +140,15 @@ static b2_status run_ntt_dir(b2_ctx *ctx, const std::vector<LimbGroup> &groups, 
         const int A = (int)logn - 8;
         P.tile_shift = logn - NTT_TB;
         P.n_limbs = (u32)(ng * P.count);
-        if (logn == 16 && P.n_limbs <= cluster_max_limbs()) {
+        // 16-CTA clusters are a non-portable size: if this device / partition cannot co-schedule one (the launch is refused
+        // synchronously), the persistent kernel below serves small launches too
+        static bool cluster_ok = true;
+        if (logn == 16 && P.n_limbs <= cluster_max_limbs() && cluster_ok) {
             P.sync = nullptr; P.lag = 0; P.total_items = 0;
             cudaError_t e = launch_cluster<FWD>(P, stream, ld, st);
-            count_launches(1);
-            B2_CUDA(e);
-            continue;
+            if (e == cudaSuccess) { count_launches(1); continue; }
+            cudaGetLastError();
+            cluster_ok = false;
         }
         P.lag = std::min<u32>(NTT_LAG, P.n_limbs);
         P.total_items = (P.n_limbs << P.tile_shift) * 2;
