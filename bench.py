@@ -398,6 +398,15 @@ def main():
         extra["relinearize_batch8_ops_per_s"] = world * nb / s8
         extra["relinearize_batch8_us_per_op"] = s8 / nb * 1e6
         del cb, db
+        # throughput regime of the headline metric: the same transforms over 10 x the operand (4200 limbs, 2.1 GiB)
+        big = torch.empty((200, NCOMP, n), dtype=torch.int64, device="cuda")
+        for i in range(10):
+            big[20 * i:20 * (i + 1)].copy_(x0)
+        tf = timed(lambda: ctx.ntt_forward(big, pcount=200, ncomp=NCOMP), 3)
+        ti = timed(lambda: ctx.ntt_inverse(big, pcount=200, ncomp=NCOMP), 3)
+        extra["ntt_4200_limbs"] = {"forward_limbs_per_s": world * 4200 / tf, "inverse_limbs_per_s": world * 4200 / ti,
+                                   "forward_hbm_frac": 4200 * n * 16 / tf / 1e9 / peak, "inverse_hbm_frac": 4200 * n * 16 / ti / 1e9 / peak}
+        del big
         # the other named parameter sets (BASELINE.json configs 2 and 4), data resident, per GPU x world
         extra["c2_bfv_n16384_batch256"] = bench_c2(b2, torch, timed, local, world)
         extra["c4_bgv_n32768"] = bench_c4(b2, torch, timed, local, world)
