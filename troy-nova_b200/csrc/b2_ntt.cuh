@@ -404,7 +404,26 @@ __device__ __forceinline__ void pass_body(const u64 *stage, u64 *sm, const ModIn
             }
         }
         const auto sp = st.prep(g, c, off);
-        if (G::xbit(LOL) == 0) {     // 16 adjacent words per thread: 16-byte stores
+        if (G::xbit(LOL) == 0 && FINAL && !COL && NR > 1 && LOL == 0) {
+            // Final row pass: a thread holds 16 adjacent words, so a direct store instruction would touch 32 different 128-byte
+            // lines with 16 bytes each (and a fused store functor would read its operands the same way).  The warp's 512 words
+            // are contiguous, and the warp's part of the exchange buffer is its own from here on (its last reads came from
+            // exactly these 512 slots): transpose through it so that consecutive lanes store consecutive 16-byte chunks.
+            const int l = t & 31;
+            u64 *wr = sm + 512 * (t >> 5);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                *reinterpret_cast<ulonglong2 *>(wr + 2 * (8 * l + (j ^ (l & 7)))) = make_ulonglong2(o[2 * j], o[2 * j + 1]);
+            __syncwarp();
+            const u32 xw = G::pos(tile, 512 * (t >> 5));
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const int ch = l + 32 * m, tq = ch >> 3;
+                const ulonglong2 d = *reinterpret_cast<const ulonglong2 *>(wr + 2 * (8 * tq + ((ch & 7) ^ (tq & 7))));
+                st.st2(sp, xw + 2u * (u32)ch, d.x, d.y);
+            }
+        } else if (G::xbit(LOL) == 0) {     // 16 adjacent words per thread: 16-byte stores
 #pragma unroll
             for (int k = 0; k < 16; k += 2) st.st2(sp, xt + (u32)k, o[k], o[k + 1]);
         } else {
