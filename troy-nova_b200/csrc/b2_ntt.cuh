@@ -171,6 +171,25 @@ template <int NL, int XLO, bool FWD, bool LAST, class AR>
 struct RoundTw {
     static constexpr int PF = !AR::PREFETCH ? 0 : (FWD ? (NL < 2 ? NL : 2) : ((LAST && NL == 1) ? 0 : 1));
     typename AR::TwT w[PF > 0 ? PF : 1][8];
+    // L1 prefetch hints for the layers load() does not fetch (register budget): their per-thread runs of 2..8 entries are
+    // distinct per thread in the row pass and would otherwise be long-scoreboard waits on L2 inside the round
+    __device__ __forceinline__ void hint_rest(const AR &ar, u32 xt, int logn) const {
+        if (!AR::PREFETCH) return;
+#pragma unroll
+        for (int s = PF; s < NL; s++) {
+            if (!FWD && LAST && s == NL - 1) continue;
+            const typename AR::TwT *p;
+            if (FWD) {
+                const int j = NL - 1 - s, l = logn - 1 - (XLO + j);
+                p = ar.ftab + (1u << l) + (xt >> (XLO + j + 1));
+            } else {
+                const int j = (4 - NL) + s, l = XLO + j;
+                const u32 n = 1u << logn;
+                p = ar.itab + n - (n >> l) + (xt >> (l + 1));
+            }
+            asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p));
+        }
+    }
     __device__ __forceinline__ void load(const AR &ar, u32 xt, int logn) {
 #pragma unroll
         for (int s = 0; s < PF; s++) {
@@ -334,6 +353,10 @@ __device__ __forceinline__ void pass_body(const u64 *stage, u64 *sm, const ModIn
         const int sb = swz16(it);
         RoundTw<NL0, G::xbit(LO0), FWD, LASTL && NR == 1, AR> tw0;
         tw0.load(ar, xt, logn);
+        if (!COL) {      // row pass: twiddles are distinct per thread — hint the ones that are loaded inside the rounds
+            tw0.hint_rest(ar, xt, logn);
+            if (NR > 1) tw1.hint_rest(ar, G::pos(tile, round_base<LO1>(t)), logn);
+        }
         hk.sync_stage();
         u64 raw[16];
         if (LO0 == 0) {
