@@ -7,6 +7,8 @@
 #include "b2_host_math.h"
 
 #include <atomic>
+#include <functional>
+#include <thread>
 namespace b2 {
 static std::atomic<unsigned long long> g_launches{0};
 void count_launches(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
@@ -20,38 +22,64 @@ b2_status cuda_fail(cudaError_t e, const char *what) {
     if (e == cudaErrorMemoryAllocation) return B2_ERR_OUT_OF_MEMORY;
     return B2_ERR_CUDA;
 }
-b2_status ensure_ws(b2_ctx *ctx, size_t bytes) {
-    if (ctx->ws_bytes >= bytes) return B2_OK;
-    if (ctx->ws) { B2_CUDA(cudaDeviceSynchronize()); B2_CUDA(cudaFree(ctx->ws)); ctx->ws = nullptr; ctx->ws_bytes = 0; }
+// Scratch records are keyed by the stream handle and — for the two handles that name a different stream in every host
+// thread (cudaStreamPerThread) or no particular one — by the calling thread as well.
+Scratch::Scratch(b2_ctx *ctx, cudaStream_t stream) : s(nullptr) {
+    const uintptr_t h = (uintptr_t)stream;
+    const size_t tid = (stream == cudaStreamPerThread) ? std::hash<std::thread::id>()(std::this_thread::get_id()) : 0;
+    {
+        std::lock_guard<std::mutex> g(ctx->mu);
+        b2_scratch *&slot = ctx->scratch[std::make_pair(h, tid)];
+        if (!slot) slot = new b2_scratch();
+        s = slot;
+    }
+    lock = std::unique_lock<std::mutex>(s->mu);
+}
+void scratch_release_all(b2_ctx *ctx) {
+    for (auto &kv : ctx->scratch) {
+        b2_scratch *sc = kv.second;
+        cudaFree(sc->ws); cudaFree(sc->stage); cudaFree(sc->d_sync);
+        for (cudaEvent_t e : sc->events) cudaEventDestroy(e);
+        if (sc->s_in) cudaStreamDestroy(sc->s_in);
+        if (sc->s_out) cudaStreamDestroy(sc->s_out);
+        delete sc;
+    }
+    ctx->scratch.clear();
+}
+// Growth happens outside the steady state (first use of a bigger shape on this stream).  Only this stream can have work
+// in flight on the old buffer (the record is private to it), so synchronising the stream is enough before freeing.
+b2_status ensure_ws(b2_scratch *sc, cudaStream_t stream, size_t bytes) {
+    if (sc->ws_bytes >= bytes) return B2_OK;
+    if (sc->ws) { B2_CUDA(cudaStreamSynchronize(stream)); B2_CUDA(cudaFree(sc->ws)); sc->ws = nullptr; sc->ws_bytes = 0; }
     size_t want = bytes + bytes / 8;
-    B2_CUDA(cudaMalloc(&ctx->ws, want));
-    ctx->ws_bytes = want;
+    B2_CUDA(cudaMalloc(&sc->ws, want));
+    sc->ws_bytes = want;
     return B2_OK;
 }
-b2_status ensure_stage(b2_ctx *ctx, size_t bytes) {
-    if (ctx->stage_bytes >= bytes) return B2_OK;
-    if (ctx->stage) { B2_CUDA(cudaDeviceSynchronize()); B2_CUDA(cudaFree(ctx->stage)); ctx->stage = nullptr; ctx->stage_bytes = 0; }
-    B2_CUDA(cudaMalloc(&ctx->stage, bytes));
-    ctx->stage_bytes = bytes;
+b2_status ensure_stage(b2_scratch *sc, cudaStream_t stream, size_t bytes) {
+    if (sc->stage_bytes >= bytes) return B2_OK;
+    if (sc->stage) { B2_CUDA(cudaStreamSynchronize(stream)); B2_CUDA(cudaFree(sc->stage)); sc->stage = nullptr; sc->stage_bytes = 0; }
+    B2_CUDA(cudaMalloc(&sc->stage, bytes));
+    sc->stage_bytes = bytes;
     return B2_OK;
 }
-b2_status ensure_copy_pipeline(b2_ctx *ctx, size_t n_events) {
-    if (!ctx->s_in) B2_CUDA(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
-    if (!ctx->s_out) B2_CUDA(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
-    while (ctx->events.size() < n_events) {
+b2_status ensure_copy_pipeline(b2_scratch *sc, size_t n_events) {
+    if (!sc->s_in) B2_CUDA(cudaStreamCreateWithFlags(&sc->s_in, cudaStreamNonBlocking));
+    if (!sc->s_out) B2_CUDA(cudaStreamCreateWithFlags(&sc->s_out, cudaStreamNonBlocking));
+    while (sc->events.size() < n_events) {
         cudaEvent_t e;
         B2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        ctx->events.push_back(e);
+        sc->events.push_back(e);
     }
     return B2_OK;
 }
-b2_status ensure_sync(b2_ctx *ctx, size_t limbs, cudaStream_t stream) {
-    if (ctx->d_sync && ctx->sync_limbs >= limbs) return B2_OK;
-    if (ctx->d_sync) { B2_CUDA(cudaDeviceSynchronize()); B2_CUDA(cudaFree(ctx->d_sync)); ctx->d_sync = nullptr; ctx->sync_limbs = 0; }
+b2_status ensure_sync(b2_scratch *sc, size_t limbs, cudaStream_t stream) {
+    if (sc->d_sync && sc->sync_limbs >= limbs) return B2_OK;
+    if (sc->d_sync) { B2_CUDA(cudaStreamSynchronize(stream)); B2_CUDA(cudaFree(sc->d_sync)); sc->d_sync = nullptr; sc->sync_limbs = 0; }
     const size_t want = std::max<size_t>(limbs * 2, 4096);
-    B2_CUDA(cudaMalloc((void **)&ctx->d_sync, (want + 2) * sizeof(unsigned)));
-    B2_CUDA(cudaMemsetAsync(ctx->d_sync, 0, (want + 2) * sizeof(unsigned), stream));
-    ctx->sync_limbs = want;
+    B2_CUDA(cudaMalloc((void **)&sc->d_sync, (want + 2) * sizeof(unsigned)));
+    B2_CUDA(cudaMemsetAsync(sc->d_sync, 0, (want + 2) * sizeof(unsigned), stream));
+    sc->sync_limbs = want;
     return B2_OK;
 }
 }  // namespace b2

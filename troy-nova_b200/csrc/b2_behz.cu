@@ -85,17 +85,23 @@ static b2_status ensure_behz(b2_ctx *ctx) {
         cudaFree(bz->d_tw); delete bz; return cuda_fail(e, "cudaMalloc(BEHZ tables)");
     }
     for (size_t a = 0; a < A; a++) { mods[a].tw = bz->d_tw + a * n; mods[a].itw = bz->d_itw + a * n; }
-    ctx->behz = bz;
-    ctx->h_mods.resize(K);                                   // host copies: run_ntt reads the arithmetic path of every table from h_mods
+    // upload everything first, publish last: a failed upload must not leave a half-initialised BEHZ state behind
+    if ((e = cudaMemcpy(bz->d_tw, tw.data(), A * n * sizeof(Tw), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(bz->d_itw, itw.data(), A * n * sizeof(Tw), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(ctx->d_mods + K, mods.data(), A * sizeof(ModInfo), cudaMemcpyHostToDevice)) != cudaSuccess) {
+        cudaFree(bz->d_tw); cudaFree(bz->d_itw); delete bz; return cuda_fail(e, "cudaMemcpy(BEHZ tables)");
+    }
+    // host copies: run_ntt reads the arithmetic path of every table from h_mods.  The capacity for these 2K+2 records was
+    // reserved by b2_ctx_create, so appending never moves the first K records that other threads may be reading.
+    ctx->h_mods.resize(K);
     ctx->h_mods.insert(ctx->h_mods.end(), mods.begin(), mods.end());
-    B2_CUDA(cudaMemcpy(bz->d_tw, tw.data(), A * n * sizeof(Tw), cudaMemcpyHostToDevice));
-    B2_CUDA(cudaMemcpy(bz->d_itw, itw.data(), A * n * sizeof(Tw), cudaMemcpyHostToDevice));
-    B2_CUDA(cudaMemcpy(ctx->d_mods + K, mods.data(), A * sizeof(ModInfo), cudaMemcpyHostToDevice));
+    ctx->behz = bz;
     return B2_OK;
 }
 
 // constants of the level with L ciphertext limbs (RNSTool::RNSTool for base_q = q_0..q_{L-1})
 static b2_status ensure_behz_level(b2_ctx *ctx, size_t L, const BehzDev **out) {
+    std::lock_guard<std::mutex> guard(ctx->mu);      // lazy, once per (context, level): concurrent first calls serialise here
     b2_status st = ensure_behz(ctx);
     if (st != B2_OK) return st;
     b2_behz *bz = ctx->behz;
@@ -306,9 +312,11 @@ extern "C" b2_status b2_bfv_multiply(b2_ctx *ctx, const uint64_t *a, const uint6
     const size_t n = ctx->n, K = ctx->K, L = nl, S = D.S;
     // workspace: lifted [4B][S][N] | wq [4B][L][N] | wb [4B][S][N] | pq [3B][L][N] | pb [3B][S][N]
     const size_t w_l = 4 * batch * S * n, w_q = 4 * batch * L * n, w_b = w_l, w_pq = 3 * batch * L * n, w_pb = 3 * batch * S * n;
-    st = ensure_ws(ctx, (w_l + w_q + w_b + w_pq + w_pb) * 8);
+    Scratch scl(ctx, stream);
+    b2_scratch *sc = scl.s;
+    st = ensure_ws(sc, stream, (w_l + w_q + w_b + w_pq + w_pb) * 8);
     if (st != B2_OK) return st;
-    u64 *lifted = (u64 *)ctx->ws, *wq = lifted + w_l, *wb = wq + w_q, *pq = wb + w_b, *pb = pq + w_pq;
+    u64 *lifted = (u64 *)sc->ws, *wq = lifted + w_l, *wb = wq + w_q, *pq = wb + w_b, *pb = pq + w_pq;
     const bool small = L <= 8;
     {   // (1)-(2)
         dim3 grid((unsigned)((n + 127) / 128), (unsigned)(4 * batch));
@@ -323,7 +331,7 @@ extern "C" b2_status b2_bfv_multiply(b2_ctx *ctx, const uint64_t *a, const uint6
         for (size_t j = 0; j < L; j++) groups.push_back(LimbGroup{(u32)j, (u32)(4 * batch), (u64)(j * n), (u64)(L * n)});
         for (size_t o = 0; o < S; o++) groups.push_back(LimbGroup{bsk_slot((u32)K, D.nB, (u32)o), (u32)(4 * batch), (u64)(w_q + o * n), (u64)(S * n)});
         BehzLoad ld{(const u64 *)a, (const u64 *)b, lifted, (u32)L, (u32)S, (u32)n};
-        st = run_ntt_dir<true>(ctx, groups, wq, ld, PlainStore{wq}, stream);
+        st = run_ntt_dir<true>(ctx, sc, groups, wq, ld, PlainStore{wq}, stream);
         if (st != B2_OK) return st;
     }
     {   // (4)
@@ -337,7 +345,7 @@ extern "C" b2_status b2_bfv_multiply(b2_ctx *ctx, const uint64_t *a, const uint6
         std::vector<LimbGroup> groups;
         for (size_t j = 0; j < L; j++) groups.push_back(LimbGroup{(u32)j, (u32)(3 * batch), (u64)(j * n), (u64)(L * n)});
         for (size_t o = 0; o < S; o++) groups.push_back(LimbGroup{bsk_slot((u32)K, D.nB, (u32)o), (u32)(3 * batch), (u64)(w_pq + o * n), (u64)(S * n)});
-        st = run_ntt_dir<false>(ctx, groups, pq, PlainLoad{pq}, PlainStore{pq}, stream);
+        st = run_ntt_dir<false>(ctx, sc, groups, pq, PlainLoad{pq}, PlainStore{pq}, stream);
         if (st != B2_OK) return st;
     }
     {   // (6)-(8)

@@ -47,6 +47,7 @@ int build_modulus_tables(uint64_t p, unsigned logn, Tw *T, Tw *IT, double *TD, d
 }
 }  // namespace b2
 
+extern "C" void b2_ctx_destroy(b2_ctx *c);
 extern "C" b2_status b2_ctx_create(int device, const b2_params *prm, b2_ctx **out) {
     B2_REQUIRE(prm && out && prm->moduli, "null argument");
     B2_REQUIRE(prm->log_n >= 1 && prm->log_n <= 17, "log_n must be in [1, 17]");
@@ -64,7 +65,9 @@ extern "C" b2_status b2_ctx_create(int device, const b2_params *prm, b2_ctx **ou
     int sms = 0;
     B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
 
-    b2_ctx *c = new b2_ctx();
+    // owned by a guard until the last upload has succeeded: every early return below releases the context and its tables
+    struct Guard { b2_ctx *c; ~Guard() { if (c) b2_ctx_destroy(c); } } guard{new b2_ctx()};
+    b2_ctx *c = guard.c;
     c->sm_count = sms > 0 ? sms : 148;
     c->device = device; c->logn = prm->log_n; c->n = (size_t)1 << prm->log_n; c->K = prm->n_moduli;
     c->t = prm->plain_modulus; c->scheme = (int)prm->scheme;
@@ -73,17 +76,17 @@ extern "C" b2_status b2_ctx_create(int device, const b2_params *prm, b2_ctx **ou
     c->psi.resize(K);
     std::vector<Tw> tw(K * n), itw(K * n);
     std::vector<double> twd(K * n), itwd(K * n);
+    c->h_mods.reserve(2 * K + 2);      // room for the lazily added BEHZ records: appending them never reallocates
     c->h_mods.resize(K);
     for (size_t i = 0; i < K; i++) {
         const int rc = build_modulus_tables(c->q[i], logn, &tw[i * n], &itw[i * n], &twd[i * n], &itwd[i * n], c->h_mods[i], c->psi[i]);
-        if (rc == 1) { delete c; set_error("b2_ctx_create: modulus %zu is not a prime below 2^61", i); return B2_ERR_INVALID_ARG; }
-        if (rc == 2) { delete c; set_error("b2_ctx_create: modulus %zu is not 1 mod 2N", i); return B2_ERR_INVALID_ARG; }
+        if (rc == 1) { set_error("b2_ctx_create: modulus %zu is not a prime below 2^61", i); return B2_ERR_INVALID_ARG; }
+        if (rc == 2) { set_error("b2_ctx_create: modulus %zu is not 1 mod 2N", i); return B2_ERR_INVALID_ARG; }
     }
     cudaError_t ce;
     if ((ce = cudaMalloc(&c->d_tw, K * n * sizeof(Tw))) != cudaSuccess || (ce = cudaMalloc(&c->d_itw, K * n * sizeof(Tw))) != cudaSuccess ||
         (ce = cudaMalloc(&c->d_twd, K * n * sizeof(double))) != cudaSuccess || (ce = cudaMalloc(&c->d_itwd, K * n * sizeof(double))) != cudaSuccess ||
         (ce = cudaMalloc(&c->d_mods, (2 * K + 2) * sizeof(ModInfo))) != cudaSuccess) {
-        b2_ctx_destroy(c);
         return cuda_fail(ce, "cudaMalloc(tables)");
     }
     for (size_t i = 0; i < K; i++) { c->h_mods[i].tw = c->d_tw + i * n; c->h_mods[i].itw = c->d_itw + i * n;
@@ -109,10 +112,10 @@ extern "C" b2_status b2_ctx_create(int device, const b2_params *prm, b2_ctx **ou
         c->h_inv_mod_t = invt;
         B2_CUDA(cudaMalloc(&c->d_inv, K * K * sizeof(Tw)));
         B2_CUDA(cudaMalloc(&c->d_inv_mod_t, K * sizeof(uint64_t)));
-        B2_CUDA(cudaMalloc(&c->d_galois, n * sizeof(uint32_t)));
         B2_CUDA(cudaMemcpy(c->d_inv, inv.data(), K * K * sizeof(Tw), cudaMemcpyHostToDevice));
         B2_CUDA(cudaMemcpy(c->d_inv_mod_t, invt.data(), K * sizeof(uint64_t), cudaMemcpyHostToDevice));
     }
+    guard.c = nullptr;
     *out = c;
     return B2_OK;
 }
@@ -120,9 +123,6 @@ extern "C" b2_status b2_ctx_create(int device, const b2_params *prm, b2_ctx **ou
 extern "C" void b2_ctx_destroy(b2_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaFree(c->d_tw); cudaFree(c->d_itw); cudaFree(c->d_twd); cudaFree(c->d_itwd); cudaFree(c->d_mods); b2::behz_release(c); cudaFree(c->d_inv); cudaFree(c->d_inv_mod_t); cudaFree(c->d_galois); cudaFree(c->ws); cudaFree(c->stage); cudaFree(c->d_sync);
-    for (cudaEvent_t e : c->events) cudaEventDestroy(e);
-    if (c->s_in) cudaStreamDestroy(c->s_in);
-    if (c->s_out) cudaStreamDestroy(c->s_out);
+    cudaFree(c->d_tw); cudaFree(c->d_itw); cudaFree(c->d_twd); cudaFree(c->d_itwd); cudaFree(c->d_mods); b2::behz_release(c); cudaFree(c->d_inv); cudaFree(c->d_inv_mod_t); b2::scratch_release_all(c);
     delete c;
 }

@@ -1,7 +1,10 @@
 // b2_ctx.h — internal definition of the opaque b2_ctx handle.
 #pragma once
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 #include <cuda_runtime.h>
 #include "../../include/b2rns.h"
@@ -24,40 +27,53 @@ struct b2_ctx {
     uint64_t *d_inv_mod_t = nullptr; // [K]: q_a^-1 mod t (BFV/BGV), 0 when t == 0
     uint64_t t_ratio = 0, t_r0 = 0, t_r1 = 0;   // floor(2^64 / t), floor(2^128 / t)
     std::vector<uint64_t> h_inv_mod_t;
-    uint32_t *d_galois = nullptr; uint64_t galois_elt_cached = 0;   // NTT-form permutation table of the last Galois element
-    // workspace arena (grown on demand outside the hot path; never shrinks)
-    void *ws = nullptr; size_t ws_bytes = 0;
-    // host-buffer staging for the *_host entry points
-    void *stage = nullptr; size_t stage_bytes = 0;
-    cudaStream_t s_in = nullptr, s_out = nullptr;     // copy streams of the pipelined *_host entry points
-    std::vector<cudaEvent_t> events;
-    // persistent-NTT work queue + per-limb completion counters (zero between launches; the kernel resets them)
-    unsigned *d_sync = nullptr; size_t sync_limbs = 0;
     int sm_count = 148;
+    // Everything above is immutable after b2_ctx_create.  The MUTABLE per-call state (workspace arena, persistent-NTT work
+    // queue, host staging) lives in b2_scratch records, one per (stream, host thread) that ever used the context: calls on
+    // one stream are ordered by the stream, calls on different streams / threads never share a record, so a context is
+    // re-entrant the way the reference is per host thread on cudaStreamPerThread (SURVEY §8b "Threading / streams").
+    std::mutex mu;                                   // guards `scratch` and the lazy BEHZ tables
+    std::map<std::pair<uintptr_t, size_t>, struct b2_scratch *> scratch;
     // BEHZ (BFV multiply) auxiliary base, built lazily by the first b2_bfv_multiply: ModInfo slots K .. 2K+1 hold
     // B_0 .. B_K (K+1 primes) and m_sk; per-level constant blobs keyed by the number of ciphertext limbs
     struct b2_behz *behz = nullptr;
 };
 
+// Mutable state of one (stream, host thread).  `mu` is held by an entry point for the whole time it enqueues its launches,
+// so two host threads that share one explicit stream cannot interleave their launch sequences on the shared workspace.
+struct b2_scratch {
+    std::mutex mu;
+    void *ws = nullptr; size_t ws_bytes = 0;          // workspace arena (grown on demand; never shrinks)
+    void *stage = nullptr; size_t stage_bytes = 0;    // device staging of the *_host entry points
+    cudaStream_t s_in = nullptr, s_out = nullptr;     // copy streams of the pipelined *_host entry points
+    std::vector<cudaEvent_t> events;
+    // persistent-NTT work queue + per-limb completion counters (zero between launches; the kernel resets them)
+    unsigned *d_sync = nullptr; size_t sync_limbs = 0;
+};
+
 namespace b2 {
+// RAII: the scratch record of (ctx, stream, calling thread), locked for the lifetime of the object
+struct Scratch {
+    b2_scratch *s;
+    std::unique_lock<std::mutex> lock;
+    Scratch(b2_ctx *ctx, cudaStream_t stream);
+    b2_scratch *operator->() const { return s; }
+};
 // number of kernels this library launched in this process (bench.py reports it as gpu_launches)
 void count_launches(unsigned n);
 void set_error(const char *fmt, ...);
 b2_status cuda_fail(cudaError_t e, const char *what);
-b2_status ensure_ws(b2_ctx *ctx, size_t bytes);
-b2_status ensure_stage(b2_ctx *ctx, size_t bytes);
-b2_status ensure_copy_pipeline(b2_ctx *ctx, size_t n_events);
-b2_status ensure_sync(b2_ctx *ctx, size_t limbs, cudaStream_t stream);
+b2_status ensure_ws(b2_scratch *sc, cudaStream_t stream, size_t bytes);
+b2_status ensure_stage(b2_scratch *sc, cudaStream_t stream, size_t bytes);
+b2_status ensure_copy_pipeline(b2_scratch *sc, size_t n_events);
+b2_status ensure_sync(b2_scratch *sc, size_t limbs, cudaStream_t stream);
+void scratch_release_all(b2_ctx *ctx);
 int build_modulus_tables(uint64_t p, unsigned logn, Tw *T, Tw *IT, double *TD, double *ITD, ModInfo &M, uint64_t &psi_out);
 void behz_release(b2_ctx *ctx);
 #define B2_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return b2::cuda_fail(e__, #call); } while (0)
 #define B2_REQUIRE(cond, msg) do { if (!(cond)) { b2::set_error("%s: %s", __func__, msg); return B2_ERR_INVALID_ARG; } } while (0)
 
 // launchers (b2_ntt.cu)
-struct NttOperand {           // where the limbs live: contiguous base, or per-batch pointer tables
-    const uint64_t *in; uint64_t *out;
-    const uint64_t *const *in_ptrs; uint64_t *const *out_ptrs;   // device arrays (or null)
-};
 struct LimbGroup;
 b2_status ntt_launch(b2_ctx *ctx, bool forward, const uint64_t *in, uint64_t *out, size_t batch, size_t pcount,
                      size_t ncomp, int mode, size_t table_base, size_t decomp, cudaStream_t stream);

@@ -49,6 +49,7 @@ struct ModUpLoad {
     const ModInfo *mods;
     u32 decomp, K, n;
     u32 g0;          // output modulus of group 0 (limb-sharded calls transform a sub-range of the output moduli)
+    u32 f64_path;    // 1 iff FP64-pipe moduli really run the FP64 back end in this launch (N >= 4096); the tiny-N kernel is integer-only
     __device__ __forceinline__ const u64 *src(int, int c, u64) const {
         const u32 b = (u32)c / decomp, j = (u32)c - b * decomp;
         return tc.p[b] + (u64)j * n;
@@ -63,7 +64,7 @@ struct ModUpLoad {
         r.m = Mi.p; r.ratio = Mi.ratio;
         // q_j <= m_i: already canonical modulo m_i.  FP64-pipe moduli take lazy inputs (|x| < 2^10 m_i, b2_modarith.cuh), so a
         // digit modulus at most 4 bits longer needs no reduction here either: the transform's first multiplication does it
-        r.reduce = !(mods[j].p <= r.m || (Mi.use_f64 && mods[j].bits <= Mi.bits + 4));
+        r.reduce = !(mods[j].p <= r.m || (f64_path && Mi.use_f64 && mods[j].bits <= Mi.bits + 4));
         return r;
     }
     __device__ __forceinline__ u64 xf(const Prep &pc, u32, u64 v) const { return pc.reduce ? barrett64(v, pc.m, pc.ratio) : v; }
@@ -135,26 +136,26 @@ struct ProdLoad {         // coefficient-form path: transform prod[b][k][j] itse
 
 // step 5 launcher: the scheme (BGV or not) and the ciphertext form select one kernel instantiation each
 template <bool BGV>
-static b2_status mod_down_t(b2_ctx *ctx, const std::vector<LimbGroup> &groups, u64 *mid, const u64 *u, const u64 *prod, const PtrTabW &dp, size_t decomp,
+static b2_status mod_down_t(b2_ctx *ctx, b2_scratch *sc, const std::vector<LimbGroup> &groups, u64 *mid, const u64 *u, const u64 *prod, const PtrTabW &dp, size_t decomp,
                             int assign, int is_ntt, size_t jbase, size_t prod_rows, size_t dest_rows, cudaStream_t stream) {
     const size_t K = ctx->K, n = ctx->n;
     ModDownTerm<BGV> T{u, ctx->d_mods, (u32)(K - 1), (u32)n, ctx->t, ctx->t_ratio, ctx->t_r0, ctx->t_r1, BGV ? ctx->h_inv_mod_t[K - 1] : 0};
     if (is_ntt) {
         ModDownStore<BGV, true> sst{T, prod, ctx->d_inv + (K - 1) * K, dp, (u32)decomp, (u32)assign, (u32)jbase, (u32)prod_rows, (u32)dest_rows};
-        return run_ntt_dir<true>(ctx, groups, mid, ModDownLoad<BGV>{T, (u32)jbase}, sst, stream);
+        return run_ntt_dir<true>(ctx, sc, groups, mid, ModDownLoad<BGV>{T, (u32)jbase}, sst, stream);
     }
     ModDownStore<BGV, false> sst{T, prod, ctx->d_inv + (K - 1) * K, dp, (u32)decomp, (u32)assign, (u32)jbase, (u32)prod_rows, (u32)dest_rows};
-    return run_ntt_dir<false>(ctx, groups, mid, ProdLoad{prod, (u32)prod_rows, (u32)n}, sst, stream);
+    return run_ntt_dir<false>(ctx, sc, groups, mid, ProdLoad{prod, (u32)prod_rows, (u32)n}, sst, stream);
 }
-static b2_status mod_down(b2_ctx *ctx, const std::vector<LimbGroup> &groups, u64 *mid, const u64 *u, const u64 *prod, const PtrTabW &dp, size_t decomp,
+static b2_status mod_down(b2_ctx *ctx, b2_scratch *sc, const std::vector<LimbGroup> &groups, u64 *mid, const u64 *u, const u64 *prod, const PtrTabW &dp, size_t decomp,
                           int assign, int is_ntt, size_t jbase, size_t prod_rows, size_t dest_rows, cudaStream_t stream) {
     // BGV ciphertexts are always NTT-form (checked by the callers): the coefficient-form BGV kernel is never instantiated
     if (ctx->scheme == B2_SCHEME_BGV) {
         ModDownTerm<true> T{u, ctx->d_mods, (u32)(ctx->K - 1), (u32)ctx->n, ctx->t, ctx->t_ratio, ctx->t_r0, ctx->t_r1, ctx->h_inv_mod_t[ctx->K - 1]};
         ModDownStore<true, true> sst{T, prod, ctx->d_inv + (ctx->K - 1) * ctx->K, dp, (u32)decomp, (u32)assign, (u32)jbase, (u32)prod_rows, (u32)dest_rows};
-        return run_ntt_dir<true>(ctx, groups, mid, ModDownLoad<true>{T, (u32)jbase}, sst, stream);
+        return run_ntt_dir<true>(ctx, sc, groups, mid, ModDownLoad<true>{T, (u32)jbase}, sst, stream);
     }
-    return mod_down_t<false>(ctx, groups, mid, u, prod, dp, decomp, assign, is_ntt, jbase, prod_rows, dest_rows, stream);
+    return mod_down_t<false>(ctx, sc, groups, mid, u, prod, dp, decomp, assign, is_ntt, jbase, prod_rows, dest_rows, stream);
 }
 }  // namespace b2
 
@@ -199,9 +200,11 @@ static b2_status keyswitch_chunk(b2_ctx *ctx, const uint64_t *const *targets, ui
     // 646 / 672 us per keyswitch); B2_KS_BLOCK is the developer override the sweep used
     const size_t blk = std::min(R, blk_env ? blk_env : R);
     const size_t w_tc = nb * decomp * n, w_temp = blk * nb * decomp * n, w_prod = nb * 2 * R * n, w_u = nb * 2 * n, w_mid = nb * 2 * decomp * n;
-    b2_status st = ensure_ws(ctx, (w_tc + w_temp + w_prod + w_u + w_mid) * 8);
+    Scratch scl(ctx, stream);
+    b2_scratch *sc = scl.s;
+    b2_status st = ensure_ws(sc, stream, (w_tc + w_temp + w_prod + w_u + w_mid) * 8);
     if (st != B2_OK) return st;
-    u64 *tc = (u64 *)ctx->ws, *temp = tc + w_tc, *prod = temp + w_temp, *u = prod + w_prod, *mid = u + w_u;
+    u64 *tc = (u64 *)sc->ws, *temp = tc + w_tc, *prod = temp + w_temp, *u = prod + w_prod, *mid = u + w_u;
 
     // developer aid: B2_KS_TIMING=1 prints per-stage device times (synchronises; never set in production)
     static const bool timing = getenv("B2_KS_TIMING") != nullptr;
@@ -217,7 +220,7 @@ static b2_status keyswitch_chunk(b2_ctx *ctx, const uint64_t *const *targets, ui
         std::vector<LimbGroup> groups;
         for (size_t j = 0; j < decomp; j++) groups.push_back(LimbGroup{(u32)j, (u32)nb, (u64)(j * n), (u64)(decomp * n)});
         TargetLoad ld{coef, (u32)n};
-        st = run_ntt_dir<false>(ctx, groups, tc, ld, PlainStore{tc}, stream);
+        st = run_ntt_dir<false>(ctx, sc, groups, tc, ld, PlainStore{tc}, stream);
         if (st != B2_OK) return st;
         for (size_t b = 0; b < nb; b++) coef.p[b] = tc + b * decomp * n;
     }
@@ -231,8 +234,8 @@ static b2_status keyswitch_chunk(b2_ctx *ctx, const uint64_t *const *targets, ui
             const size_t i = i0 + il;
             groups.push_back(LimbGroup{(u32)(i == decomp ? K - 1 : i), (u32)(nb * decomp), (u64)(il * nb * decomp * n), (u64)n});
         }
-        ModUpLoad ld{coef, ctx->d_mods, (u32)decomp, (u32)K, (u32)n, (u32)i0};
-        st = run_ntt_dir<true>(ctx, groups, temp, ld, PlainStore{temp}, stream);
+        ModUpLoad ld{coef, ctx->d_mods, (u32)decomp, (u32)K, (u32)n, (u32)i0, ctx->logn > 11 ? 1u : 0u};
+        st = run_ntt_dir<true>(ctx, sc, groups, temp, ld, PlainStore{temp}, stream);
         if (st != B2_OK) return st;
         if (i0 == 0) mark();
         dim3 grid((unsigned)nb, (unsigned)((n / 2 + 255) / 256), (unsigned)cnt);
@@ -246,7 +249,7 @@ static b2_status keyswitch_chunk(b2_ctx *ctx, const uint64_t *const *targets, ui
     {
         std::vector<LimbGroup> groups{LimbGroup{(u32)(K - 1), (u32)(2 * nb), 0, (u64)n}};
         SpecialLoad ld{prod, (u32)R, (u32)decomp, (u32)n};
-        st = run_ntt_dir<false>(ctx, groups, u, ld, PlainStore{u}, stream);
+        st = run_ntt_dir<false>(ctx, sc, groups, u, ld, PlainStore{u}, stream);
         if (st != B2_OK) return st;
     }
     mark();
@@ -256,7 +259,7 @@ static b2_status keyswitch_chunk(b2_ctx *ctx, const uint64_t *const *targets, ui
         for (size_t j = 0; j < decomp; j++) groups.push_back(LimbGroup{(u32)j, (u32)(2 * nb), (u64)(j * n), (u64)(decomp * n)});
         PtrTabW dp;
         for (size_t b = 0; b < (size_t)KS_MAXB; b++) dp.p[b] = b < nb ? (u64 *)dests[b] : nullptr;
-        st = mod_down(ctx, groups, mid, u, prod, dp, decomp, assign, is_ntt, 0, R, decomp, stream);
+        st = mod_down(ctx, sc, groups, mid, u, prod, dp, decomp, assign, is_ntt, 0, R, decomp, stream);
         if (st != B2_OK) return st;
     }
     mark();
@@ -364,7 +367,9 @@ b2_status b2_keyswitch_shard_prepare(b2_ctx *ctx, const uint64_t *target_local, 
     for (size_t jl = 0; jl < nct; jl++) groups.push_back(LimbGroup{(u32)(first + jl), 1u, (u64)(jl * n), 0});
     PtrTab coef;
     for (int b = 0; b < KS_MAXB; b++) coef.p[b] = b == 0 ? (const u64 *)target_local : nullptr;
-    return run_ntt_dir<false>(ctx, groups, (u64 *)send, TargetLoad{coef, (u32)n}, PlainStore{(u64 *)send}, stream);
+    Scratch scl(ctx, stream);
+    b2_scratch *sc = scl.s;
+    return run_ntt_dir<false>(ctx, sc, groups, (u64 *)send, TargetLoad{coef, (u32)n}, PlainStore{(u64 *)send}, stream);
 }
 
 // workspace of the sharded stages: prod [2][count][N] | mid [2][nct][N] | tc [decomp][N] | temp [count][decomp][N];
@@ -380,9 +385,11 @@ b2_status b2_keyswitch_shard_products(b2_ctx *ctx, const uint64_t *gathered, int
     B2_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t stream = (cudaStream_t)stream_;
     const size_t n = ctx->n, K = ctx->K, nct = owned_ct_limbs(decomp, first, count);
-    b2_status st = ensure_ws(ctx, (2 * count + 2 * nct + decomp + count * decomp) * n * 8);
+    Scratch scl(ctx, stream);
+    b2_scratch *sc = scl.s;
+    b2_status st = ensure_ws(sc, stream, (2 * count + 2 * nct + decomp + count * decomp) * n * 8);
     if (st != B2_OK) return st;
-    u64 *prod = (u64 *)ctx->ws, *tc = prod + (2 * count + 2 * nct) * n, *temp = tc + decomp * n;
+    u64 *prod = (u64 *)sc->ws, *tc = prod + (2 * count + 2 * nct) * n, *temp = tc + decomp * n;
     // the all-gather delivered [world][pad][N]: rank r's owned ciphertext limbs first_r .. ; compact to tc[decomp][N]
     {
         const size_t R = decomp + 1, base = R / (size_t)world, rem = R % (size_t)world;
@@ -405,8 +412,8 @@ b2_status b2_keyswitch_shard_products(b2_ctx *ctx, const uint64_t *gathered, int
             const size_t i = first + il;
             groups.push_back(LimbGroup{(u32)(i == decomp ? K - 1 : i), (u32)decomp, (u64)(il * decomp * n), (u64)n});
         }
-        ModUpLoad ld{coef, ctx->d_mods, (u32)decomp, (u32)K, (u32)n, (u32)first};
-        st = run_ntt_dir<true>(ctx, groups, temp, ld, PlainStore{temp}, stream);
+        ModUpLoad ld{coef, ctx->d_mods, (u32)decomp, (u32)K, (u32)n, (u32)first, ctx->logn > 11 ? 1u : 0u};
+        st = run_ntt_dir<true>(ctx, sc, groups, temp, ld, PlainStore{temp}, stream);
         if (st != B2_OK) return st;
     }
     {
@@ -419,7 +426,7 @@ b2_status b2_keyswitch_shard_products(b2_ctx *ctx, const uint64_t *gathered, int
     if (owns_special) {
         std::vector<LimbGroup> groups{LimbGroup{(u32)(K - 1), 2u, 0, (u64)n}};
         SpecialLoad ld{prod, (u32)count, (u32)(count - 1), (u32)n};
-        st = run_ntt_dir<false>(ctx, groups, (u64 *)u, ld, PlainStore{(u64 *)u}, stream);
+        st = run_ntt_dir<false>(ctx, sc, groups, (u64 *)u, ld, PlainStore{(u64 *)u}, stream);
         if (st != B2_OK) return st;
     }
     return B2_OK;
@@ -434,15 +441,17 @@ b2_status b2_keyswitch_shard_finish(b2_ctx *ctx, const uint64_t *u, size_t decom
     const size_t n = ctx->n, K = ctx->K, nct = owned_ct_limbs(decomp, first, count);
     if (nct == 0) return B2_OK;
     B2_REQUIRE(dest_local && (((uintptr_t)dest_local | (uintptr_t)u) & 15) == 0, "operands must be non-null and 16-byte aligned");
-    B2_REQUIRE(ctx->ws && ctx->ws_bytes >= (2 * count + 2 * nct) * n * 8, "b2_keyswitch_shard_products must run first");
     B2_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t stream = (cudaStream_t)stream_;
-    u64 *prod = (u64 *)ctx->ws, *mid = prod + 2 * count * n;
+    Scratch scl(ctx, stream);
+    b2_scratch *sc = scl.s;
+    B2_REQUIRE(sc->ws && sc->ws_bytes >= (2 * count + 2 * nct) * n * 8, "b2_keyswitch_shard_products must run first (same stream, same thread)");
+    u64 *prod = (u64 *)sc->ws, *mid = prod + 2 * count * n;
     std::vector<LimbGroup> groups;
     for (size_t jl = 0; jl < nct; jl++) groups.push_back(LimbGroup{(u32)(first + jl), 2u, (u64)(jl * n), (u64)(nct * n)});
     PtrTabW dp;
     for (int b = 0; b < KS_MAXB; b++) dp.p[b] = b == 0 ? (u64 *)dest_local : nullptr;
-    return mod_down(ctx, groups, mid, (const u64 *)u, prod, dp, decomp, assign, is_ntt, first, count, nct, stream);
+    return mod_down(ctx, sc, groups, mid, (const u64 *)u, prod, dp, decomp, assign, is_ntt, first, count, nct, stream);
 }
 
 }  // extern "C"

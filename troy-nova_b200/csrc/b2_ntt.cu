@@ -35,7 +35,8 @@ b2_status ntt_launch(b2_ctx *ctx, bool forward, const uint64_t *in, uint64_t *ou
             groups.push_back(LimbGroup{table, (u32)(batch * pcount), (u64)(j * n), (u64)(ncomp * n)});
         }
     }
-    return run_ntt(ctx, forward, groups, (u64 *)out, PlainLoad{(const u64 *)in}, PlainStore{(u64 *)out}, stream);
+    Scratch sc(ctx, stream);
+    return run_ntt(ctx, sc.s, forward, groups, (u64 *)out, PlainLoad{(const u64 *)in}, PlainStore{(u64 *)out}, stream);
 }
 
 }  // namespace b2
@@ -83,18 +84,19 @@ static b2_status ntt_host(b2_ctx *ctx, bool fwd, const uint64_t *in, uint64_t *o
     b2_status st = check_ntt_args(ctx, batch, pcount, ncomp, mode, table_base, decomp);
     if (st != B2_OK) return st;
     B2_CUDA(cudaSetDevice(ctx->device));
-    st = ensure_stage(ctx, bytes);
+    Scratch sc(ctx, (cudaStream_t)stream);
+    st = ensure_stage(sc.s, (cudaStream_t)stream, bytes);
     if (st != B2_OK) return st;
     // chunk size: large enough that a copy runs at link rate, small enough that filling / draining the three-stage pipeline
     // stays a small part of the call (B2_HOST_CHUNK_MB: developer override for tuning)
     static const size_t chunk_mb = [] { const char *e = getenv("B2_HOST_CHUNK_MB"); return e && atoi(e) > 0 ? (size_t)atoi(e) : (size_t)16; }();
     const size_t chunk = std::max<size_t>(1, std::min<size_t>((size_t)NTT_MAX_GROUPS, (chunk_mb << 20) / (n * 8)));
     const size_t nchunks = (limbs + chunk - 1) / chunk;
-    st = ensure_copy_pipeline(ctx, 2 * nchunks + 2);
+    st = ensure_copy_pipeline(sc.s, 2 * nchunks + 2);
     if (st != B2_OK) return st;
-    cudaStream_t s = (cudaStream_t)stream, s_in = ctx->s_in, s_out = ctx->s_out;
-    cudaEvent_t *ev = ctx->events.data();
-    u64 *dev = (u64 *)ctx->stage;
+    cudaStream_t s = (cudaStream_t)stream, s_in = sc->s_in, s_out = sc->s_out;
+    cudaEvent_t *ev = sc->events.data();
+    u64 *dev = (u64 *)sc->stage;
     B2_CUDA(cudaEventRecord(ev[0], s));                 // copies start after the caller's earlier work on `stream`
     B2_CUDA(cudaStreamWaitEvent(s_in, ev[0], 0));
     std::vector<LimbGroup> groups;
@@ -110,7 +112,7 @@ static b2_status ntt_host(b2_ctx *ctx, bool fwd, const uint64_t *in, uint64_t *o
                             : mode == B2_TABLES_KS_SET_PRODUCTS ? (u32)(k == decomp ? K - 1 : k) : (u32)(j == decomp ? K - 1 : j);
             groups.push_back(LimbGroup{table, 1u, (u64)(l * n), 0});
         }
-        st = run_ntt(ctx, fwd, groups, dev, PlainLoad{dev}, PlainStore{dev}, s);
+        st = run_ntt(ctx, sc.s, fwd, groups, dev, PlainLoad{dev}, PlainStore{dev}, s);
         if (st != B2_OK) return st;
         B2_CUDA(cudaEventRecord(ev[3 + 2 * c], s));
         B2_CUDA(cudaStreamWaitEvent(s_out, ev[3 + 2 * c], 0));

@@ -66,13 +66,14 @@ static constexpr u32 NTT_LAG = 48;
 #endif
 constexpr int NTT_OCC = B2_NTT_OCC;     // resident CTAs per SM (register allocation is held to 65536 / (256 * NTT_OCC))
 
+constexpr int B2_MAX_DEVICES = 64;      // function attributes are per device: one flag per (instantiation, device)
 template <int A, bool FWD, class Load, class Store>
-static cudaError_t launch_persistent(const NttJob &J, unsigned grid, cudaStream_t s, Load ld, Store st) {
-    static bool configured = false;     // per instantiation; the attribute is per function and device-independent here
-    if (!configured) {
+static cudaError_t launch_persistent(const NttJob &J, int device, unsigned grid, cudaStream_t s, Load ld, Store st) {
+    static bool configured[B2_MAX_DEVICES] = {};
+    if (!configured[device & (B2_MAX_DEVICES - 1)]) {
         cudaError_t e = cudaFuncSetAttribute(ntt_persistent_kernel<A, FWD, NTT_OCC, Load, Store>, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[device & (B2_MAX_DEVICES - 1)] = true;
     }
     ntt_persistent_kernel<A, FWD, NTT_OCC, Load, Store><<<grid, NTT_THREADS, NTT_SMEM_BYTES, s>>>(J, ld, st);
     return cudaGetLastError();
@@ -80,13 +81,13 @@ static cudaError_t launch_persistent(const NttJob &J, unsigned grid, cudaStream_
 
 // N = 2^16, few limbs: one 16-CTA cluster per limb, intermediate in distributed shared memory (b2_ntt_cluster.cuh)
 template <bool FWD, class Load, class Store>
-static cudaError_t launch_cluster(const NttJob &J, cudaStream_t s, Load ld, Store st) {
-    static bool configured = false;
-    if (!configured) {
+static cudaError_t launch_cluster(const NttJob &J, int device, cudaStream_t s, Load ld, Store st) {
+    static bool configured[B2_MAX_DEVICES] = {};
+    if (!configured[device & (B2_MAX_DEVICES - 1)]) {
         cudaError_t e = cudaFuncSetAttribute(ntt_cluster_kernel<FWD, Load, Store>, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_SMEM_BYTES);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ntt_cluster_kernel<FWD, Load, Store>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[device & (B2_MAX_DEVICES - 1)] = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(J.n_limbs * CL_SIZE, 1, 1);
@@ -109,7 +110,7 @@ static inline unsigned cluster_max_limbs() {
 // functors map (group, limb) to wherever the external operands live.  All groups must have the same count.
 // The direction is a template parameter so that a call site instantiates only the kernels it launches.
 template <bool FWD, class Load, class Store>
-static b2_status run_ntt_dir(b2_ctx *ctx, const std::vector<LimbGroup> &groups, u64 *mid, Load ld, Store st, cudaStream_t stream) {
+static b2_status run_ntt_dir(b2_ctx *ctx, b2_scratch *sc, const std::vector<LimbGroup> &groups, u64 *mid, Load ld, Store st, cudaStream_t stream) {
     const unsigned logn = ctx->logn;
     const size_t n = ctx->n;
     if (groups.empty() || groups[0].count == 0) return B2_OK;
@@ -142,28 +143,28 @@ static b2_status run_ntt_dir(b2_ctx *ctx, const std::vector<LimbGroup> &groups, 
         P.n_limbs = (u32)(ng * P.count);
         // 16-CTA clusters are a non-portable size: if this device / partition cannot co-schedule one (the launch is refused
         // synchronously), the persistent kernel below serves small launches too
-        static bool cluster_ok = true;
-        if (logn == 16 && P.n_limbs <= cluster_max_limbs() && cluster_ok) {
+        static bool cluster_refused[B2_MAX_DEVICES] = {};
+        if (logn == 16 && P.n_limbs <= cluster_max_limbs() && !cluster_refused[ctx->device & (B2_MAX_DEVICES - 1)]) {
             P.sync = nullptr; P.lag = 0; P.total_items = 0;
-            cudaError_t e = launch_cluster<FWD>(P, stream, ld, st);
+            cudaError_t e = launch_cluster<FWD>(P, ctx->device, stream, ld, st);
             if (e == cudaSuccess) { count_launches(1); continue; }
             cudaGetLastError();
-            cluster_ok = false;
+            cluster_refused[ctx->device & (B2_MAX_DEVICES - 1)] = true;
         }
         P.lag = std::min<u32>(NTT_LAG, P.n_limbs);
         P.total_items = (P.n_limbs << P.tile_shift) * 2;
-        b2_status s = ensure_sync(ctx, P.n_limbs, stream);
+        b2_status s = ensure_sync(sc, P.n_limbs, stream);
         if (s != B2_OK) return s;
-        P.sync = ctx->d_sync;
+        P.sync = sc->d_sync;
         const unsigned grid = std::min<unsigned>(P.total_items, (unsigned)NTT_OCC * (unsigned)ctx->sm_count);
         cudaError_t e;
         switch (A) {
-        case 4: e = launch_persistent<4, FWD>(P, grid, stream, ld, st); break;
-        case 5: e = launch_persistent<5, FWD>(P, grid, stream, ld, st); break;
-        case 6: e = launch_persistent<6, FWD>(P, grid, stream, ld, st); break;
-        case 7: e = launch_persistent<7, FWD>(P, grid, stream, ld, st); break;
-        case 8: e = launch_persistent<8, FWD>(P, grid, stream, ld, st); break;
-        default: e = launch_persistent<9, FWD>(P, grid, stream, ld, st); break;
+        case 4: e = launch_persistent<4, FWD>(P, ctx->device, grid, stream, ld, st); break;
+        case 5: e = launch_persistent<5, FWD>(P, ctx->device, grid, stream, ld, st); break;
+        case 6: e = launch_persistent<6, FWD>(P, ctx->device, grid, stream, ld, st); break;
+        case 7: e = launch_persistent<7, FWD>(P, ctx->device, grid, stream, ld, st); break;
+        case 8: e = launch_persistent<8, FWD>(P, ctx->device, grid, stream, ld, st); break;
+        default: e = launch_persistent<9, FWD>(P, ctx->device, grid, stream, ld, st); break;
         }
         count_launches(1);
         B2_CUDA(e);
@@ -172,8 +173,8 @@ static b2_status run_ntt_dir(b2_ctx *ctx, const std::vector<LimbGroup> &groups, 
 }
 // run-time direction (the plain transforms of b2_ntt.cu)
 template <class Load, class Store>
-static b2_status run_ntt(b2_ctx *ctx, bool forward, const std::vector<LimbGroup> &groups, u64 *mid, Load ld, Store st, cudaStream_t stream) {
-    return forward ? run_ntt_dir<true>(ctx, groups, mid, ld, st, stream) : run_ntt_dir<false>(ctx, groups, mid, ld, st, stream);
+static b2_status run_ntt(b2_ctx *ctx, b2_scratch *sc, bool forward, const std::vector<LimbGroup> &groups, u64 *mid, Load ld, Store st, cudaStream_t stream) {
+    return forward ? run_ntt_dir<true>(ctx, sc, groups, mid, ld, st, stream) : run_ntt_dir<false>(ctx, sc, groups, mid, ld, st, stream);
 }
 
 

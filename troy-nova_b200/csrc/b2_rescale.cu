@@ -67,12 +67,14 @@ extern "C" b2_status b2_mod_switch_to_next(b2_ctx *ctx, const uint64_t *in, uint
     }
     B2_REQUIRE(kind != B2_MODSWITCH_BGV || ctx->t > 1, "BGV needs a plain modulus");
     // workspace: u [count][N] | mid [count][nl-1][N]
-    b2_status st = ensure_ws(ctx, (count * n + count * (nl - 1) * n) * 8);
+    Scratch scl(ctx, stream);
+    b2_scratch *sc = scl.s;
+    b2_status st = ensure_ws(sc, stream, (count * n + count * (nl - 1) * n) * 8);
     if (st != B2_OK) return st;
-    u64 *u = (u64 *)ctx->ws, *mid = u + count * n;
+    u64 *u = (u64 *)sc->ws, *mid = u + count * n;
     {   // u_p = INTT_{q_last}(in[p][last])
         std::vector<LimbGroup> groups{LimbGroup{(u32)last, (u32)count, 0, (u64)n}};
-        st = run_ntt_dir<false>(ctx, groups, u, LastLimbLoad{(const u64 *)in, (u32)nl, (u32)n}, PlainStore{u}, stream);
+        st = run_ntt_dir<false>(ctx, sc, groups, u, LastLimbLoad{(const u64 *)in, (u32)nl, (u32)n}, PlainStore{u}, stream);
         if (st != B2_OK) return st;
     }
     {   // NTT of the correction term, final store scales by q_last^-1
@@ -81,10 +83,10 @@ extern "C" b2_status b2_mod_switch_to_next(b2_ctx *ctx, const uint64_t *in, uint
         RescaleStore sst{(const u64 *)in, (u64 *)out, ctx->d_mods, ctx->d_inv + last * K, (u32)nl, (u32)n};
         if (kind == B2_MODSWITCH_BGV) {
             ModDownTerm<true> T{u, ctx->d_mods, (u32)last, (u32)n, ctx->t, ctx->t_ratio, ctx->t_r0, ctx->t_r1, ctx->h_inv_mod_t[last]};
-            st = run_ntt_dir<true>(ctx, groups, mid, ModDownLoad<true>{T}, sst, stream);
+            st = run_ntt_dir<true>(ctx, sc, groups, mid, ModDownLoad<true>{T}, sst, stream);
         } else {
             ModDownTerm<false> T{u, ctx->d_mods, (u32)last, (u32)n, ctx->t, ctx->t_ratio, ctx->t_r0, ctx->t_r1, 0};
-            st = run_ntt_dir<true>(ctx, groups, mid, ModDownLoad<false>{T}, sst, stream);
+            st = run_ntt_dir<true>(ctx, sc, groups, mid, ModDownLoad<false>{T}, sst, stream);
         }
         if (st != B2_OK) return st;
     }

@@ -398,8 +398,12 @@ void Evaluator::mod_switch_to_next(const Ciphertext &e, Ciphertext &d) const {
     check(b2_mod_switch_to_next(context_->raw(), e.data(), r.data(), e.polynomial_count(), L, kind, context_->stream), "[Evaluator::mod_switch_to_next]");
     if (s == SchemeType::BGV) {      // correction_factor *= q_last^-1 mod t (src/evaluator_modswitch.cu:69-73)
         const uint64_t t = context_->plain_modulus(), ql = context_->coeff_modulus()[L - 1] % t;
-        uint64_t inv = 1, base = ql, ex = t - 2;                 // t is prime for batching parameters
-        while (ex) { if (ex & 1) inv = mulmod_u64(inv, base, t); base = mulmod_u64(base, base, t); ex >>= 1; }
+        // general modular inverse (extended Euclid): the plain modulus need not be prime (the reference uses
+        // utils::try_invert_uint64_mod here); a non-invertible q_last is a parameter error
+        __int128 r0 = (__int128)t, r1 = (__int128)ql, s0 = 0, s1 = 1;
+        while (r1 != 0) { const __int128 qq = r0 / r1, r2 = r0 - qq * r1, s2 = s0 - qq * s1; r0 = r1; r1 = r2; s0 = s1; s1 = s2; }
+        if (r0 != 1) throw std::invalid_argument("[Evaluator::mod_switch_to_next] q_last is not invertible modulo the plain modulus.");
+        const uint64_t inv = (uint64_t)((s0 % (__int128)t + (__int128)t) % (__int128)t);
         r.correction_factor() = mulmod_u64(e.correction_factor(), inv, t);
     }
     d = std::move(r);
