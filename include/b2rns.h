@@ -163,6 +163,15 @@ b2_status b2_dyadic_broadcast(b2_ctx *ctx, const uint64_t *a, const uint64_t *pl
  * a, out [batch][pcount][ncomp][N], plain [batch][ncomp][N]; ciphertext b is multiplied by plaintext b, one launch */
 b2_status b2_dyadic_broadcast_batched(b2_ctx *ctx, const uint64_t *a, const uint64_t *plain, uint64_t *out, size_t batch, size_t pcount, size_t ncomp,
                                       int accumulate, void *stream);
+/* Evaluator::multiply_plain_ntt_batched / multiply_plain_ntt_accumulate over SCATTERED operands
+ * (src/evaluator_multiply_plain.cu:216-307 -> kernel_dyadic_broadcast_product_bps, src/fgk/dyadic_convolute.cu:167-171).
+ * ct / pt / dest are HOST arrays of n_terms DEVICE pointers: ct[i] [pcount][ncomp][N], pt[i] [ncomp][N], dest[i]
+ * [pcount][ncomp][N]; limb j uses modulus table_base + j.  Destinations may REPEAT: all terms with the same destination are
+ * summed into it (the reference loops the terms in-thread in order; modular sums are order-independent, so the stored words
+ * are identical).  add_to_dest != 0 keeps the destinations' contents as starting values (the reference's set_zero == false).
+ * One launch per 65535 distinct destinations; every operand word is read once. */
+b2_status b2_multiply_plain_accumulate(b2_ctx *ctx, const uint64_t *const *ct, const uint64_t *const *pt, uint64_t *const *dest, size_t n_terms,
+                                       size_t pcount, size_t ncomp, size_t table_base, int add_to_dest, void *stream);
 /* Evaluator::bfv_multiply / bfv_square device branch (src/evaluator.cu:29-116,199-282) = BEHZ RNS multiplication:
  * RNSTool::fast_b_conv_m_tilde_sm_mrq + NTT + dyadic convolution + INTT + RNSTool::fast_floor_fast_b_conv_sk
  * (src/fgk/rns_tool.cu:7-343).  a, b [batch][2][nl][N] coefficient form -> out [batch][3][nl][N] coefficient form.

@@ -54,8 +54,10 @@ _SIGS = {
     "b2_stream_sync": (C.c_int, [vp, vp]),
 }
 _NTT_ARGS = [vp, vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t, vp]
-for _n in ("b2_ntt_forward", "b2_ntt_inverse", "b2_ntt_forward_ptrs", "b2_ntt_inverse_ptrs", "b2_ntt_forward_host", "b2_ntt_inverse_host"):
+for _n in ("b2_ntt_forward", "b2_ntt_inverse", "b2_ntt_forward_host", "b2_ntt_inverse_host"):
     _SIGS[_n] = (C.c_int, _NTT_ARGS)
+for _n in ("b2_ntt_forward_ptrs", "b2_ntt_inverse_ptrs"):
+    _SIGS[_n] = (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t, vp])
 
 
 _SIGS.update({
@@ -77,6 +79,7 @@ _SIGS.update({
     "b2_dyadic_square": (C.c_int, [vp, vp, vp, C.c_size_t, C.c_size_t, vp]),
     "b2_dyadic_broadcast": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_size_t, C.c_int, vp]),
     "b2_dyadic_broadcast_batched": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, vp]),
+    "b2_multiply_plain_accumulate": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, vp]),
     "b2_negacyclic_shift": (C.c_int, [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp]),
     "b2_galois": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, vp]),
     "b2_bfv_multiply": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_size_t, vp]),
@@ -190,6 +193,15 @@ class Context:
         _chk(self.L.b2_ntt_inverse(self.h, _dptr(src), _dptr(dst), batch, pcount, ncomp, mode, table_base, decomp, self._stream(stream)))
         return dst
 
+    def ntt_ptrs(self, forward, srcs, dsts=None, pcount=1, ncomp=1, mode=TABLES_COMPONENTWISE, table_base=0, decomp=0, stream=None):
+        """scattered batch (the reference's *_batched over a SliceVec): lists of device tensors / raw pointers, ONE launch"""
+        dsts = srcs if dsts is None else dsts
+        nb = len(srcs)
+        ip = (vp * nb)(*[_dptr(t) for t in srcs]); op = (vp * nb)(*[_dptr(t) for t in dsts])
+        f = self.L.b2_ntt_forward_ptrs if forward else self.L.b2_ntt_inverse_ptrs
+        _chk(f(self.h, ip, op, nb, pcount, ncomp, mode, table_base, decomp, self._stream(stream)))
+        return dsts
+
     def ntt_host(self, forward, src_np, dst_np, batch=1, pcount=1, ncomp=1, mode=TABLES_COMPONENTWISE, table_base=0, decomp=0, stream=0):
         f = self.L.b2_ntt_forward_host if forward else self.L.b2_ntt_inverse_host
         _chk(f(self.h, src_np.ctypes.data, dst_np.ctypes.data, batch, pcount, ncomp, mode, table_base, decomp, stream))
@@ -255,6 +267,13 @@ class Context:
 
     def dyadic_broadcast_batched(self, a, plain, out, batch, pcount, ncomp, accumulate=False, stream=None):
         _chk(self.L.b2_dyadic_broadcast_batched(self.h, _dptr(a), _dptr(plain), _dptr(out), batch, pcount, ncomp, int(accumulate), self._stream(stream))); return out
+
+    def multiply_plain_accumulate(self, cts, pts, dests, pcount, ncomp, add_to_dest=False, table_base=0, stream=None):
+        """dest[i] (+)= ct[i] o pt[i] over lists of device tensors / pointers; destinations may repeat; one launch"""
+        nt = len(cts)
+        cp = (vp * nt)(*[_dptr(t) for t in cts]); pp = (vp * nt)(*[_dptr(t) for t in pts]); dp = (vp * nt)(*[_dptr(t) for t in dests])
+        _chk(self.L.b2_multiply_plain_accumulate(self.h, cp, pp, dp, nt, pcount, ncomp, table_base, int(add_to_dest), self._stream(stream)))
+        return dests
 
     def bfv_multiply(self, a, b, out, nl, batch=1, stream=None):
         _chk(self.L.b2_bfv_multiply(self.h, _dptr(a), _dptr(b), _dptr(out), batch, nl, self._stream(stream))); return out

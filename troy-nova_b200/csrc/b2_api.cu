@@ -38,7 +38,7 @@ Scratch::Scratch(b2_ctx *ctx, cudaStream_t stream) : s(nullptr) {
 void scratch_release_all(b2_ctx *ctx) {
     for (auto &kv : ctx->scratch) {
         b2_scratch *sc = kv.second;
-        cudaFree(sc->ws); cudaFree(sc->stage); cudaFree(sc->d_sync);
+        cudaFree(sc->ws); cudaFree(sc->stage); cudaFree(sc->d_sync); cudaFree(sc->ptrtab);
         for (cudaEvent_t e : sc->events) cudaEventDestroy(e);
         if (sc->s_in) cudaStreamDestroy(sc->s_in);
         if (sc->s_out) cudaStreamDestroy(sc->s_out);
@@ -61,6 +61,14 @@ b2_status ensure_stage(b2_scratch *sc, cudaStream_t stream, size_t bytes) {
     if (sc->stage) { B2_CUDA(cudaStreamSynchronize(stream)); B2_CUDA(cudaFree(sc->stage)); sc->stage = nullptr; sc->stage_bytes = 0; }
     B2_CUDA(cudaMalloc(&sc->stage, bytes));
     sc->stage_bytes = bytes;
+    return B2_OK;
+}
+b2_status ensure_ptrtab(b2_scratch *sc, cudaStream_t stream, size_t bytes) {
+    if (sc->ptrtab_bytes >= bytes) return B2_OK;
+    if (sc->ptrtab) { B2_CUDA(cudaStreamSynchronize(stream)); B2_CUDA(cudaFree(sc->ptrtab)); sc->ptrtab = nullptr; sc->ptrtab_bytes = 0; }
+    const size_t want = std::max<size_t>(bytes * 2, 1 << 16);
+    B2_CUDA(cudaMalloc(&sc->ptrtab, want));
+    sc->ptrtab_bytes = want;
     return B2_OK;
 }
 b2_status ensure_copy_pipeline(b2_scratch *sc, size_t n_events) {

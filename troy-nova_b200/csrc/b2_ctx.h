@@ -49,6 +49,9 @@ struct b2_scratch {
     std::vector<cudaEvent_t> events;
     // persistent-NTT work queue + per-limb completion counters (zero between launches; the kernel resets them)
     unsigned *d_sync = nullptr; size_t sync_limbs = 0;
+    // device copy of the pointer tables of the *_ptrs / batched entry points (one upload per call, like the reference's
+    // construct_batch, src/utils/box_batch.h:222-247, but into a buffer that is reused)
+    void *ptrtab = nullptr; size_t ptrtab_bytes = 0;
 };
 
 namespace b2 {
@@ -67,6 +70,7 @@ b2_status ensure_ws(b2_scratch *sc, cudaStream_t stream, size_t bytes);
 b2_status ensure_stage(b2_scratch *sc, cudaStream_t stream, size_t bytes);
 b2_status ensure_copy_pipeline(b2_scratch *sc, size_t n_events);
 b2_status ensure_sync(b2_scratch *sc, size_t limbs, cudaStream_t stream);
+b2_status ensure_ptrtab(b2_scratch *sc, cudaStream_t stream, size_t bytes);
 void scratch_release_all(b2_ctx *ctx);
 int build_modulus_tables(uint64_t p, unsigned logn, Tw *T, Tw *IT, double *TD, double *ITD, ModInfo &M, uint64_t &psi_out);
 void behz_release(b2_ctx *ctx);

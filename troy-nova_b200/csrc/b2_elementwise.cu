@@ -4,6 +4,9 @@
 // the Galois automorphisms (src/utils/galois.cu:141-300).  All HBM-bound: 16-byte vector accesses, one
 // pass over the data, the modulus record read once per thread.  Layout [count][ncomp][N]; the modulus
 // of limb j is table_base + j.
+#include <algorithm>
+#include <map>
+#include <vector>
 #include "b2_ctx.h"
 
 using namespace b2;
@@ -141,6 +144,81 @@ __global__ void __launch_bounds__(256) ew_broadcast_kernel(const ulonglong2 *__r
     }
 }
 
+
+// ---- multiply_plain over scattered pointers, ONE launch (M3 / B1) -----------------------------------------------------
+// Reference: Evaluator::multiply_plain_ntt_batched / multiply_plain_ntt_accumulate (src/evaluator_multiply_plain.cu:216-307)
+// -> kernel_dyadic_broadcast_product_bps (src/fgk/dyadic_convolute.cu:167-171), whose in-thread loop over the batch makes
+// REPEATED destinations well defined: dest[i] (+)= ct[i] o pt[i] for i = 0, 1, ... in order.  Here the host groups the terms
+// by destination (CSR: terms row_start[d] .. row_start[d+1] all write dest d) and a thread accumulates all terms of one
+// destination word in registers: every ciphertext / plaintext word is read once, every destination word is read at most
+// once and written once, however many terms it has.  The sums are the same canonical residues (modular addition is
+// associative), so the result is bit-identical to the reference's term-by-term order.
+//   ct[i] [pcount][ncomp][N], pt[i] [ncomp][N], dest[d] [pcount][ncomp][N]; limb j uses modulus table_base + j
+struct TermTables { const u64 *const *ct; const u64 *const *pt; u64 *const *dest; const u32 *row_start; };
+template <int PC>
+__global__ void __launch_bounds__(256) ew_terms_kernel(TermTables T, const ModInfo *__restrict__ mods, u32 ncomp, u32 n2, u32 table_base, u32 pcount_,
+                                                         int add_to_dest) {
+    const u32 pcount = PC ? (u32)PC : pcount_;
+    const u32 d = blockIdx.y;
+    const u32 t0 = T.row_start[d], t1 = T.row_start[d + 1];
+    const u64 per = (u64)ncomp * n2;
+    ulonglong2 *__restrict__ dp = reinterpret_cast<ulonglong2 *>(T.dest[d]);
+    for (u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x; v < per; v += (u64)gridDim.x * blockDim.x) {
+        const ModInfo &M = mods[table_base + (u32)(v / n2)];
+        const u64 p = M.p;
+        ulonglong2 res[3];
+        if (M.use_f64) {          // p < 2^41: exact double-double products; partial sums stay below 2^10 p between reductions
+            const double pd = M.pd, pinv = M.pinv;
+            double s[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+            for (u32 t = t0; t < t1; t++) {
+                const ulonglong2 y = __ldg(reinterpret_cast<const ulonglong2 *>(T.pt[t]) + v);
+                const double y0 = u64_to_dd(y.x), y1 = u64_to_dd(y.y);
+                const ulonglong2 *cp = reinterpret_cast<const ulonglong2 *>(T.ct[t]) + v;
+#pragma unroll
+                for (u32 k = 0; k < 3; k++) if (k < pcount) {
+                    const ulonglong2 x = __ldcs(cp + k * per);
+                    s[k][0] += mulmod_dd(u64_to_dd(x.x), y0, pd, pinv);
+                    s[k][1] += mulmod_dd(u64_to_dd(x.y), y1, pd, pinv);
+                }
+                if (((t - t0) & 511) == 511) {
+#pragma unroll
+                    for (u32 k = 0; k < 3; k++) { s[k][0] = reduce_dd(s[k][0], pd, pinv); s[k][1] = reduce_dd(s[k][1], pd, pinv); }
+                }
+            }
+#pragma unroll
+            for (u32 k = 0; k < 3; k++) { res[k].x = dd_to_canonical(reduce_dd(s[k][0], pd, pinv), pd); res[k].y = dd_to_canonical(reduce_dd(s[k][1], pd, pinv), pd); }
+        } else {                  // 128-bit lazy sums, one Barrett reduction per 64 terms (64 products of 61-bit residues < 2^128)
+            const u64 r0 = M.r0, r1 = M.r1;
+            u64 lo[3][2] = {{0, 0}, {0, 0}, {0, 0}}, hi[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+            for (u32 t = t0; t < t1; t++) {
+                const ulonglong2 y = __ldg(reinterpret_cast<const ulonglong2 *>(T.pt[t]) + v);
+                const ulonglong2 *cp = reinterpret_cast<const ulonglong2 *>(T.ct[t]) + v;
+#pragma unroll
+                for (u32 k = 0; k < 3; k++) if (k < pcount) {
+                    const ulonglong2 x = __ldcs(cp + k * per);
+                    mac128(lo[k][0], hi[k][0], x.x, y.x);
+                    mac128(lo[k][1], hi[k][1], x.y, y.y);
+                }
+                if (((t - t0) & 63) == 63) {
+#pragma unroll
+                    for (u32 k = 0; k < 3; k++) {
+                        lo[k][0] = barrett128(lo[k][0], hi[k][0], p, r0, r1); hi[k][0] = 0;
+                        lo[k][1] = barrett128(lo[k][1], hi[k][1], p, r0, r1); hi[k][1] = 0;
+                    }
+                }
+            }
+#pragma unroll
+            for (u32 k = 0; k < 3; k++) { res[k].x = barrett128(lo[k][0], hi[k][0], p, r0, r1); res[k].y = barrett128(lo[k][1], hi[k][1], p, r0, r1); }
+        }
+#pragma unroll
+        for (u32 k = 0; k < 3; k++) if (k < pcount) {
+            ulonglong2 r = res[k];
+            if (add_to_dest) { const ulonglong2 o = dp[k * per + v]; r.x = addmod(o.x, r.x, p); r.y = addmod(o.y, r.y, p); }
+            dp[k * per + v] = r;
+        }
+    }
+}
+
 // multiply by x^shift in Z[x]/(x^N+1)             (host_negacyclic_shift_ps, poly_small_mod.cu:902-925)
 __global__ void __launch_bounds__(256) ew_negacyclic_shift_kernel(const u64 *__restrict__ a, u64 *__restrict__ o, const ModInfo *__restrict__ mods,
                                                                     u32 ncomp, u32 n, u32 table_base, u64 total, u32 shift) {
@@ -265,6 +343,62 @@ b2_status b2_dyadic_broadcast_batched(b2_ctx *ctx, const uint64_t *a, const uint
 }
 b2_status b2_dyadic_broadcast(b2_ctx *ctx, const uint64_t *a, const uint64_t *plain, uint64_t *out, size_t pcount, size_t ncomp, int accumulate, void *stream_) {
     return b2_dyadic_broadcast_batched(ctx, a, plain, out, 1, pcount, ncomp, accumulate, stream_);
+}
+
+// Evaluator::multiply_plain_ntt_batched / multiply_plain_ntt_accumulate over scattered operands, one launch.
+// ct / pt / dest: HOST arrays of n_terms DEVICE pointers; dest[i] may repeat (every term with the same destination is
+// accumulated into it, as the reference's in-thread loop does).  add_to_dest != 0: the destinations' current contents are
+// the starting values (set_zero == false in the reference); 0: they are overwritten by the sums.
+b2_status b2_multiply_plain_accumulate(b2_ctx *ctx, const uint64_t *const *ct, const uint64_t *const *pt, uint64_t *const *dest, size_t n_terms,
+                                       size_t pcount, size_t ncomp, size_t table_base, int add_to_dest, void *stream_) {
+    EW_PROLOG((n_terms == 0 || (ct && pt && dest)) && pcount >= 1 && pcount <= 3 && table_base + ncomp <= ctx->K && ctx->n >= 2, "bad arguments (polynomial count must be 1..3)");
+    if (n_terms * ncomp == 0) return B2_OK;
+    B2_REQUIRE(n_terms < ((size_t)1 << 31), "too many terms");
+    // group the terms by destination, keeping first-appearance order of the destinations
+    std::vector<uint32_t> order(n_terms);
+    std::map<const uint64_t *, uint32_t> slot;
+    std::vector<uint64_t *> dests;
+    std::vector<uint32_t> cnt;
+    for (size_t i = 0; i < n_terms; i++) {
+        B2_REQUIRE(ct[i] && pt[i] && dest[i] && ((((uintptr_t)ct[i] | (uintptr_t)pt[i] | (uintptr_t)dest[i]) & 15) == 0), "null or misaligned operand in batch");
+        auto it = slot.find(dest[i]);
+        if (it == slot.end()) { it = slot.emplace(dest[i], (uint32_t)dests.size()).first; dests.push_back(dest[i]); cnt.push_back(0); }
+        order[i] = it->second; cnt[it->second]++;
+    }
+    const size_t nd = dests.size();
+    // one host blob -> one upload: ct[n_terms] | pt[n_terms] | dest[nd] | row_start[nd + 1]
+    const size_t words = 2 * n_terms + nd, bytes = words * 8 + (nd + 1) * 4;
+    std::vector<uint64_t> blob((bytes + 7) / 8);
+    uint32_t *rs = reinterpret_cast<uint32_t *>(blob.data() + words);
+    rs[0] = 0;
+    for (size_t d = 0; d < nd; d++) rs[d + 1] = rs[d] + cnt[d];
+    std::vector<uint32_t> fill(rs, rs + nd);
+    for (size_t i = 0; i < n_terms; i++) {
+        const uint32_t pos = fill[order[i]]++;
+        blob[pos] = (uint64_t)(uintptr_t)ct[i]; blob[n_terms + pos] = (uint64_t)(uintptr_t)pt[i];
+    }
+    for (size_t d = 0; d < nd; d++) blob[2 * n_terms + d] = (uint64_t)(uintptr_t)dests[d];
+    Scratch sc(ctx, stream);
+    b2_status st = ensure_ptrtab(sc.s, stream, blob.size() * 8);
+    if (st != B2_OK) return st;
+    // pageable source: the runtime stages the bytes before returning, so `blob` may go out of scope; the copy is ordered on
+    // `stream` after every earlier kernel that still reads the table
+    B2_CUDA(cudaMemcpyAsync(sc->ptrtab, blob.data(), blob.size() * 8, cudaMemcpyHostToDevice, stream));
+    const u64 *base = (const u64 *)sc->ptrtab;
+    TermTables T{(const u64 *const *)base, (const u64 *const *)(base + n_terms), (u64 *const *)(base + 2 * n_terms), (const u32 *)(base + words)};
+    const u64 per = (u64)ncomp * (n / 2);
+    for (size_t d0 = 0; d0 < nd; d0 += 65535) {        // gridDim.y limit
+        const unsigned ny = (unsigned)std::min<size_t>(65535, nd - d0);
+        TermTables Td = T; Td.dest = T.dest + d0; Td.row_start = T.row_start + d0;
+        // enough CTAs per destination to fill the machine when there are few destinations, grid-stride otherwise
+        const unsigned gx = (unsigned)std::max<u64>(1, std::min<u64>((per + 255) / 256, (u64)(148 * 8 + ny - 1) / ny));
+        dim3 grid(gx, ny);
+        if (pcount == 2) ew_terms_kernel<2><<<grid, 256, 0, stream>>>(Td, ctx->d_mods, (u32)ncomp, (u32)(n / 2), (u32)table_base, 2u, add_to_dest);
+        else ew_terms_kernel<0><<<grid, 256, 0, stream>>>(Td, ctx->d_mods, (u32)ncomp, (u32)(n / 2), (u32)table_base, (u32)pcount, add_to_dest);
+        count_launches(1);
+        B2_CUDA(cudaGetLastError());
+    }
+    return B2_OK;
 }
 b2_status b2_scale_inv_degree(b2_ctx *ctx, uint64_t *data, size_t count, size_t ncomp, size_t table_base, uint64_t scalar, void *stream_) {
     EW_PROLOG(data && table_base + ncomp <= ctx->K && ctx->n >= 2, "bad arguments");

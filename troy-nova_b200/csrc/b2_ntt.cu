@@ -54,14 +54,46 @@ b2_status b2_ntt_inverse(b2_ctx *ctx, const uint64_t *in, uint64_t *out, size_t 
     return ntt_launch(ctx, false, in, out, batch, pcount, ncomp, mode, table_base, decomp, (cudaStream_t)stream);
 }
 
+// Scattered batch (the reference's ntt_transfer_*_batched over a SliceVec, src/fgk/ntt_grouped.cu:297-344,642-685: one
+// launch with blockIdx.y = batch item).  Here too ONE launch: the pointer tables are uploaded once into the stream's scratch
+// record and the batch is a dimension of the persistent kernel's work queue (limb c of group j = (item c / pcount, poly
+// c % pcount)); the intermediate between the two passes lives in each item's own output, exactly as for contiguous operands.
 static b2_status ntt_ptrs(b2_ctx *ctx, bool fwd, const uint64_t *const *in, uint64_t *const *out, size_t batch, size_t pcount,
-                          size_t ncomp, int mode, size_t table_base, size_t decomp, void *stream) {
+                          size_t ncomp, int mode, size_t table_base, size_t decomp, void *stream_) {
     B2_REQUIRE(ctx && (batch == 0 || (in && out)), "null argument");
-    for (size_t b = 0; b < batch; b++) {
-        b2_status st = ntt_launch(ctx, fwd, in[b], out[b], 1, pcount, ncomp, mode, table_base, decomp, (cudaStream_t)stream);
-        if (st != B2_OK) return st;
+    if (batch * pcount * ncomp == 0) return B2_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (batch == 1 || mode == B2_TABLES_KS_SET_PRODUCTS) {      // KS_SET_PRODUCTS groups by polynomial: not a batched shape the reference uses
+        for (size_t b = 0; b < batch; b++) {
+            b2_status st = ntt_launch(ctx, fwd, in[b], out[b], 1, pcount, ncomp, mode, table_base, decomp, stream);
+            if (st != B2_OK) return st;
+        }
+        return B2_OK;
     }
-    return B2_OK;
+    b2_status st = check_ntt_args(ctx, batch, pcount, ncomp, mode, table_base, decomp);
+    if (st != B2_OK) return st;
+    for (size_t b = 0; b < batch; b++) {
+        B2_REQUIRE(in[b] && out[b], "null operand in batch");
+        B2_REQUIRE((((uintptr_t)in[b] | (uintptr_t)out[b]) & 15) == 0, "operands must be 16-byte aligned");
+    }
+    B2_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = ctx->n, K = ctx->K;
+    Scratch sc(ctx, stream);
+    st = ensure_ptrtab(sc.s, stream, 2 * batch * 8);
+    if (st != B2_OK) return st;
+    std::vector<uint64_t> blob(2 * batch);
+    for (size_t b = 0; b < batch; b++) { blob[b] = (uint64_t)(uintptr_t)in[b]; blob[batch + b] = (uint64_t)(uintptr_t)out[b]; }
+    B2_CUDA(cudaMemcpyAsync(sc->ptrtab, blob.data(), blob.size() * 8, cudaMemcpyHostToDevice, stream));
+    const u64 *const *d_in = (const u64 *const *)sc->ptrtab;
+    const u64 *const *d_out = d_in + batch;
+    std::vector<LimbGroup> groups;
+    for (size_t j = 0; j < ncomp; j++) {
+        const u32 table = mode == B2_TABLES_COMPONENTWISE ? (u32)(table_base + j) : (u32)(j == decomp ? K - 1 : j);
+        groups.push_back(LimbGroup{table, (u32)(batch * pcount), (u64)(j * n), 0});      // stride unused: offsets come from the table
+    }
+    NttScatter sca; sca.out_tab = d_out; sca.pc = (u32)pcount; sca.pstride = (u64)ncomp * n;
+    u64 *mid = (u64 *)out[0];
+    return run_ntt(ctx, sc.s, fwd, groups, mid, PtrTabLoad{d_in, (u32)pcount, (u32)n, (u64)ncomp * n}, PlainStore{mid}, stream, sca);
 }
 b2_status b2_ntt_forward_ptrs(b2_ctx *ctx, const uint64_t *const *in, uint64_t *const *out, size_t batch, size_t pcount,
                               size_t ncomp, int mode, size_t table_base, size_t decomp, void *stream) {

@@ -62,8 +62,19 @@ struct NttJob {
     u32 total_items;    // 2 * n_limbs * tiles
     int g_base;         // index of groups[0] in the caller's group list (functors see absolute indices)
     int n_groups;
+    // scattered batches (b2_ntt_*_ptrs, the reference's SliceVec operands): limb c of a group belongs to batch item
+    // c / tab_pc; its offset is that item's distance from `mid` (= out_tab[0]) plus the in-item offset.  Null: contiguous.
+    const u64 *const *out_tab;
+    u32 tab_pc;         // limbs of one group per batch item (pcount)
+    u64 tab_pstride;    // elements between consecutive polynomials of an item (ncomp * N)
     LimbGroup groups[NTT_MAX_GROUPS];
 };
+// element offset (relative to J.mid) of limb c of a group
+__device__ __forceinline__ u64 limb_offset(const NttJob &J, const LimbGroup &grp, u32 c) {
+    if (J.out_tab == nullptr) return grp.base + (u64)c * grp.stride;
+    const u32 b = c / J.tab_pc, k = c - b * J.tab_pc;
+    return (u64)(J.out_tab[b] - J.mid) + grp.base + (u64)k * J.tab_pstride;
+}
 
 // XOR swizzle of a tile-local coefficient index (8-byte units).  It is GF(2)-linear, so
 // swz(a | b) == swz(a) ^ swz(b) for disjoint a, b: per-register offsets are compile-time constants.
@@ -278,6 +289,15 @@ __device__ __forceinline__ void inv_round(const AR &ar, typename AR::T (&v)[16],
 struct PlainLoad {
     const u64 *base;
     __device__ __forceinline__ const u64 *src(int, int, u64 off) const { return base + off; }
+    B2_IDENTITY_XF
+};
+// scattered batch: limb c of group g lives in batch item c / pc at [c % pc][g0 + g][N] of that item
+struct PtrTabLoad {
+    const u64 *const *tab; u32 pc, n; u64 pstride;
+    __device__ __forceinline__ const u64 *src(int g, int c, u64) const {
+        const u32 b = (u32)c / pc, k = (u32)c - b * pc;
+        return tab[b] + (u64)k * pstride + (u64)g * n;
+    }
     B2_IDENTITY_XF
 };
 // A STORE functor receives canonical results.  prep(g, c, off) is evaluated once per work item (row pointers, per-limb
@@ -555,7 +575,7 @@ __global__ void __launch_bounds__(NTT_THREADS, OCC) ntt_persistent_kernel(const 
     auto stage_item = [&](const NttItem &it) {
         const u32 c = it.limb / (u32)J.n_groups, g = it.limb - c * (u32)J.n_groups;
         const LimbGroup &grp = J.groups[g];
-        const u64 off = grp.base + (u64)c * grp.stride;
+        const u64 off = limb_offset(J, grp, c);
         if (it.phase == 0) {
             const u64 *src = ld.src(J.g_base + (int)g, (int)c, off);
             stage_tile<A, FWD>(stage, src, (int)it.tile);          // forward: column tile; inverse: row tile
@@ -614,7 +634,7 @@ __global__ void __launch_bounds__(NTT_THREADS, OCC) ntt_persistent_kernel(const 
             {
                 const u32 c = cur.limb / (u32)J.n_groups, g = cur.limb - c * (u32)J.n_groups;
                 const LimbGroup &grp = J.groups[g];
-                const u64 off = grp.base + (u64)c * grp.stride;
+                const u64 off = limb_offset(J, grp, c);
                 const ModInfo &M = J.mods[group_table(grp.table)];
                 const u32 path = group_path(grp.table, FWD);
                 const int ga = J.g_base + (int)g;

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_cluster_kernel(const __gri
     const u32 limb = blockIdx.x / CL_SIZE;
     const u32 c = limb / (u32)J.n_groups, g = limb - c * (u32)J.n_groups;
     const LimbGroup &grp = J.groups[g];
-    const u64 off = grp.base + (u64)c * grp.stride;
+    const u64 off = limb_offset(J, grp, c);
     const ModInfo &M = J.mods[group_table(grp.table)];
     const u32 path = group_path(grp.table, FWD);
     const int ga = J.g_base + (int)g;

@@ -18,7 +18,7 @@ __global__ void ntt_small_kernel(const __grid_constant__ NttJob P, Load ld, Stor
     const int c = blockIdx.x;
     if (c >= (int)grp.count) return;
     const ModInfo M = P.mods[group_table(grp.table)];
-    const u64 off = grp.base + (u64)c * grp.stride;
+    const u64 off = limb_offset(P, grp, (u32)c);
     const int logn = P.logn, n = 1 << logn, half = n >> 1;
     const int g = P.g_base + (int)blockIdx.y;
     const u64 p = M.p, p2 = p << 1;
@@ -109,14 +109,17 @@ static inline unsigned cluster_max_limbs() {
 // groups' base/stride address the intermediate buffer `mid` (raw values between the passes); the
 // functors map (group, limb) to wherever the external operands live.  All groups must have the same count.
 // The direction is a template parameter so that a call site instantiates only the kernels it launches.
+struct NttScatter { const u64 *const *out_tab = nullptr; u32 pc = 0; u64 pstride = 0; };   // see NttJob::out_tab
 template <bool FWD, class Load, class Store>
-static b2_status run_ntt_dir(b2_ctx *ctx, b2_scratch *sc, const std::vector<LimbGroup> &groups, u64 *mid, Load ld, Store st, cudaStream_t stream) {
+static b2_status run_ntt_dir(b2_ctx *ctx, b2_scratch *sc, const std::vector<LimbGroup> &groups, u64 *mid, Load ld, Store st, cudaStream_t stream,
+                             const NttScatter &scatter = NttScatter()) {
     const unsigned logn = ctx->logn;
     const size_t n = ctx->n;
     if (groups.empty() || groups[0].count == 0) return B2_OK;
     NttJob P;
     P.mods = ctx->d_mods;
     P.mid = mid;
+    P.out_tab = scatter.out_tab; P.tab_pc = scatter.pc; P.tab_pstride = scatter.pstride;
     P.logn = (int)logn;
     P.count = groups[0].count;
     for (const LimbGroup &g : groups) B2_REQUIRE(g.count == P.count, "internal: limb groups of one transform must have equal counts");
@@ -173,8 +176,9 @@ static b2_status run_ntt_dir(b2_ctx *ctx, b2_scratch *sc, const std::vector<Limb
 }
 // run-time direction (the plain transforms of b2_ntt.cu)
 template <class Load, class Store>
-static b2_status run_ntt(b2_ctx *ctx, b2_scratch *sc, bool forward, const std::vector<LimbGroup> &groups, u64 *mid, Load ld, Store st, cudaStream_t stream) {
-    return forward ? run_ntt_dir<true>(ctx, sc, groups, mid, ld, st, stream) : run_ntt_dir<false>(ctx, sc, groups, mid, ld, st, stream);
+static b2_status run_ntt(b2_ctx *ctx, b2_scratch *sc, bool forward, const std::vector<LimbGroup> &groups, u64 *mid, Load ld, Store st, cudaStream_t stream,
+                         const NttScatter &scatter = NttScatter()) {
+    return forward ? run_ntt_dir<true>(ctx, sc, groups, mid, ld, st, stream, scatter) : run_ntt_dir<false>(ctx, sc, groups, mid, ld, st, stream, scatter);
 }
 
 
