@@ -119,6 +119,10 @@ b2_status b2_ntt_inverse_host(b2_ctx *ctx, const uint64_t *in, uint64_t *out, si
  *      (b2_assign).  BFV ciphertexts are coefficient form, CKKS / BGV are NTT form. ---- */
 b2_status b2_kswitch_key_create(b2_ctx *ctx, const uint64_t *const *digit_ptrs, size_t digits, b2_kswitch_key **out);
 b2_status b2_kswitch_key_create_contiguous(b2_ctx *ctx, const uint64_t *key /* [digits][2][K][N] */, size_t digits, b2_kswitch_key **out);
+/* zero-copy variant for callers that already keep the pointer table on the device (KSwitchKeys::get_data_ptrs,
+ * src/kswitch_keys.h:50-57): device_ptr_table = DEVICE array of `digits` device pointers, digit_ptrs = the same pointers
+ * in a HOST array.  Nothing is allocated or copied; both arrays' contents must outlive the handle. */
+b2_status b2_kswitch_key_wrap(b2_ctx *ctx, const uint64_t *const *device_ptr_table, const uint64_t *const *digit_ptrs, size_t digits, b2_kswitch_key **out);
 void      b2_kswitch_key_destroy(b2_kswitch_key *key);
 b2_status b2_keyswitch(b2_ctx *ctx, const uint64_t *target, size_t decomp, int is_ntt, const b2_kswitch_key *key,
                        uint64_t *dest, int assign, void *stream);

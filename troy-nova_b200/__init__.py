@@ -63,6 +63,7 @@ for _n in ("b2_ntt_forward_ptrs", "b2_ntt_inverse_ptrs"):
 _SIGS.update({
     "b2_kswitch_key_create": (C.c_int, [vp, C.POINTER(vp), C.c_size_t, C.POINTER(vp)]),
     "b2_kswitch_key_create_contiguous": (C.c_int, [vp, vp, C.c_size_t, C.POINTER(vp)]),
+    "b2_kswitch_key_wrap": (C.c_int, [vp, vp, C.POINTER(vp), C.c_size_t, C.POINTER(vp)]),
     "b2_kswitch_key_destroy": (None, [vp]),
     "b2_keyswitch": (C.c_int, [vp, vp, C.c_size_t, C.c_int, vp, vp, C.c_int, vp]),
     "b2_keyswitch_batched": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.c_size_t, C.c_size_t, C.c_int, vp, C.c_int, vp]),

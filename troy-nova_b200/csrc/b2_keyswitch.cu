@@ -28,6 +28,7 @@ struct b2_kswitch_key {
     std::vector<const uint64_t *> h_ptrs; // host copy of the same pointers
     size_t digits = 0;
     int device = 0;
+    bool borrowed = false;               // b2_kswitch_key_wrap: d_ptrs belongs to the caller
     // limb shard (b2_kswitch_key_shard): rows first .. first+count-1 of the output moduli 0..decomp only, owned storage
     uint64_t *own = nullptr;
     size_t rows = 0, first = 0, decomp = 0;   // rows == 0: a full key ([2][K][N] per digit)
@@ -180,8 +181,20 @@ b2_status b2_kswitch_key_create_contiguous(b2_ctx *ctx, const uint64_t *key, siz
     for (size_t j = 0; j < digits; j++) ptrs[j] = key + j * 2 * ctx->K * ctx->n;
     return b2_kswitch_key_create(ctx, ptrs, digits, out);
 }
+// zero-copy handle over a pointer table the caller already keeps on the device (the reference's KSwitchKeys::get_data_ptrs,
+// src/kswitch_keys.h:36-57): no allocation, no copy, no synchronisation — cheap enough to build per keyswitch call
+b2_status b2_kswitch_key_wrap(b2_ctx *ctx, const uint64_t *const *device_ptr_table, const uint64_t *const *digit_ptrs, size_t digits, b2_kswitch_key **out) {
+    B2_REQUIRE(ctx && device_ptr_table && digit_ptrs && out && digits >= 1 && digits <= 64, "bad arguments");
+    b2_kswitch_key *k = new b2_kswitch_key();
+    k->digits = digits; k->device = ctx->device; k->borrowed = true;
+    k->h_ptrs.assign(digit_ptrs, digit_ptrs + digits);
+    k->d_ptrs = (const uint64_t **)device_ptr_table;
+    *out = k;
+    return B2_OK;
+}
 void b2_kswitch_key_destroy(b2_kswitch_key *k) {
     if (!k) return;
+    if (k->borrowed) { delete k; return; }
     cudaSetDevice(k->device);
     cudaFree((void *)k->d_ptrs);
     cudaFree(k->own);
