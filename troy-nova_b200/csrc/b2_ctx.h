@@ -22,6 +22,7 @@ struct b2_ctx {
     b2::Tw *d_tw = nullptr;          // [K][N] forward twiddles
     b2::Tw *d_itw = nullptr;         // [K][N] inverse twiddles
     double *d_twd = nullptr, *d_itwd = nullptr;   // same tables as doubles (FP64-pipe path)
+    double *d_n5 = nullptr;                       // per-row / per-limb tables of the TMA kernel (N = 2^16 only), see ModInfo::n5_*
     std::vector<b2::ModInfo> h_mods;
     b2::Tw *d_inv = nullptr;         // [K][K]: d_inv[a*K+b] = q_a^-1 mod q_b as a Shoup pair (a != b)
     uint64_t *d_inv_mod_t = nullptr; // [K]: q_a^-1 mod t (BFV/BGV), 0 when t == 0

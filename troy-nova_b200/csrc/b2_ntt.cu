@@ -1,7 +1,7 @@
 // b2_ntt.cu — C-ABI entry points b2_ntt_forward / b2_ntt_inverse (+ _ptrs, _host).  Reference seam:
 // utils::ntt_transfer_to_rev / ntt_transfer_from_rev and their _batched forms (src/utils/ntt.h:132-144,
 // src/fgk/ntt_grouped.cu:258-344,597-685).
-#include "b2_ntt_launch.cuh"
+#include "b2_ntt5_launch.cuh"
 
 namespace b2 {
 
@@ -36,6 +36,12 @@ b2_status ntt_launch(b2_ctx *ctx, bool forward, const uint64_t *in, uint64_t *ou
         }
     }
     Scratch sc(ctx, stream);
+    // throughput regime at N = 2^16: the FP64-pipe moduli take the TMA kernel (b2_ntt5.cuh); few-limb calls stay on the
+    // cluster kernel (latency regime)
+    const size_t limbs = batch * pcount * ncomp;
+    if (ctx->logn == N5_LOGN && limbs > cluster_max_limbs() && ((((uintptr_t)in | (uintptr_t)out) & 127) == 0) && n5_enabled())
+        return forward ? run_ntt_split<true>(ctx, sc.s, groups, (const u64 *)in, (u64 *)out, limbs, stream)
+                       : run_ntt_split<false>(ctx, sc.s, groups, (const u64 *)in, (u64 *)out, limbs, stream);
     return run_ntt(ctx, sc.s, forward, groups, (u64 *)out, PlainLoad{(const u64 *)in}, PlainStore{(u64 *)out}, stream);
 }
 

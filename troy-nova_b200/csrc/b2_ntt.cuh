@@ -67,6 +67,7 @@ struct NttJob {
     const u64 *const *out_tab;
     u32 tab_pc;         // limbs of one group per batch item (pcount)
     u64 tab_pstride;    // elements between consecutive polynomials of an item (ncomp * N)
+    u32 dbg;            // developer switches of the TMA kernel (B2_NTT5_DBG): 1 skip the arithmetic, 2 skip the stores
     LimbGroup groups[NTT_MAX_GROUPS];
 };
 // element offset (relative to J.mid) of limb c of a group

@@ -119,7 +119,7 @@ static b2_status run_ntt_dir(b2_ctx *ctx, b2_scratch *sc, const std::vector<Limb
     NttJob P;
     P.mods = ctx->d_mods;
     P.mid = mid;
-    P.out_tab = scatter.out_tab; P.tab_pc = scatter.pc; P.tab_pstride = scatter.pstride;
+    P.out_tab = scatter.out_tab; P.tab_pc = scatter.pc; P.tab_pstride = scatter.pstride; P.dbg = 0;
     P.logn = (int)logn;
     P.count = groups[0].count;
     for (const LimbGroup &g : groups) B2_REQUIRE(g.count == P.count, "internal: limb groups of one transform must have equal counts");
