@@ -18,6 +18,12 @@ every step streams from HBM).  840 limb-transforms per step per GPU.
 Multi-GPU (torchrun, one rank per GPU): the batch is sharded by ciphertext (independent limbs, no data-path
 collective) -> weak scaling; NCCL is only used for the barrier and the max-over-ranks of the timings.
 
+The second half of BASELINE's metric — relinearize / rotate ops/s on the same parameter set — is reported as TOP-LEVEL
+blocks "relinearize" and "rotate", each with its own value (data resident), roofline (492.8 MB compulsory bytes per keyswitch,
+SURVEY.md §8d), cpu_baseline (the reference's host Evaluator::relinearize / rotate_vector through oracle/_ref, threads stated)
+and e2e (b2_keyswitch_host: ciphertext in pinned host memory, key resident).  "gpu_baseline" times the reference's own DEVICE
+branch (its generic kernels recompiled for sm_100, oracle/_ref) in the same run: the bar SURVEY.md §8d sets.
+
 --impl reference : times the reference's CPU implementation of the same path (oracle/_ref when built, else
 the C oracle port) on all host cores, bounded sample per step.
 """
@@ -47,6 +53,14 @@ def measured_traffic():
     p = os.path.join(ROOT, "profiles", "ntt_traffic.json")
     try:
         return json.load(open(p))
+    except Exception:
+        return None
+
+
+def ks_traffic(name):
+    """dram bytes of one C3 keyswitch from the committed ncu launch list (profiles/ks_traffic.json), or None"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ks_traffic.json")))["bytes_per_keyswitch"]
     except Exception:
         return None
 
@@ -129,6 +143,54 @@ def cpu_reference_ntt(seconds_budget=12.0, threads=None):
             "sample": "%d limb-transforms (N=2^16, fwd+inv, 60/40-bit primes) over %.1f s on %d threads" % (total, wall, threads)}
 
 
+def cpu_reference_keyswitch(seconds_budget=6.0, threads=None):
+    """Reference host Evaluator::relinearize and rotate_vector(1) at C3 (CKKS N=65536, 20+1 moduli) through oracle/_ref:
+    one shared context (keys are read-only), `threads` host threads each timing its own ciphertexts.  ops/s per op kind."""
+    import pyoracle as po
+    if not po.ref_available():
+        return None
+    n = 1 << LOG_N
+    threads = threads or min(os.cpu_count() or 1, 16)
+    r = po.Reference(po.CKKS, n, BITS, seed=0x123)
+    r.gen_relin()
+    r.gen_galois([r.galois_element_from_step(1)])
+    out = {}
+    for op, name in ((3, "relinearize"), (4, "rotate")):
+        res = [None] * threads
+
+        def work(i):
+            t0 = time.perf_counter(); k = 0; busy = 0.0
+            while time.perf_counter() - t0 < seconds_budget or k == 0:
+                busy += r.time_op(op, NCOMP - 1, 1, 0, 1); k += 1
+            res[i] = (k, busy)
+        ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+        [t.start() for t in ths]; [t.join() for t in ths]
+        out[name] = {"value": sum(k / b for k, b in res), "unit": "ops/s", "cores": threads, "kind": "reference",
+                     "sample": "%d x Evaluator::%s on the host branch (CKKS N=65536, 20 limbs + special prime, reference KeyGenerator keys, seed 0x123) "
+                               "on %d threads, %.2f s per op per thread" % (sum(k for k, _ in res), "relinearize_new" if op == 3 else "rotate_vector_new(1)", threads,
+                                                                             sum(b for _, b in res) / max(1, sum(k for k, _ in res)))}
+    return out
+
+
+def gpu_reference_baseline():
+    """The reference's DEVICE branch (oracle/_ref = its generic kernels recompiled for sm_100) on this GPU, data resident:
+    the GPU bar of SURVEY.md §8d.  Timed by the shim with cudaDeviceSynchronize around each op."""
+    import pyoracle as po
+    if not po.ref_available():
+        return None
+    n = 1 << LOG_N
+    r = po.Reference(po.CKKS, n, BITS, seed=0x123, device=True)
+    r.gen_relin()
+    r.gen_galois([r.galois_element_from_step(1)])
+    tf = r.time_op(0, NCOMP, PCOUNT, 2, 10); ti = r.time_op(1, NCOMP, PCOUNT, 2, 10)
+    g = {"kind": "reference device branch (sm_100 recompile of the reference kernels, oracle/_ref)",
+         "ntt_limbs_per_s": 2 * PCOUNT * NCOMP / (tf + ti), "ntt_forward_us": tf * 1e6, "ntt_inverse_us": ti * 1e6}
+    for op, name in ((3, "relinearize"), (4, "rotate"), (2, "multiply"), (5, "rescale")):
+        t = r.time_op(op, NCOMP - 1, 1, 2, 10)
+        g[name + "_us"] = t * 1e6; g[name + "_ops_per_s"] = 1.0 / t
+    return g
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -141,11 +203,17 @@ def run_reference_arm(args):
             vals.append(r)
     v = sum(x["value"] for x in vals) / len(vals)
     cb = dict(vals[-1]); cb["value"] = v
+    ks = None
+    try:
+        ks = cpu_reference_keyswitch(seconds_budget=min(8.0, per_step))
+    except Exception as ex:                      # the NTT line stands on its own
+        ks = {"error": str(ex)[:200]}
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": "C3 CKKS N=65536, q={60,40x19,60}: forward+inverse negacyclic NTT of a [20][21][N] operand (420 limbs, 210 MiB) per GPU per step",
                        "sample": "reference host branch (utils::ntt_inplace_ps on host slices), %.1f s of [2][3][N] forward+inverse calls per step on every host thread, 60/40-bit primes" % per_step},
-            "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+            "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+            "relinearize": (ks or {}).get("relinearize"), "rotate": (ks or {}).get("rotate")}
     print(json.dumps(line), flush=True)
 
 
@@ -216,11 +284,12 @@ def bench_c4(b2, torch, timed, local, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b2", choices=["b2", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b2" else args.warmup
     if args.impl == "reference":
@@ -299,7 +368,7 @@ def main():
     tr = measured_traffic()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": tr["bytes_per_launch"] if tr else None, "traffic_source": tr["source"] if tr else None,
-                "kernel": "ntt_persistent_kernel (one launch = one b2_ntt_forward over 420 limbs, both passes)",
+                "kernel": "b2_ntt_forward over 420 limbs = ntt5_kernel (TMA, 380 FP64-pipe limbs) + ntt_persistent_kernel (40 integer-pipe limbs)",
                 "algorithmic_bytes_per_call": limbs * n * 16, "call_ms": fwd_s * 1e3, "peak_source": peak_src}
 
     # ---- end to end through the host-buffer C ABI (pinned host memory, H2D + D2H inside the timed region)
@@ -343,8 +412,9 @@ def main():
     except Exception as ex:        # measurement aid only
         e2e["host_link_duplex_gbs_per_direction"] = None; e2e["host_link_note"] = str(ex)[:80]
 
-    # ---- extra: relinearize / rotate ops/s on the same parameter set (keyswitch core, data resident)
+    # ---- relinearize / rotate ops/s on the same parameter set (keyswitch core, data resident): top-level blocks of the line
     extra = {}
+    ksblocks = {}
     if not args.no_extra:
         L = NCOMP - 1
         key = torch.empty((L, 2, NCOMP, n), dtype=torch.int64, device="cuda")
@@ -362,6 +432,7 @@ def main():
         def rotate():
             ctx.galois(ct3[:2], gal, rot, 2, L, True)
             ctx.keyswitch(rot[1], L, True, kh, rot, b2.ASSIGN_OVERWRITE_EXCEPT_FIRST)
+        ks_bytes = 8 * n * (L + 2 * L * (L + 1) + 4 * L)          # target + key + dest write + dest read (accumulating forms)
         for name, fn in (("relinearize", relin), ("rotate", rotate)):
             for _ in range(3):
                 fn()
@@ -375,10 +446,39 @@ def main():
             s = max_over_ranks(a0.elapsed_time(a1) * 1e-3)
             extra[name + "_ops_per_s"] = world * k / s
             extra[name + "_us"] = s / k * 1e6
-        extra["keyswitch_compulsory_bytes"] = 8 * n * (L + 2 * L * (L + 1) + 4 * L)
-        extra["keyswitch_hbm_frac"] = extra["keyswitch_compulsory_bytes"] / (extra["relinearize_us"] * 1e-6) / 1e9 / peak
-        extra["note"] = "relinearize/rotate ops/s above: one independent ciphertext stream per GPU (batch sharding, whole-job aggregate)"
+            ach = ks_bytes / (s / k) / 1e9
+            ksblocks[name] = {"value": world * k / s, "unit": "ops/s", "us_per_op": s / k * 1e6, "steps": k,
+                              "config": "C3 CKKS N=65536, 20 limbs + special prime, one ciphertext per GPU per op, operands and key resident in HBM",
+                              "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": ks_traffic(name),
+                                           "algorithmic_bytes_per_op": ks_bytes, "kernels": "INTT(target), mod-up NTT, key inner product, INTT(special), mod-down NTT (5 launches)",
+                                           "peak_source": peak_src}}
+        # end to end: the ciphertext lives in pinned host memory, the key stays resident (b2_keyswitch_host)
+        try:
+            h3 = torch.empty((3, L, n), dtype=torch.int64).pin_memory(); h3.copy_(ct3.cpu())
+            hd = torch.empty((2, L, n), dtype=torch.int64).pin_memory()
+            t_np = h3[2].numpy().view(np.uint64).reshape(-1); d_np = hd.numpy().view(np.uint64).reshape(-1)
+            stream = torch.cuda.current_stream().cuda_stream
 
+            def relin_host():
+                hd.copy_(h3[:2])
+                ctx.keyswitch_host(t_np, L, True, kh, d_np, b2.ASSIGN_ADD_INPLACE, stream=stream)
+            for _ in range(2):
+                relin_host()
+            relin(); torch.cuda.synchronize()
+            assert torch.equal(hd, dest.cpu()), "e2e relinearize differs from the resident result"
+            barrier(); t0 = time.perf_counter(); k = max(5, args.steps // 2)
+            for _ in range(k):
+                relin_host()
+            s = max_over_ranks(time.perf_counter() - t0)
+            for nm in ("relinearize", "rotate"):
+                ksblocks[nm]["e2e"] = {"value": world * k / s, "unit": "ops/s", "h2d_bytes_per_step": 3 * L * n * 8, "d2h_bytes_per_step": 2 * L * n * 8,
+                                       "note": "b2_keyswitch_host: target + destination from pinned host memory, key resident, result back to the host; "
+                                               "measured on relinearize (rotate moves the same bytes)"}
+            del h3, hd
+        except Exception as ex:
+            for nm in ("relinearize", "rotate"):
+                ksblocks[nm]["e2e"] = {"error": str(ex)[:160]}
+        extra["keyswitch_compulsory_bytes"] = ks_bytes
         def timed(fn, k):
             for _ in range(2):
                 fn()
@@ -451,8 +551,27 @@ def main():
             extra["limb_partition"] = [sh.partition(L + 1, world, r)[1] for r in range(world)]
 
     cpu = None
+    gpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_ntt()
+        if not args.no_extra:
+            try:
+                kcpu = cpu_reference_keyswitch()
+                for nm in ("relinearize", "rotate"):
+                    if kcpu and nm in ksblocks:
+                        ksblocks[nm]["cpu_baseline"] = kcpu[nm]
+            except Exception as ex:
+                extra["cpu_keyswitch_baseline_error"] = str(ex)[:200]
+    if rank == 0 and world == 1 and not args.no_gpu_baseline and not args.no_extra:
+        try:
+            gpu_base = gpu_reference_baseline()
+            if gpu_base:
+                gpu_base["speedup_ntt"] = value / gpu_base["ntt_limbs_per_s"]
+                for nm in ("relinearize", "rotate"):
+                    if nm in ksblocks:
+                        gpu_base["speedup_" + nm] = ksblocks[nm]["value"] / gpu_base[nm + "_ops_per_s"]
+        except Exception as ex:
+            gpu_base = {"error": str(ex)[:200]}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -462,7 +581,9 @@ def main():
                            "l2": "inputs (210 MiB) larger than L2 (126 MB); no flush needed", "limbs_per_step_per_gpu": 2 * limbs,
                            "sharding": "by ciphertext batch, no data-path collective"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-                "clocks": sampler.summary() if sampler else None, "extra": extra}
+                "clocks": sampler.summary() if sampler else None,
+                "relinearize": ksblocks.get("relinearize") if not args.no_extra else None, "rotate": ksblocks.get("rotate") if not args.no_extra else None,
+                "gpu_baseline": gpu_base, "extra": extra}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

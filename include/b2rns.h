@@ -126,6 +126,9 @@ b2_status b2_kswitch_key_wrap(b2_ctx *ctx, const uint64_t *const *device_ptr_tab
 void      b2_kswitch_key_destroy(b2_kswitch_key *key);
 b2_status b2_keyswitch(b2_ctx *ctx, const uint64_t *target, size_t decomp, int is_ntt, const b2_kswitch_key *key,
                        uint64_t *dest, int assign, void *stream);
+/* same with HOST buffers for target and dest (key resident on the device): H2D, keyswitch, D2H on `stream`, synchronised on return */
+b2_status b2_keyswitch_host(b2_ctx *ctx, const uint64_t *target, size_t decomp, int is_ntt, const b2_kswitch_key *key,
+                            uint64_t *dest, int assign, void *stream);
 /* K5: Evaluator::switch_key_internal_batched (src/evaluator_keyswitching_core.cu:1055-1267): `batch` ciphertexts sharing one
  * key.  targets / dests are HOST arrays of `batch` DEVICE pointers (the reference's ConstSliceVec / vector<Ciphertext*>);
  * the same five launches serve up to 16 ciphertexts at a time, pointer tables travel as kernel arguments. */

@@ -66,6 +66,7 @@ _SIGS.update({
     "b2_kswitch_key_wrap": (C.c_int, [vp, vp, C.POINTER(vp), C.c_size_t, C.POINTER(vp)]),
     "b2_kswitch_key_destroy": (None, [vp]),
     "b2_keyswitch": (C.c_int, [vp, vp, C.c_size_t, C.c_int, vp, vp, C.c_int, vp]),
+    "b2_keyswitch_host": (C.c_int, [vp, vp, C.c_size_t, C.c_int, vp, vp, C.c_int, vp]),
     "b2_keyswitch_batched": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.c_size_t, C.c_size_t, C.c_int, vp, C.c_int, vp]),
     "b2_limb_partition": (C.c_int, [C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "b2_kswitch_key_shard": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(vp)]),
@@ -219,6 +220,11 @@ class Context:
     def keyswitch(self, target, decomp, is_ntt, key, dest, assign=ASSIGN_OVERWRITE, stream=None):
         _chk(self.L.b2_keyswitch(self.h, _dptr(target), decomp, int(is_ntt), key.h, _dptr(dest), assign, self._stream(stream)))
         return dest
+
+    def keyswitch_host(self, target_np, decomp, is_ntt, key, dest_np, assign=ASSIGN_OVERWRITE, stream=0):
+        """target / dest in host memory (numpy uint64, ideally pinned); key resident on the device; synchronised on return"""
+        _chk(self.L.b2_keyswitch_host(self.h, target_np.ctypes.data, decomp, int(is_ntt), key.h, dest_np.ctypes.data, assign, stream))
+        return dest_np
 
     def keyswitch_batched(self, targets, decomp, is_ntt, key, dests, assign=ASSIGN_OVERWRITE, stream=None):
         """targets / dests: lists of device tensors (or raw device pointers), one per ciphertext"""

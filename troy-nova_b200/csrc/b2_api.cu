@@ -38,7 +38,10 @@ Scratch::Scratch(b2_ctx *ctx, cudaStream_t stream) : s(nullptr) {
 void scratch_release_all(b2_ctx *ctx) {
     for (auto &kv : ctx->scratch) {
         b2_scratch *sc = kv.second;
-        cudaFree(sc->ws); cudaFree(sc->stage); cudaFree(sc->d_sync); cudaFree(sc->ptrtab);
+        cudaFree(sc->ws); cudaFree(sc->stage); cudaFree(sc->d_sync); cudaFree(sc->ptrtab); cudaFree(sc->d_sync2);
+        if (sc->s_side) cudaStreamDestroy(sc->s_side);
+        if (sc->ev_fork) cudaEventDestroy(sc->ev_fork);
+        if (sc->ev_join) cudaEventDestroy(sc->ev_join);
         for (cudaEvent_t e : sc->events) cudaEventDestroy(e);
         if (sc->s_in) cudaStreamDestroy(sc->s_in);
         if (sc->s_out) cudaStreamDestroy(sc->s_out);
@@ -61,6 +64,22 @@ b2_status ensure_stage(b2_scratch *sc, cudaStream_t stream, size_t bytes) {
     if (sc->stage) { B2_CUDA(cudaStreamSynchronize(stream)); B2_CUDA(cudaFree(sc->stage)); sc->stage = nullptr; sc->stage_bytes = 0; }
     B2_CUDA(cudaMalloc(&sc->stage, bytes));
     sc->stage_bytes = bytes;
+    return B2_OK;
+}
+b2_status ensure_side(b2_scratch *sc, size_t limbs, cudaStream_t stream) {
+    if (!sc->s_side) {
+        int lo = 0, hi = 0;
+        B2_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        B2_CUDA(cudaStreamCreateWithPriority(&sc->s_side, cudaStreamNonBlocking, hi));      // its few CTAs should be placed first
+        B2_CUDA(cudaEventCreateWithFlags(&sc->ev_fork, cudaEventDisableTiming));
+        B2_CUDA(cudaEventCreateWithFlags(&sc->ev_join, cudaEventDisableTiming));
+    }
+    if (sc->d_sync2 && sc->sync2_limbs >= limbs) return B2_OK;
+    if (sc->d_sync2) { B2_CUDA(cudaStreamSynchronize(stream)); B2_CUDA(cudaStreamSynchronize(sc->s_side)); B2_CUDA(cudaFree(sc->d_sync2)); sc->d_sync2 = nullptr; sc->sync2_limbs = 0; }
+    const size_t want = std::max<size_t>(limbs * 2, 1024);
+    B2_CUDA(cudaMalloc((void **)&sc->d_sync2, (want + 2) * sizeof(unsigned)));
+    B2_CUDA(cudaMemsetAsync(sc->d_sync2, 0, (want + 2) * sizeof(unsigned), stream));
+    sc->sync2_limbs = want;
     return B2_OK;
 }
 b2_status ensure_ptrtab(b2_scratch *sc, cudaStream_t stream, size_t bytes) {

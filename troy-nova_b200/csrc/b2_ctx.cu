@@ -3,16 +3,18 @@
 // HeContext::to_device_inplace (src/he_context.cu:134-145) of NTTTables (src/utils/ntt.cu:14-76).
 #include "b2_ctx.h"
 #include "b2_host_math.h"
+#include <type_traits>
 
 using namespace b2;
 
 namespace b2 {
 // position of twiddle jj of the layer with 2^m twiddles inside a 256-entry table of the TMA kernel (layout: b2_ntt5.cuh)
-static size_t n5_table_slot(int m, size_t jj) {
-    if (m <= 5) return ((size_t)1 << m) + jj;
-    const int per = 1 << (m - 4);                       // twiddles per thread: 4 (m = 6) or 8 (m = 7)
+static size_t n5_table_slot(int m, size_t jj, bool f64) {
+    if (m <= 4) return ((size_t)1 << m) + jj;
+    const int per = 1 << (m - 4);                       // twiddles per thread y: 2 (m = 5), 4 (m = 6) or 8 (m = 7)
     const size_t y = jj / per, i = jj % per;
-    return ((size_t)1 << m) + (i >> 1) * 32 + 2 * y + (i & 1);
+    if (f64) return ((size_t)1 << m) + (i >> 1) * 32 + 2 * y + (i & 1);      // 8-byte entries: two per 16-byte chunk
+    return ((size_t)1 << m) + 16 * i + y;                                    // 16-byte entries: one per chunk
 }
 // Per-modulus constants and twiddle tables (host side).  T / IT: N Shoup pairs each; TD / ITD: the same values as
 // doubles (may be null).  Returns 0, 1 (not a prime below 2^61) or 2 (not 1 mod 2N).
@@ -102,39 +104,39 @@ extern "C" b2_status b2_ctx_create(int device, const b2_params *prm, b2_ctx **ou
     B2_CUDA(cudaMemcpy(c->d_itw, itw.data(), K * n * sizeof(Tw), cudaMemcpyHostToDevice));
     B2_CUDA(cudaMemcpy(c->d_twd, twd.data(), K * n * sizeof(double), cudaMemcpyHostToDevice));
     B2_CUDA(cudaMemcpy(c->d_itwd, itwd.data(), K * n * sizeof(double), cudaMemcpyHostToDevice));
-    // tables of the TMA kernel (b2_ntt5.cuh): the same twiddles, regrouped per 256-point sub-transform
+    // tables of the TMA kernel (b2_ntt5.cuh): the same twiddles, regrouped per 256-point sub-transform — doubles for the
+    // FP64-path moduli, Shoup pairs for the integer-path moduli
     if (logn == 16) {
-        size_t nf = 0;
-        for (size_t i = 0; i < K; i++) nf += c->h_mods[i].use_f64 ? 1 : 0;
-        if (nf) {
-            const size_t per = 2 * 256 + 2 * 256 * 256 + 2 * 256 * 16;          // fcol | icol | frow | irow | frow_u | irow_u
-            std::vector<double> n5(nf * per, 0.0);
-            B2_CUDA(cudaMalloc(&c->d_n5, n5.size() * sizeof(double)));
-            size_t f = 0;
-            for (size_t i = 0; i < K; i++) {
-                if (!c->h_mods[i].use_f64) continue;
-                double *fcol = &n5[f * per], *icol = fcol + 256, *frow = icol + 256, *irow = frow + 65536;
-                const double *ft = &twd[i * n], *it = &itwd[i * n];
-                for (int m = 0; m < 8; m++)
-                    for (size_t jj = 0; jj < ((size_t)1 << m); jj++) {
-                        const size_t s = n5_table_slot(m, jj);
-                        fcol[s] = ft[((size_t)1 << m) + jj];
-                        icol[s] = it[n - (n >> (8 + (7 - m))) + jj];          // layer 8 + u, u = 7 - m, 128 >> u = 2^m entries
-                        for (size_t r = 0; r < 256; r++) {
-                            frow[r * 256 + s] = ft[((size_t)1 << (8 + m)) + (r << m) + jj];
-                            irow[r * 256 + s] = it[n - (n >> (7 - m)) + (r << m) + jj];   // layer l = 7 - m, 128 >> l = 2^m entries per row
-                        }
+        const size_t ent = 2 * 256 + 2 * 65536 + 2 * 4096;          // fcol | icol | frow | irow | frow_u | irow_u  (entries)
+        size_t bytes = 0;
+        for (size_t i = 0; i < K; i++) bytes += ent * (c->h_mods[i].use_f64 ? sizeof(double) : sizeof(Tw));
+        std::vector<unsigned char> blob(bytes);
+        B2_CUDA(cudaMalloc(&c->d_n5, bytes));
+        size_t off = 0;
+        auto fill = [&](auto *base, const auto *ft, const auto *it, bool f64, ModInfo &M) {
+            typedef typename std::remove_pointer<decltype(base)>::type E;
+            E *fcol = base, *icol = fcol + 256, *frow = icol + 256, *irow = frow + 65536, *fu = irow + 65536, *iu = fu + 4096;
+            for (int m = 0; m < 8; m++)
+                for (size_t jj = 0; jj < ((size_t)1 << m); jj++) {
+                    const size_t s = n5_table_slot(m, jj, f64);
+                    fcol[s] = ft[((size_t)1 << m) + jj];
+                    icol[s] = it[n - (n >> (8 + (7 - m))) + jj];          // layer 8 + u, u = 7 - m, 128 >> u = 2^m entries
+                    for (size_t r = 0; r < 256; r++) {
+                        frow[r * 256 + s] = ft[((size_t)1 << (8 + m)) + (r << m) + jj];
+                        irow[r * 256 + s] = it[n - (n >> (7 - m)) + (r << m) + jj];   // layer l = 7 - m, 128 >> l = 2^m entries per row
                     }
-                double *fu = irow + 65536, *iu = fu + 4096;
-                for (size_t r = 0; r < 256; r++)
-                    for (size_t h = 0; h < 16; h++) { fu[r * 16 + h] = frow[r * 256 + h]; iu[r * 16 + h] = irow[r * 256 + h]; }
-                double *d = c->d_n5 + f * per;
-                c->h_mods[i].n5_fcol = d; c->h_mods[i].n5_icol = d + 256; c->h_mods[i].n5_frow = d + 512; c->h_mods[i].n5_irow = d + 512 + 65536;
-                c->h_mods[i].n5_frow_u = d + 512 + 2 * 65536; c->h_mods[i].n5_irow_u = d + 512 + 2 * 65536 + 4096;
-                f++;
-            }
-            B2_CUDA(cudaMemcpy(c->d_n5, n5.data(), n5.size() * sizeof(double), cudaMemcpyHostToDevice));
+                }
+            for (size_t r = 0; r < 256; r++)
+                for (size_t h = 0; h < 16; h++) { fu[r * 16 + h] = frow[r * 256 + h]; iu[r * 16 + h] = irow[r * 256 + h]; }
+            const E *d = reinterpret_cast<const E *>(reinterpret_cast<const unsigned char *>(c->d_n5) + off);
+            M.n5_fcol = d; M.n5_icol = d + 256; M.n5_frow = d + 512; M.n5_irow = d + 512 + 65536;
+            M.n5_frow_u = d + 512 + 2 * 65536; M.n5_irow_u = d + 512 + 2 * 65536 + 4096;
+        };
+        for (size_t i = 0; i < K; i++) {
+            if (c->h_mods[i].use_f64) { fill(reinterpret_cast<double *>(blob.data() + off), &twd[i * n], &itwd[i * n], true, c->h_mods[i]); off += ent * sizeof(double); }
+            else { fill(reinterpret_cast<Tw *>(blob.data() + off), &tw[i * n], &itw[i * n], false, c->h_mods[i]); off += ent * sizeof(Tw); }
         }
+        B2_CUDA(cudaMemcpy(c->d_n5, blob.data(), bytes, cudaMemcpyHostToDevice));
     }
     B2_CUDA(cudaMemcpy(c->d_mods, c->h_mods.data(), K * sizeof(ModInfo), cudaMemcpyHostToDevice));
     // cross-modulus inverses used by mod-down / rescale (reference: RNSTool::inv_q_last_mod_q, inv_q_last_mod_t,

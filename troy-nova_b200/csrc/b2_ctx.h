@@ -22,7 +22,7 @@ struct b2_ctx {
     b2::Tw *d_tw = nullptr;          // [K][N] forward twiddles
     b2::Tw *d_itw = nullptr;         // [K][N] inverse twiddles
     double *d_twd = nullptr, *d_itwd = nullptr;   // same tables as doubles (FP64-pipe path)
-    double *d_n5 = nullptr;                       // per-row / per-limb tables of the TMA kernel (N = 2^16 only), see ModInfo::n5_*
+    void *d_n5 = nullptr;                         // per-row / per-limb tables of the TMA kernel (N = 2^16 only), see ModInfo::n5_*
     std::vector<b2::ModInfo> h_mods;
     b2::Tw *d_inv = nullptr;         // [K][K]: d_inv[a*K+b] = q_a^-1 mod q_b as a Shoup pair (a != b)
     uint64_t *d_inv_mod_t = nullptr; // [K]: q_a^-1 mod t (BFV/BGV), 0 when t == 0
@@ -53,6 +53,10 @@ struct b2_scratch {
     // device copy of the pointer tables of the *_ptrs / batched entry points (one upload per call, like the reference's
     // construct_batch, src/utils/box_batch.h:222-247, but into a buffer that is reused)
     void *ptrtab = nullptr; size_t ptrtab_bytes = 0;
+    // mixed transforms at N = 2^16: the integer-pipe limbs run on a side stream next to the TMA kernel (b2_ntt5_launch.cuh), with
+    // their own work queue
+    cudaStream_t s_side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    unsigned *d_sync2 = nullptr; size_t sync2_limbs = 0;
 };
 
 namespace b2 {
@@ -72,6 +76,7 @@ b2_status ensure_stage(b2_scratch *sc, cudaStream_t stream, size_t bytes);
 b2_status ensure_copy_pipeline(b2_scratch *sc, size_t n_events);
 b2_status ensure_sync(b2_scratch *sc, size_t limbs, cudaStream_t stream);
 b2_status ensure_ptrtab(b2_scratch *sc, cudaStream_t stream, size_t bytes);
+b2_status ensure_side(b2_scratch *sc, size_t limbs, cudaStream_t stream);
 void scratch_release_all(b2_ctx *ctx);
 int build_modulus_tables(uint64_t p, unsigned logn, Tw *T, Tw *IT, double *TD, double *ITD, ModInfo &M, uint64_t &psi_out);
 void behz_release(b2_ctx *ctx);

@@ -312,6 +312,35 @@ b2_status b2_keyswitch_batched(b2_ctx *ctx, const uint64_t *const *targets, uint
     return B2_OK;
 }
 
+// Host-buffer keyswitch (the e2e leg of bench.py; what a host-memory caller of the reference does with to_device / to_host
+// around Evaluator::relinearize / apply_galois): the key stays resident on the device, target and destination live in host
+// memory (pinned for full-rate DMA).  H2D of the target (and of the destination when it is accumulated into), the five
+// launches, D2H of the destination; synchronised on return.
+b2_status b2_keyswitch_host(b2_ctx *ctx, const uint64_t *target, size_t decomp, int is_ntt, const b2_kswitch_key *key,
+                            uint64_t *dest, int assign, void *stream_) {
+    B2_REQUIRE(ctx && target && key && dest, "null argument");
+    B2_REQUIRE(decomp >= 1 && decomp + 1 <= ctx->K, "decomp must be in [1, K-1]");
+    B2_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t n = ctx->n, tb = decomp * n * 8, db = 2 * decomp * n * 8;
+    uint64_t *d_t = nullptr, *d_d = nullptr;
+    {
+        Scratch sc(ctx, stream);
+        b2_status st = ensure_stage(sc.s, stream, tb + db);
+        if (st != B2_OK) return st;
+        d_t = (uint64_t *)sc->stage; d_d = d_t + decomp * n;
+    }   // (the scratch lock is released: b2_keyswitch takes it again; the staging buffer is private to this stream)
+    B2_CUDA(cudaMemcpyAsync(d_t, target, tb, cudaMemcpyHostToDevice, stream));
+    if (assign == B2_ASSIGN_ADD_INPLACE) B2_CUDA(cudaMemcpyAsync(d_d, dest, db, cudaMemcpyHostToDevice, stream));
+    else if (assign == B2_ASSIGN_OVERWRITE_EXCEPT_FIRST) B2_CUDA(cudaMemcpyAsync(d_d, dest, db / 2, cudaMemcpyHostToDevice, stream));
+    const uint64_t *tp = d_t; uint64_t *dp = d_d;
+    b2_status st = b2_keyswitch_batched(ctx, &tp, &dp, 1, decomp, is_ntt, key, assign, stream_);
+    if (st != B2_OK) return st;
+    B2_CUDA(cudaMemcpyAsync(dest, d_d, db, cudaMemcpyDeviceToHost, stream));
+    B2_CUDA(cudaStreamSynchronize(stream));
+    return B2_OK;
+}
+
 b2_status b2_keyswitch(b2_ctx *ctx, const uint64_t *target, size_t decomp, int is_ntt, const b2_kswitch_key *key,
                        uint64_t *dest, int assign, void *stream_) {
     B2_REQUIRE(ctx && target && key && dest, "null argument");

@@ -112,7 +112,8 @@ struct ModInfo {
     // TMA kernel (b2_ntt5.cuh; N = 2^16, FP64 path only, else null): 256-entry twiddle tables of the 256-point sub-transforms,
     // one per limb for the column passes (fcol / icol) and one per row for the row passes (frow / irow: [256 rows][256])
     // (frow_u / irow_u: entries [0, 16) of every row table, packed [256 rows][16] — the part that is staged in shared memory)
-    const double *n5_fcol, *n5_frow, *n5_icol, *n5_irow, *n5_frow_u, *n5_irow_u;
+    // entries are doubles on the FP64 path, Shoup pairs (Tw) on the integer path
+    const void *n5_fcol, *n5_frow, *n5_icol, *n5_irow, *n5_frow_u, *n5_irow_u;
     u64 pad[8];
 };
 static_assert(sizeof(ModInfo) == 256, "ModInfo must be 256 bytes");

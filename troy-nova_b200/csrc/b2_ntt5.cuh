@@ -20,13 +20,14 @@
 // Shared memory per CTA: two stages of (32 KiB tile + 2 KiB twiddles) = 68 KiB -> 3 CTAs per SM, every load a whole item ahead.
 #pragma once
 #include <cstdio>
+#include <type_traits>
 #include <cuda.h>
 #include "b2_ntt.cuh"
 
 namespace b2 {
 
 constexpr int N5_LOGN = 16;
-constexpr int N5_STAGE_BYTES = 32768, N5_TW_BYTES = 2048;
+constexpr int N5_STAGE_BYTES = 32768, N5_TW_BYTES = 4096;      // per stage: tile + 256 staged twiddles (8-byte or 16-byte entries)
 constexpr int N5_SMEM_BYTES = 2 * (N5_STAGE_BYTES + N5_TW_BYTES) + 1024;      // two stages; + slack to align them to 1024 B (SWIZZLE_128B)
 
 // first pass loads `first` (the operand), stores `mid_st`; second pass loads `mid_ld`, stores `last` (same buffer as mid)
@@ -93,101 +94,130 @@ __device__ __forceinline__ double ldsd(u32 a, u32 tok) { double v; asm("ld.share
 __device__ __forceinline__ double2 ldsd2(u32 a, u32 tok) { double2 v; asm("ld.shared.v2.f64 {%0, %1}, [%2]; // %3\n" : "=d"(v.x), "=d"(v.y) : "r"(a), "r"(tok)); return v; }
 
 // ---- 256-point transforms on 16 registers ---------------------------------------------------------------------------
-// Twiddle table of one 256-point transform (256 doubles; built by b2_ctx.cu: n5_table_slot):
-//   [1 .. 15]            the 15 twiddles of the four layers whose twiddle depends on the REGISTER index only (heap order)
-//   [16 + y]             layer with one twiddle per thread y (0..15)
-//   [32 + 2y + i]        layer with two per thread
-//   [64 + 32q + 2y + i]  layer with four per thread, entry 2q + i      (chunk-major: lanes y read consecutive 16-byte chunks)
-//   [128 + 32q + 2y + i] layer with eight per thread, entry 2q + i
-__device__ __forceinline__ void n5_fwd_uniform(const ArithF64 &ar, double (&v)[16], u32 T, u32 tok) {
+// Twiddle table of one 256-point transform (256 entries; built by b2_ctx.cu: n5_table_slot).  Entries [1, 16): the 15 twiddles
+// of the four layers whose twiddle depends on the REGISTER index only (heap order).  Then the four layers with 1 / 2 / 4 / 8
+// twiddles per thread y (0..15), laid out so that the sixteen lanes of a row / column group read consecutive 16-byte chunks:
+//   FP64 path (8-byte entries)                           integer path (16-byte Shoup pairs)
+//   [16 + y]                                             [16 + y]
+//   [32 + 2y + i]                                        [32 + 16 i + y]
+//   [64 + 32 q + 2y + i]    entry 2q + i of thread y     [64 + 16 i + y]
+//   [128 + 32 q + 2y + i]   entry 2q + i                 [128 + 16 i + y]
+// An accessor hides where the table lives (shared memory for the column passes, global memory for the per-thread part of
+// the row passes: 30 KiB per tile that stay out of shared memory; coalesced read-only loads) and the entry type.
+__device__ __forceinline__ ulonglong2 lds128_tok(u32 a, u32 tok) { ulonglong2 v; asm("ld.shared.v2.u64 {%0, %1}, [%2]; // %3\n" : "=l"(v.x), "=l"(v.y) : "r"(a), "r"(tok)); return v; }
+
+template <class TwT> struct N5Shared;
+template <> struct N5Shared<double> {
+    u32 T, Ty, tok;
+    __device__ __forceinline__ N5Shared(u32 T_, u32 y, u32 tok_) : T(T_), Ty(T_ + 16 * y), tok(tok_) {}
+    __device__ __forceinline__ double uni(int idx) const { return ldsd(T + 8 * idx, tok); }
+    __device__ __forceinline__ double one() const { return ldsd(T + 8 * 16 + (Ty - T) / 2, tok); }
+    template <int M, int I0, int CNT> __device__ __forceinline__ void layer(double (&w)[CNT]) const {      // entries I0 .. I0+CNT-1 of the layer with 2^M twiddles
+#pragma unroll
+        for (int i = 0; i < CNT; i += 2) { const double2 d = ldsd2(Ty + 16 * ((1 << (M - 1)) + 16 * ((I0 + i) >> 1)), tok); w[i] = d.x; w[i + 1] = d.y; }
+    }
+};
+template <> struct N5Shared<Tw> {
+    u32 T, Ty, tok;
+    __device__ __forceinline__ N5Shared(u32 T_, u32 y, u32 tok_) : T(T_), Ty(T_ + 16 * y), tok(tok_) {}
+    __device__ __forceinline__ Tw uni(int idx) const { const ulonglong2 d = lds128_tok(T + 16 * idx, tok); return d; }
+    __device__ __forceinline__ Tw one() const { return lds128_tok(Ty + 16 * 16, tok); }
+    template <int M, int I0, int CNT> __device__ __forceinline__ void layer(Tw (&w)[CNT]) const {
+#pragma unroll
+        for (int i = 0; i < CNT; i++) w[i] = lds128_tok(Ty + 16 * ((1 << M) + 16 * (I0 + i)), tok);
+    }
+};
+template <class TwT> struct N5Global;
+template <> struct N5Global<double> {
+    const double *T; const double2 *T2;
+    __device__ __forceinline__ N5Global(const void *T_, u32 y) : T(reinterpret_cast<const double *>(T_) + y), T2(reinterpret_cast<const double2 *>(T_) + y) {}
+    __device__ __forceinline__ double one() const { return __ldg(T + 16); }
+    template <int M, int I0, int CNT> __device__ __forceinline__ void layer(double (&w)[CNT]) const {
+#pragma unroll
+        for (int i = 0; i < CNT; i += 2) { const double2 d = __ldg(T2 + (1 << (M - 1)) + 16 * ((I0 + i) >> 1)); w[i] = d.x; w[i + 1] = d.y; }
+    }
+};
+template <> struct N5Global<Tw> {
+    const Tw *T;
+    __device__ __forceinline__ N5Global(const void *T_, u32 y) : T(reinterpret_cast<const Tw *>(T_) + y) {}
+    __device__ __forceinline__ Tw one() const { return __ldg(T + 16); }
+    template <int M, int I0, int CNT> __device__ __forceinline__ void layer(Tw (&w)[CNT]) const {
+#pragma unroll
+        for (int i = 0; i < CNT; i++) w[i] = __ldg(T + (1 << M) + 16 * (I0 + i));
+    }
+};
+
+// layers whose twiddle depends on the register index only (shared-memory table)
+template <class AR>
+__device__ __forceinline__ void n5_fwd_uniform(const AR &ar, typename AR::T (&v)[16], const N5Shared<typename AR::TwT> &tw) {
 #pragma unroll
     for (int s = 0; s < 4; s++) {
         const int j = 3 - s;
-        double w[8];
 #pragma unroll
-        for (int a = 0; a < 8; a++) if (a < (1 << s)) w[a] = ldsd(T + 8 * ((1 << s) + a), tok);
+        for (int a = 0; a < 8; a++) if (a < (1 << s)) {
+            const typename AR::TwT w = tw.uni((1 << s) + a);
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            if (k & (1 << j)) continue;
-            ar.bf_fwd(v[k], v[k | (1 << j)], w[k >> (j + 1)]);
+            for (int k = 0; k < 16; k++) if (!(k & (1 << j)) && (k >> (j + 1)) == a) ar.bf_fwd(v[k], v[k | (1 << j)], w);
         }
     }
 }
-// per-thread twiddles, from the shared-memory table (column passes) ...
-struct N5TwShared {
-    u32 Ty, T, tok; u32 y;
-    __device__ __forceinline__ N5TwShared(u32 T_, int y_, u32 tok_) : Ty(T_ + 16 * (u32)y_), T(T_), tok(tok_), y((u32)y_) {}
-    __device__ __forceinline__ double one() const { return ldsd(T + 8 * (16 + y), tok); }
-    __device__ __forceinline__ double2 chunk(int c) const { return ldsd2(Ty + 16 * c, tok); }     // c: 16-byte chunk row (16 chunks each)
-};
-// ... or from the same table in global memory (row passes: 30 KiB of per-thread twiddles per tile stay out of shared memory;
-// the lanes of a row read consecutive 16-byte chunks, so these are coalesced read-only loads, issued well ahead of their use)
-struct N5TwGlobal {
-    const double *T; const double2 *T2;
-    __device__ __forceinline__ N5TwGlobal(const double *T_, int y) : T(T_ + y), T2(reinterpret_cast<const double2 *>(T_) + y) {}
-    __device__ __forceinline__ double one() const { return __ldg(T + 16); }
-    __device__ __forceinline__ double2 chunk(int c) const { return __ldg(T2 + c); }
-};
-// The loads are staged so that at most 16 + 8 twiddle registers are live at once (the kernel is held to 72 registers):
-// forward needs w1, w2, w4, w8 in that order — w8 (eight twiddles) is requested after the first layer;
-// inverse needs w8 first — w2 and w1 are requested after the first layer.
-template <class TW>
-__device__ __forceinline__ void n5_fwd_thread(const ArithF64 &ar, double (&v)[16], const TW &tw) {
-    double w1 = tw.one(), w2[2], w4[4], w8[8];
-    { const double2 a = tw.chunk(16); w2[0] = a.x; w2[1] = a.y; }
-#pragma unroll
-    for (int q = 0; q < 2; q++) { const double2 d = tw.chunk(32 + 16 * q); w4[2 * q] = d.x; w4[2 * q + 1] = d.y; }
-#pragma unroll
-    for (int k = 0; k < 8; k++) ar.bf_fwd(v[k], v[k | 8], w1);
-#pragma unroll
-    for (int q = 0; q < 4; q++) { const double2 d = tw.chunk(64 + 16 * q); w8[2 * q] = d.x; w8[2 * q + 1] = d.y; }
-#pragma unroll
-    for (int k = 0; k < 16; k++) if (!(k & 4)) ar.bf_fwd(v[k], v[k | 4], w2[k >> 3]);
-#pragma unroll
-    for (int k = 0; k < 16; k++) if (!(k & 2)) ar.bf_fwd(v[k], v[k | 2], w4[k >> 2]);
-#pragma unroll
-    for (int k = 0; k < 16; k++) if (!(k & 1)) ar.bf_fwd(v[k], v[k | 1], w8[k >> 1]);
-}
-// the eight first-layer twiddles are passed in (requested by the caller before it reads the data)
-template <class TW>
-__device__ __forceinline__ void n5_inv_thread(const ArithF64 &ar, double (&v)[16], const TW &tw, const double (&w8)[8]) {
-    double w1, w2[2], w4[4];
-#pragma unroll
-    for (int q = 0; q < 2; q++) { const double2 d = tw.chunk(32 + 16 * q); w4[2 * q] = d.x; w4[2 * q + 1] = d.y; }
-#pragma unroll
-    for (int k = 0; k < 16; k++) if (!(k & 1)) ar.bf_inv(v[k], v[k | 1], w8[k >> 1], 0);
-    { const double2 a = tw.chunk(16); w2[0] = a.x; w2[1] = a.y; }
-    w1 = tw.one();
-#pragma unroll
-    for (int k = 0; k < 16; k++) if (!(k & 2)) ar.bf_inv(v[k], v[k | 2], w4[k >> 2], 0);
-#pragma unroll
-    for (int k = 0; k < 16; k++) if (!(k & 4)) ar.bf_inv(v[k], v[k | 4], w2[k >> 3], 0);
-#pragma unroll
-    for (int k = 0; k < 8; k++) ar.bf_inv(v[k], v[k | 8], w1, 0);
-}
-template <class TW>
-__device__ __forceinline__ void n5_load_w8(const TW &tw, double (&w8)[8]) {
-#pragma unroll
-    for (int q = 0; q < 4; q++) { const double2 d = tw.chunk(64 + 16 * q); w8[2 * q] = d.x; w8[2 * q + 1] = d.y; }
-}
-template <bool LAST>
-__device__ __forceinline__ void n5_inv_uniform(const ArithF64 &ar, double (&v)[16], u32 T, u32 tok) {
+// LB: index of the first of the four layers inside the whole 16-layer inverse transform (the lazy integer path needs it)
+template <bool LAST, int LB, class AR>
+__device__ __forceinline__ void n5_inv_uniform(const AR &ar, typename AR::T (&v)[16], const N5Shared<typename AR::TwT> &tw) {
 #pragma unroll
     for (int s = 0; s < 4; s++) {         // pairs (k, k | 1 << s); 8 >> s twiddles at heap index (8 >> s) + (k >> (s + 1))
         if (LAST && s == 3) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) ar.bf_inv_last(v[k], v[k | 8], 0);
+            for (int k = 0; k < 8; k++) ar.bf_inv_last(v[k], v[k | 8], LB + 3);
         } else {
-            double w[8];
 #pragma unroll
-            for (int a = 0; a < 8; a++) if (a < (8 >> s)) w[a] = ldsd(T + 8 * ((8 >> s) + a), tok);
+            for (int a = 0; a < 8; a++) if (a < (8 >> s)) {
+                const typename AR::TwT w = tw.uni((8 >> s) + a);
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-                if (k & (1 << s)) continue;
-                ar.bf_inv(v[k], v[k | (1 << s)], w[k >> (s + 1)], 0);
+                for (int k = 0; k < 16; k++) if (!(k & (1 << s)) && (k >> (s + 1)) == a) ar.bf_inv(v[k], v[k | (1 << s)], w, LB + s);
             }
         }
     }
+}
+// layers with per-thread twiddles.  Loads are staged (each layer's twiddles are requested while the previous layer computes,
+// the eight-twiddle layer in two halves) so that the kernel fits 72 registers on both arithmetic paths.
+template <class AR, class TW>
+__device__ __forceinline__ void n5_fwd_thread(const AR &ar, typename AR::T (&v)[16], const TW &tw) {
+    typedef typename AR::TwT W;
+    const W w1 = tw.one();
+    W w2[2]; tw.template layer<5, 0, 2>(w2);
+#pragma unroll
+    for (int k = 0; k < 8; k++) ar.bf_fwd(v[k], v[k | 8], w1);
+    W w4[4]; tw.template layer<6, 0, 4>(w4);
+#pragma unroll
+    for (int k = 0; k < 16; k++) if (!(k & 4)) ar.bf_fwd(v[k], v[k | 4], w2[k >> 3]);
+    W wa[4]; tw.template layer<7, 0, 4>(wa);
+#pragma unroll
+    for (int k = 0; k < 16; k++) if (!(k & 2)) ar.bf_fwd(v[k], v[k | 2], w4[k >> 2]);
+    W wb[4]; tw.template layer<7, 4, 4>(wb);
+#pragma unroll
+    for (int k = 0; k < 8; k++) if (!(k & 1)) ar.bf_fwd(v[k], v[k | 1], wa[k >> 1]);
+#pragma unroll
+    for (int k = 8; k < 16; k++) if (!(k & 1)) ar.bf_fwd(v[k], v[k | 1], wb[(k >> 1) - 4]);
+}
+// wa: entries 0..3 of the first layer's eight twiddles, requested by the caller before it reads the data
+template <int LB, class AR, class TW>
+__device__ __forceinline__ void n5_inv_thread(const AR &ar, typename AR::T (&v)[16], const TW &tw, const typename AR::TwT (&wa)[4]) {
+    typedef typename AR::TwT W;
+    W wb[4]; tw.template layer<7, 4, 4>(wb);
+#pragma unroll
+    for (int k = 0; k < 8; k++) if (!(k & 1)) ar.bf_inv(v[k], v[k | 1], wa[k >> 1], LB);
+    W w4[4]; tw.template layer<6, 0, 4>(w4);
+#pragma unroll
+    for (int k = 8; k < 16; k++) if (!(k & 1)) ar.bf_inv(v[k], v[k | 1], wb[(k >> 1) - 4], LB);
+    W w2[2]; tw.template layer<5, 0, 2>(w2);
+    const W w1 = tw.one();
+#pragma unroll
+    for (int k = 0; k < 16; k++) if (!(k & 2)) ar.bf_inv(v[k], v[k | 2], w4[k >> 2], LB + 1);
+#pragma unroll
+    for (int k = 0; k < 16; k++) if (!(k & 4)) ar.bf_inv(v[k], v[k | 4], w2[k >> 3], LB + 2);
+#pragma unroll
+    for (int k = 0; k < 8; k++) ar.bf_inv(v[k], v[k | 8], w1, LB + 3);
 }
 
 // ---- the four pass bodies (byte offsets into the stage buffer; see the header comment and DESIGN.md §4.1) ------------------
@@ -223,31 +253,34 @@ __device__ __forceinline__ N5Lane n5_lane() {
 #define N5_ST64(off, val) sts64(stage + (off), (val))
 
 // forward, first pass: column tile (natural layout in, (col, row_hi, row_lo) layout out), external words in
-template <class XF>
-__device__ __forceinline__ void n5_fwd_col(u32 stage, u32 T, const ArithF64 &ar, const N5Lane &L, const XF &xf, u32 tok) {
-    double v[16];
+template <class AR, class XF>
+__device__ __forceinline__ void n5_fwd_col(u32 stage, u32 T, const AR &ar, const N5Lane &L, const XF &xf, u32 tok) {
+    typename AR::T v[16];
+    const N5Shared<typename AR::TwT> tw(T, L.xc, tok);
 #pragma unroll
     for (int k = 0; k < 16; k++) v[k] = ar.from_ext(xf(N5_LD64(L.base0 + k * 2048)));
-    n5_fwd_uniform(ar, v, T, tok);
+    n5_fwd_uniform(ar, v, tw);
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < 16; k++) N5_ST64((L.pbw ^ ((k & 7) * 144)) + k * 2048, ar.to_raw(v[k]));
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < 16; k++) v[k] = ar.from_raw(N5_LD64((L.pbr ^ ((k & 7) * 144)) + (k >> 3) * 1024));
-    n5_fwd_thread(ar, v, N5TwShared(T, (int)L.xc, tok));
+    n5_fwd_thread(ar, v, tw);
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < 16; k++) N5_ST64(L.base0 + k * 2048, ar.to_raw(v[k]));
 }
-// forward, second pass: row tile, canonical words out.  Tu: the rows' 16 register-indexed twiddles (shared memory, 16 doubles
+// forward, second pass: row tile, canonical words out.  Tu: the rows' 16 register-indexed twiddles (shared memory, 16 entries
 // per row); Tg: the rows' full 256-entry tables in global memory
-__device__ __forceinline__ void n5_fwd_row(u32 stage, u32 Tu, const double *Tg, const ArithF64 &ar, const N5Lane &L, u32 tok) {
-    const u32 T = Tu + L.row * 128;
-    double v[16];
+template <class AR>
+__device__ __forceinline__ void n5_fwd_row(u32 stage, u32 Tu, const void *Tg, const AR &ar, const N5Lane &L, u32 tok) {
+    typedef typename AR::TwT W;
+    const N5Shared<W> twu(Tu + L.row * 16 * (u32)sizeof(W), 0, tok);
+    typename AR::T v[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) v[k] = ar.from_raw(N5_LD64((L.q0 ^ ((k & 7) << 4)) + k * 128));
-    n5_fwd_uniform(ar, v, T, tok);
+    n5_fwd_uniform(ar, v, twu);
 #pragma unroll
     for (int k = 0; k < 16; k++) N5_ST64((L.q0 ^ ((k & 7) << 4)) + k * 128, ar.to_raw(v[k]));
     __syncwarp();
@@ -256,45 +289,46 @@ __device__ __forceinline__ void n5_fwd_row(u32 stage, u32 Tu, const double *Tg, 
         const ulonglong2 d = lds128(stage + (L.q1 ^ (j << 4)));
         v[2 * j] = ar.from_raw(d.x); v[2 * j + 1] = ar.from_raw(d.y);
     }
-    n5_fwd_thread(ar, v, N5TwGlobal(Tg + L.row * 256, (int)L.xr));
+    n5_fwd_thread(ar, v, N5Global<W>(reinterpret_cast<const W *>(Tg) + L.row * 256, L.xr));
 #pragma unroll
     for (int j = 0; j < 8; j++) sts128(stage + (L.q1 ^ (j << 4)), ar.final_fwd(v[2 * j]), ar.final_fwd(v[2 * j + 1]));
 }
-// inverse, first pass: row tile, external words in
-template <class XF>
-__device__ __forceinline__ void n5_inv_row(u32 stage, u32 Tu, const double *Tg, const ArithF64 &ar, const N5Lane &L, const XF &xf, u32 tok) {
-    const u32 T = Tu + L.row * 128;
-    double v[16];
+// inverse, first pass: row tile, external words in (layers 0..7 of the inverse transform)
+template <class AR, class XF>
+__device__ __forceinline__ void n5_inv_row(u32 stage, u32 Tu, const void *Tg, const AR &ar, const N5Lane &L, const XF &xf, u32 tok) {
+    typedef typename AR::TwT W;
+    const N5Shared<W> twu(Tu + L.row * 16 * (u32)sizeof(W), 0, tok);
+    typename AR::T v[16];
     {
-        const N5TwGlobal tw(Tg + L.row * 256, (int)L.xr);
-        double w8[8];
-        n5_load_w8(tw, w8);
+        const N5Global<W> tw(reinterpret_cast<const W *>(Tg) + L.row * 256, L.xr);
+        W wa[4]; tw.template layer<7, 0, 4>(wa);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const ulonglong2 d = lds128(stage + (L.q1 ^ (j << 4)));
             v[2 * j] = ar.from_ext(xf(d.x)); v[2 * j + 1] = ar.from_ext(xf(d.y));
         }
-        n5_inv_thread(ar, v, tw, w8);
+        n5_inv_thread<0>(ar, v, tw, wa);
     }
 #pragma unroll
     for (int j = 0; j < 8; j++) sts128(stage + (L.q1 ^ (j << 4)), ar.to_raw(v[2 * j]), ar.to_raw(v[2 * j + 1]));
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < 16; k++) v[k] = ar.from_raw(N5_LD64((L.q0 ^ ((k & 7) << 4)) + k * 128));
-    n5_inv_uniform<false>(ar, v, T, tok);
+    n5_inv_uniform<false, 4>(ar, v, twu);
 #pragma unroll
     for (int k = 0; k < 16; k++) { ar.pass_boundary_inv(v[k]); N5_ST64((L.q0 ^ ((k & 7) << 4)) + k * 128, ar.to_raw(v[k])); }
 }
-// inverse, second pass: column tile ((col, row_hi, row_lo) layout in, natural layout out), canonical words out
-__device__ __forceinline__ void n5_inv_col(u32 stage, u32 T, const ArithF64 &ar, const N5Lane &L, u32 tok) {
-    double v[16];
+// inverse, second pass: column tile ((col, row_hi, row_lo) layout in, natural layout out), canonical words out (layers 8..15)
+template <class AR>
+__device__ __forceinline__ void n5_inv_col(u32 stage, u32 T, const AR &ar, const N5Lane &L, u32 tok) {
+    typedef typename AR::TwT W;
+    typename AR::T v[16];
+    const N5Shared<W> tw(T, L.xc, tok);
     {
-        const N5TwShared tw(T, (int)L.xc, tok);
-        double w8[8];
-        n5_load_w8(tw, w8);
+        W wa[4]; tw.template layer<7, 0, 4>(wa);
 #pragma unroll
         for (int k = 0; k < 16; k++) v[k] = ar.from_raw(N5_LD64(L.base0 + k * 2048));
-        n5_inv_thread(ar, v, tw, w8);
+        n5_inv_thread<8>(ar, v, tw, wa);
     }
     __syncwarp();
 #pragma unroll
@@ -302,7 +336,7 @@ __device__ __forceinline__ void n5_inv_col(u32 stage, u32 T, const ArithF64 &ar,
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < 16; k++) v[k] = ar.from_raw(N5_LD64((L.pbw ^ ((k & 7) * 144)) + k * 2048));
-    n5_inv_uniform<true>(ar, v, T, tok);
+    n5_inv_uniform<true, 12>(ar, v, tw);
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < 16; k++) N5_ST64(L.base0 + k * 2048, ar.final_inv(v[k]));
@@ -372,16 +406,25 @@ __global__ void __launch_bounds__(N5_THREADS, 3) ntt5_kernel(const __grid_consta
             u32 g, c;
             limb_of(it, g, c);
             const ModInfo &M = J.mods[group_table(J.groups[g].table)];
-            const ArithF64 ar(M);
+            const u32 path = group_path(J.groups[g].table, FWD);
             const u32 stage = stage0 + s * N5_STAGE_BYTES, tw = tw0 + s * N5_TW_BYTES;
+            const void *rowtab = FWD ? M.n5_frow : M.n5_irow;
+            const bool first = it.phase == 0;
+            auto run = [&](const auto &ar) {
+                typedef typename std::remove_reference<decltype(ar)>::type AR;
+                const size_t rt = (size_t)it.tile * 4096 * sizeof(typename AR::TwT);
+                if (FWD) {
+                    if (first) { const auto pp = pro.prep(J.g_base + (int)g, (int)c); n5_fwd_col(stage, tw, ar, L, pro.fn(pp), cur_id); }
+                    else n5_fwd_row(stage, tw, reinterpret_cast<const char *>(rowtab) + rt, ar, L, cur_id);
+                } else {
+                    if (first) { const auto pp = pro.prep(J.g_base + (int)g, (int)c); n5_inv_row(stage, tw, reinterpret_cast<const char *>(rowtab) + rt, ar, L, pro.fn(pp), cur_id); }
+                    else n5_inv_col(stage, tw, ar, L, cur_id);
+                }
+            };
             if (J.dbg & 1) {}
-            else if (FWD) {
-                if (it.phase == 0) { const auto pp = pro.prep(J.g_base + (int)g, (int)c); n5_fwd_col(stage, tw, ar, L, pro.fn(pp), cur_id); }
-                else n5_fwd_row(stage, tw, M.n5_frow + (size_t)it.tile * 4096, ar, L, cur_id);
-            } else {
-                if (it.phase == 0) { const auto pp = pro.prep(J.g_base + (int)g, (int)c); n5_inv_row(stage, tw, M.n5_irow + (size_t)it.tile * 4096, ar, L, pro.fn(pp), cur_id); }
-                else n5_inv_col(stage, tw, ar, L, cur_id);
-            }
+            else if (path == PATH_F64) run(ArithF64(M));
+            else if (path == PATH_INT_LAZY) run(ArithInt<true>(M));
+            else run(ArithInt<false>(M));
             fence_proxy_async_smem();     // this thread's shared-memory writes -> visible to the copy engine
             __syncwarp();
             if ((t & 31) == 0) mbar_arrive(&s_empty[s]);
@@ -397,22 +440,25 @@ __global__ void __launch_bounds__(N5_THREADS, 3) ntt5_kernel(const __grid_consta
             const ModInfo &M = J.mods[group_table(J.groups[g].table)];
             const u32 stage = stage0 + s * N5_STAGE_BYTES, tw = tw0 + s * N5_TW_BYTES;
             u64 *bar = &s_full[s];
-            mbar_expect_tx(bar, (u32)N5_STAGE_BYTES + (u32)N5_TW_BYTES);
+            const u32 twb = group_path(J.groups[g].table, FWD) == PATH_F64 ? 2048u : 4096u;      // 256 staged twiddles of 8 or 16 bytes
+            mbar_expect_tx(bar, (u32)N5_STAGE_BYTES + twb);
+            const char *colt = reinterpret_cast<const char *>(FWD ? M.n5_fcol : M.n5_icol);
+            const char *rowu = reinterpret_cast<const char *>(FWD ? M.n5_frow_u : M.n5_irow_u) + (size_t)it.tile * twb;
             if (FWD) {
                 if (it.phase == 0) {
                     tma_load_3d(stage, &MP.first, bar, (int)(it.tile * 16), 0, (int)pro.src_limb(J.g_base + (int)g, (int)c, limb));
-                    bulk_load(tw, M.n5_fcol, N5_TW_BYTES, bar);
+                    bulk_load(tw, colt, twb, bar);
                 } else {
                     tma_load_2d(stage, &MP.mid_ld, bar, 0, (int)(limb * 4096 + it.tile * 256));
-                    bulk_load(tw, M.n5_frow_u + (size_t)it.tile * 256, N5_TW_BYTES, bar);
+                    bulk_load(tw, rowu, twb, bar);
                 }
             } else {
                 if (it.phase == 0) {
                     tma_load_2d(stage, &MP.first, bar, 0, (int)(pro.src_limb(J.g_base + (int)g, (int)c, limb) * 4096 + it.tile * 256));
-                    bulk_load(tw, M.n5_irow_u + (size_t)it.tile * 256, N5_TW_BYTES, bar);
+                    bulk_load(tw, rowu, twb, bar);
                 } else {
                     tma_load_4d(stage, &MP.mid_ld, bar, (int)(it.tile * 16), 0, 0, (int)limb);
-                    bulk_load(tw, M.n5_icol, N5_TW_BYTES, bar);
+                    bulk_load(tw, colt, twb, bar);
                 }
             }
         };

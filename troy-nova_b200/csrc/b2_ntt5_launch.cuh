@@ -45,7 +45,7 @@ static inline bool n5_enabled() {
     return on && n5_encoder() != nullptr;
 }
 
-// All `groups` must be FP64-path moduli of an N = 2^16 context, with element offsets that are multiples of N; `dst` holds the
+// All `groups` must be moduli of an N = 2^16 context (either arithmetic path), with element offsets that are multiples of N; `dst` holds the
 // intermediate and the result, `src` the operand (`src_limbs` limbs; the prologue functor names the source limb of each limb).
 template <bool FWD, class Pro>
 static b2_status run_ntt5(b2_ctx *ctx, b2_scratch *sc, const std::vector<LimbGroup> &groups, const u64 *src, size_t src_limbs, u64 *dst, Pro pro, cudaStream_t stream) {
@@ -79,7 +79,12 @@ static b2_status run_ntt5(b2_ctx *ctx, b2_scratch *sc, const std::vector<LimbGro
     for (size_t g0 = 0; g0 < groups.size(); g0 += NTT_MAX_GROUPS) {
         const size_t ng = std::min(groups.size() - g0, (size_t)NTT_MAX_GROUPS);
         P.g_base = (int)g0; P.n_groups = (int)ng;
-        for (size_t g = 0; g < ng; g++) P.groups[g] = groups[g0 + g];
+        for (size_t g = 0; g < ng; g++) {
+            P.groups[g] = groups[g0 + g];
+            const ModInfo &M = ctx->h_mods[groups[g0 + g].table];
+            P.groups[g].table = tag_table(groups[g0 + g].table, M.use_f64 ? PATH_F64 : (M.fwd_lazy ? PATH_INT_LAZY : PATH_INT),
+                                          M.use_f64 ? PATH_F64 : (M.inv_lazy ? PATH_INT_LAZY : PATH_INT));
+        }
         P.n_limbs = (u32)(ng * P.count);
         // claimed-but-unfinished items: 3 CTAs x 2 stages + 1 claim ahead per CTA, ~1350 items = 42 limbs; a lag of 96 limbs keeps a
         // second-pass item from being claimed while first-pass tiles of its limb are still in that window (48 MiB of intermediate
@@ -101,11 +106,46 @@ static b2_status run_ntt5(b2_ctx *ctx, b2_scratch *sc, const std::vector<LimbGro
 // (b2_ntt.cuh).  Plain operands only (src + off / dst + off addressing).
 template <bool FWD>
 static b2_status run_ntt_split(b2_ctx *ctx, b2_scratch *sc, const std::vector<LimbGroup> &groups, const u64 *src, u64 *dst, size_t total_limbs, cudaStream_t stream) {
+    // developer switch for the mixed-path experiments (profiles/r02_ntt5_experiments.txt): 0 everything on the TMA kernel,
+    // 1 / 2 integer-path limbs on the cp.async kernel next to it (capped at SMs/2 / SMs CTAs), 3 the same, one after the other
+    static const int mix = [] { const char *e = getenv("B2_NTT5_MIX"); return e ? atoi(e) : -1; }();
+    if (mix < 0) {
+        // Default, by measurement on B200 (profiles/r02_ntt5_experiments.txt): launches whose limbs are all FP64-path take the TMA
+        // kernel (380 limbs 168 us, 3800 limbs 1484 us vs 1542 us); a launch that also has integer-path (60-bit) limbs is still
+        // served fastest by the cp.async kernel, whose CTAs overlap the two pipes (420 limbs: 208 us vs 218 us all-TMA, 224-231 us split)
+        bool pure = true;
+        for (const LimbGroup &g : groups) pure = pure && ctx->h_mods[g.table].use_f64 && ctx->h_mods[g.table].n5_frow && g.base % ctx->n == 0 && g.stride % ctx->n == 0;
+        if (pure) return run_ntt5<FWD>(ctx, sc, groups, src, total_limbs, dst, N5Identity{}, stream);
+        return run_ntt_dir<FWD>(ctx, sc, groups, dst, PlainLoad{src}, PlainStore{dst}, stream);
+    }
     std::vector<LimbGroup> f64, rest;
-    for (const LimbGroup &g : groups) (ctx->h_mods[g.table].n5_frow && g.base % ctx->n == 0 && g.stride % ctx->n == 0 ? f64 : rest).push_back(g);
+    for (const LimbGroup &g : groups) {
+        const bool ok = ctx->h_mods[g.table].n5_frow && g.base % ctx->n == 0 && g.stride % ctx->n == 0 && (mix == 0 || ctx->h_mods[g.table].use_f64);
+        (ok ? f64 : rest).push_back(g);
+    }
     b2_status st = B2_OK;
-    if (!rest.empty()) st = run_ntt_dir<FWD>(ctx, sc, rest, dst, PlainLoad{src}, PlainStore{dst}, stream);
-    if (st == B2_OK && !f64.empty()) st = run_ntt5<FWD>(ctx, sc, f64, src, total_limbs, dst, N5Identity{}, stream);
+    if (rest.empty()) return run_ntt5<FWD>(ctx, sc, f64, src, total_limbs, dst, N5Identity{}, stream);
+    if (f64.empty()) return run_ntt_dir<FWD>(ctx, sc, rest, dst, PlainLoad{src}, PlainStore{dst}, stream);
+    // Both kinds: the few integer-pipe limbs run NEXT TO the TMA kernel instead of after it — a capped grid of the persistent
+    // kernel on a high-priority side stream (one CTA on every second SM: 20 k registers + 64 KiB, which still leaves room for two
+    // CTAs of the TMA kernel there and three elsewhere).  The two kernels use different pipes (integer vs FP64) and touch
+    // disjoint limbs; each has its own work queue.
+    size_t rest_limbs = 0;
+    for (const LimbGroup &g : rest) rest_limbs += g.count;
+    st = ensure_side(sc, rest_limbs, stream);
+    if (st != B2_OK) return st;
+    B2_CUDA(cudaEventRecord(sc->ev_fork, stream));
+    B2_CUDA(cudaStreamWaitEvent(sc->s_side, sc->ev_fork, 0));
+    if (mix == 3) {
+        st = run_ntt_dir<FWD>(ctx, sc, rest, dst, PlainLoad{src}, PlainStore{dst}, stream);
+        return st != B2_OK ? st : run_ntt5<FWD>(ctx, sc, f64, src, total_limbs, dst, N5Identity{}, stream);
+    }
+    NttScatter side; side.max_ctas = (unsigned)std::max(1, mix == 2 ? ctx->sm_count : ctx->sm_count / 2); side.sync = sc->d_sync2;
+    st = run_ntt_dir<FWD>(ctx, sc, rest, dst, PlainLoad{src}, PlainStore{dst}, sc->s_side, side);
+    if (st != B2_OK) return st;
+    B2_CUDA(cudaEventRecord(sc->ev_join, sc->s_side));
+    st = run_ntt5<FWD>(ctx, sc, f64, src, total_limbs, dst, N5Identity{}, stream);
+    B2_CUDA(cudaStreamWaitEvent(stream, sc->ev_join, 0));
     return st;
 }
 

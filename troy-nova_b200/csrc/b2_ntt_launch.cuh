@@ -109,7 +109,11 @@ static inline unsigned cluster_max_limbs() {
 // groups' base/stride address the intermediate buffer `mid` (raw values between the passes); the
 // functors map (group, limb) to wherever the external operands live.  All groups must have the same count.
 // The direction is a template parameter so that a call site instantiates only the kernels it launches.
-struct NttScatter { const u64 *const *out_tab = nullptr; u32 pc = 0; u64 pstride = 0; };   // see NttJob::out_tab
+struct NttScatter {
+    const u64 *const *out_tab = nullptr; u32 pc = 0; u64 pstride = 0;   // see NttJob::out_tab
+    unsigned max_ctas = 0;      // 0: fill the machine; else cap the persistent grid (a launch that shares the SMs with another kernel)
+    unsigned *sync = nullptr;   // work queue / counters to use instead of the scratch record's (concurrent launches need their own)
+};
 template <bool FWD, class Load, class Store>
 static b2_status run_ntt_dir(b2_ctx *ctx, b2_scratch *sc, const std::vector<LimbGroup> &groups, u64 *mid, Load ld, Store st, cudaStream_t stream,
                              const NttScatter &scatter = NttScatter()) {
@@ -147,7 +151,7 @@ static b2_status run_ntt_dir(b2_ctx *ctx, b2_scratch *sc, const std::vector<Limb
         // 16-CTA clusters are a non-portable size: if this device / partition cannot co-schedule one (the launch is refused
         // synchronously), the persistent kernel below serves small launches too
         static bool cluster_refused[B2_MAX_DEVICES] = {};
-        if (logn == 16 && P.n_limbs <= cluster_max_limbs() && !cluster_refused[ctx->device & (B2_MAX_DEVICES - 1)]) {
+        if (logn == 16 && P.n_limbs <= cluster_max_limbs() && !cluster_refused[ctx->device & (B2_MAX_DEVICES - 1)] && !scatter.max_ctas) {
             P.sync = nullptr; P.lag = 0; P.total_items = 0;
             cudaError_t e = launch_cluster<FWD>(P, ctx->device, stream, ld, st);
             if (e == cudaSuccess) { count_launches(1); continue; }
@@ -156,10 +160,14 @@ static b2_status run_ntt_dir(b2_ctx *ctx, b2_scratch *sc, const std::vector<Limb
         }
         P.lag = std::min<u32>(NTT_LAG, P.n_limbs);
         P.total_items = (P.n_limbs << P.tile_shift) * 2;
-        b2_status s = ensure_sync(sc, P.n_limbs, stream);
-        if (s != B2_OK) return s;
-        P.sync = sc->d_sync;
-        const unsigned grid = std::min<unsigned>(P.total_items, (unsigned)NTT_OCC * (unsigned)ctx->sm_count);
+        if (scatter.sync) P.sync = scatter.sync;
+        else {
+            b2_status s = ensure_sync(sc, P.n_limbs, stream);
+            if (s != B2_OK) return s;
+            P.sync = sc->d_sync;
+        }
+        unsigned grid = std::min<unsigned>(P.total_items, (unsigned)NTT_OCC * (unsigned)ctx->sm_count);
+        if (scatter.max_ctas) grid = std::min(grid, scatter.max_ctas);
         cudaError_t e;
         switch (A) {
         case 4: e = launch_persistent<4, FWD>(P, ctx->device, grid, stream, ld, st); break;
