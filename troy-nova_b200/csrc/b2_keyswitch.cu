@@ -18,7 +18,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
-#include "b2_ntt_launch.cuh"
+#include "b2_ntt5_launch.cuh"
+#include "b2_ks5.cuh"
 #include "b2_fused.cuh"
 
 using namespace b2;
@@ -240,7 +241,48 @@ static b2_status keyswitch_chunk(b2_ctx *ctx, const uint64_t *const *targets, ui
     mark();
     // 2 + 3. mod-up NTT and key inner product, per block of `blk` output moduli (one block by default, see above)
     //   group i = output modulus, limbs c = (b, j); temp[il][b][j], il = i - i0
-    for (size_t i0 = 0; i0 < R; i0 += blk) {
+    // 4. u_{b,k} = INTT_P(prod[b][k][decomp]).  In the one-block case the special prime's inner product is launched first and its
+    //   inverse transform (a few limbs on the cluster kernel: latency-bound, ~30 us) runs on a side stream UNDER the inner
+    //   product of the other moduli instead of after it.
+    static const bool no_overlap = getenv("B2_KS_NO_OVERLAP") != nullptr;      // developer switch for A/B timing
+    // N = 2^16, one ciphertext: steps 2 + 3 as one persistent launch whose temp is an L2-resident ring (b2_ks5.cuh).  Bit-exact, but
+    // measured SLOWER than the two launches on B200 (585 us vs 460 us per C3 keyswitch; the in-order queue stalls on the group
+    // dependencies and L2 still writes 239 MB of the ring back: profiles/r03b_ks5_*), so it is opt-in (B2_KS5=1) until that is solved.
+    static const bool ks5_off = [] { const char *e = getenv("B2_KS5"); return !(e && e[0] == '1'); }();
+    bool fused = false;
+    if (ctx->logn == N5_LOGN && nb == 1 && blk == R && R * decomp >= (size_t)KS5_RING * decomp && R <= (size_t)KS5_MAX_GROUPS && !ks5_off && !timing && n5_enabled() &&
+        (((uintptr_t)coef.p[0]) & 127) == 0) {
+        Ks5Job J;
+        J.mods = ctx->d_mods; J.keys = (const u64 *const *)key->d_ptrs; J.ring = temp; J.prod = prod;
+        J.G = (u32)R; J.C = (u32)decomp; J.K = (u32)K; J.key_rows = (u32)K;
+        J.total_items = (u32)(R * decomp * 32 + R * KS5_IPI);
+        J.f64_lazy = 1;
+        for (size_t i = 0; i < R; i++) {
+            const u32 ti = (u32)(i == decomp ? K - 1 : i);
+            const ModInfo &M = ctx->h_mods[ti];
+            J.table[i] = tag_table(ti, M.use_f64 ? PATH_F64 : (M.fwd_lazy ? PATH_INT_LAZY : PATH_INT), M.use_f64 ? PATH_F64 : (M.inv_lazy ? PATH_INT_LAZY : PATH_INT));
+        }
+        Ks5Maps MP;
+        if (n5_make_map(&MP.tc, N5_NATURAL, coef.p[0], decomp) && n5_make_map(&MP.ring_perm, N5_PERMUTED, temp, KS5_RING * decomp) &&
+            n5_make_map(&MP.ring_rows, N5_ROWS, temp, KS5_RING * decomp)) {
+            st = ensure_sync(sc, R * decomp + 2 * R, stream);
+            if (st != B2_OK) return st;
+            J.sync = sc->d_sync;
+            static bool configured[B2_MAX_DEVICES] = {};
+            if (!configured[ctx->device & (B2_MAX_DEVICES - 1)]) {
+                B2_CUDA(cudaFuncSetAttribute(ks5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, N5_SMEM_BYTES));
+                configured[ctx->device & (B2_MAX_DEVICES - 1)] = true;
+            }
+            const unsigned grid = std::min<unsigned>(J.total_items, 3u * (unsigned)ctx->sm_count);
+            ks5_kernel<<<grid, N5_THREADS, N5_SMEM_BYTES, stream>>>(J, MP);
+            count_launches(1);
+            B2_CUDA(cudaGetLastError());
+            fused = true;
+        }
+    }
+    const bool overlap_special = blk == R && 2 * nb <= cluster_max_limbs() && ctx->logn == 16 && !timing && !no_overlap;
+    bool special_done = false;
+    for (size_t i0 = 0; i0 < R && !fused; i0 += blk) {
         const size_t cnt = std::min(blk, R - i0);
         std::vector<LimbGroup> groups;
         for (size_t il = 0; il < cnt; il++) {
@@ -251,15 +293,40 @@ static b2_status keyswitch_chunk(b2_ctx *ctx, const uint64_t *const *targets, ui
         st = run_ntt_dir<true>(ctx, sc, groups, temp, ld, PlainStore{temp}, stream);
         if (st != B2_OK) return st;
         if (i0 == 0) mark();
-        dim3 grid((unsigned)nb, (unsigned)((n / 2 + 255) / 256), (unsigned)cnt);
+        const unsigned gy = (unsigned)((n / 2 + 255) / 256);
+        if (overlap_special) {
+            st = ensure_side(sc, 0, stream);
+            if (st != B2_OK) return st;
+            // special prime first (row `decomp` of temp and of prod) ...
+            ks_inner_product_kernel<<<dim3((unsigned)nb, gy, 1), 256, 0, stream>>>(temp + decomp * nb * decomp * n, (const u64 *const *)key->d_ptrs, prod, ctx->d_mods,
+                                                                                 (u32)decomp, (u32)K, (u32)n, (u32)decomp, (u32)K, (u32)R, (u32)decomp);
+            B2_CUDA(cudaGetLastError());
+            B2_CUDA(cudaEventRecord(sc->ev_fork, stream));
+            B2_CUDA(cudaStreamWaitEvent(sc->s_side, sc->ev_fork, 0));
+            {   // ... its inverse transform on the side stream ...
+                std::vector<LimbGroup> sg{LimbGroup{(u32)(K - 1), (u32)(2 * nb), 0, (u64)n}};
+                SpecialLoad sld{prod, (u32)R, (u32)decomp, (u32)n};
+                st = run_ntt_dir<false>(ctx, sc, sg, u, sld, PlainStore{u}, sc->s_side);
+                if (st != B2_OK) return st;
+            }
+            B2_CUDA(cudaEventRecord(sc->ev_join, sc->s_side));
+            // ... under the inner product of the ciphertext moduli
+            ks_inner_product_kernel<<<dim3((unsigned)nb, gy, (unsigned)decomp), 256, 0, stream>>>(temp, (const u64 *const *)key->d_ptrs, prod, ctx->d_mods, (u32)decomp, (u32)K, (u32)n,
+                                                                                             0u, (u32)K, (u32)R, 0u);
+            count_launches(2);
+            B2_CUDA(cudaGetLastError());
+            B2_CUDA(cudaStreamWaitEvent(stream, sc->ev_join, 0));
+            special_done = true;
+            continue;
+        }
+        dim3 grid((unsigned)nb, gy, (unsigned)cnt);
         ks_inner_product_kernel<<<grid, 256, 0, stream>>>(temp, (const u64 *const *)key->d_ptrs, prod, ctx->d_mods, (u32)decomp, (u32)K, (u32)n,
                                                           (u32)i0, (u32)K, (u32)R, (u32)i0);
         count_launches(1);
         B2_CUDA(cudaGetLastError());
     }
     mark();
-    // 4. u_{b,k} = INTT_P(prod[b][k][decomp])
-    {
+    if (!special_done) {
         std::vector<LimbGroup> groups{LimbGroup{(u32)(K - 1), (u32)(2 * nb), 0, (u64)n}};
         SpecialLoad ld{prod, (u32)R, (u32)decomp, (u32)n};
         st = run_ntt_dir<false>(ctx, sc, groups, u, ld, PlainStore{u}, stream);
