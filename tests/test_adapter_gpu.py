@@ -1,0 +1,61 @@
+"""The drop-in proof: the UNMODIFIED reference objects linked with integration/b2_adapter.cu
+(ld --wrap on the reference's own L2 seam functions) run the reference's OWN gtest suite on libb2rns.
+
+Every suite below is the reference's test/**/*.cu compiled where it lies; its assertions are the reference's (decrypt(op(enc(x))) ==
+op(x), serialisation round trips, multi-threaded evaluation ...).  The tests pass only if the B200-native kernels are a correct
+replacement behind Evaluator / Encryptor / Decryptor / KeyGenerator / LWE packing / matmul / conv2d; the adapter's counters prove
+that the device calls really went through libb2rns and not through the reference's kernels.
+One reference test (SerializeTest.DeviceCKKSCiphertext) fails on the reference's own device branch too (profiles/r02b_*) and is excluded."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "integration", "_build", "troytest_b2")
+KNOWN_REFERENCE_FAILURE = "SerializeTest.DeviceCKKSCiphertext"
+
+
+def _run(filt, adapter="1", timeout=900):
+    env = dict(os.environ, B2_ADAPTER=adapter, B2_ADAPTER_STATS="1")
+    p = subprocess.run([BIN, "--gtest_filter=%s:-%s" % (filt, KNOWN_REFERENCE_FAILURE), "--gtest_brief=1"], capture_output=True, text=True, env=env, timeout=timeout)
+    out = p.stdout + p.stderr
+    m = re.search(r"\[  PASSED  \] (\d+) tests", out)
+    stats = re.search(r"\[b2_adapter\] ntt (\d+) \(\+(\d+) batched\)\s+keyswitch (\d+) \(\+(\d+) batched\)\s+dyadic (\d+)\s+modswitch (\d+)\s+galois (\d+)\s+bfv_multiply (\d+) \| "
+                      r"device calls left to the reference (\d+)", out)
+    return p.returncode, int(m.group(1)) if m else 0, [int(x) for x in stats.groups()] if stats else None, out
+
+
+needs_bin = pytest.mark.skipif(not os.path.exists(BIN), reason="integration/_build/troytest_b2 not built (python -c 'import __graft_entry__ as g; g.build()')")
+
+
+@needs_bin
+def test_adapter_library_passes_host_tests_untouched():
+    """host operands must reach the reference's own bodies through __real_*: a few host suites, no GPU needed"""
+    rc, passed, stats, out = _run("NTT.*:GaloisToolTest.Host*:EvaluatorTest.HostBFVMultiply*:EvaluatorTest.HostCKKSKeySwitching*:EvaluatorBatchTest.HostBFVRotate*")
+    assert rc == 0 and passed >= 5, out[-2000:]
+    assert stats is not None and sum(stats[:8]) == 0, "host operands must not be routed to libb2rns"
+
+
+@needs_bin
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,filt,need", [
+    # (suite, gtest filter, indices of adapter counters that must be non-zero: 0 ntt 2 keyswitch 3 keyswitch_batched 4 dyadic 5 modswitch 6 galois 7 bfv_multiply)
+    ("evaluator", "EvaluatorTest.Device*", [0, 2, 4, 5, 6, 7]),
+    ("evaluator_batched", "EvaluatorBatchTest.Device*", [0, 1, 3, 4]),
+    ("encryptor_decryptor_keygen", "EncryptorTest.Device*:EncryptorBatchTest.Device*:SpecialPrimeForEncryptionTest.Device*", [0]),
+    ("lwe_packing", "LweTest.Device*", [0, 3, 6]),
+    ("bumblebee_matmul_cheetah_conv2d", "MatmulTest.Device*:Conv2dTest.Device*:BFVRing2kTest.Device*", [0, 4]),
+    ("encoders_serialisation_context", "BatchEncoderTest.Device*:BatchEncoderBatchTest.Device*:CKKSEncoderTest.Device*:SerializeTest.Device*:HeContextTest.Device*", []),
+    ("multithread", "MultithreadTest.*", [0]),
+    ("utils_device", "NTT.Device*:RNSToolTest.Device*:GaloisToolTest.Device*:RNSBase.Device*", []),
+])
+def test_reference_suite_on_libb2rns(name, filt, need):
+    rc, passed, stats, out = _run(filt)
+    assert rc == 0, "%s: reference tests failed on libb2rns\n%s" % (name, out[-3000:])
+    assert passed > 0, "%s: no test ran\n%s" % (name, out[-1000:])
+    assert stats is not None, out[-1000:]
+    for i in need:
+        assert stats[i] > 0, "%s: adapter counter %d is zero — the suite did not exercise libb2rns (%s)" % (name, i, stats)
+    assert stats[8] == 0, "%s: %d device calls fell through to the reference's kernels" % (name, stats[8])
