@@ -413,6 +413,7 @@ def main():
         e2e["host_link_duplex_gbs_per_direction"] = None; e2e["host_link_note"] = str(ex)[:80]
 
     # ---- relinearize / rotate ops/s on the same parameter set (keyswitch core, data resident): top-level blocks of the line
+    limb_sharded = None
     extra = {}
     ksblocks = {}
     if not args.no_extra:
@@ -548,6 +549,36 @@ def main():
             extra["relinearize_limb_sharded_ops_per_s"] = k / s
             extra["relinearize_limb_sharded_speedup_vs_1gpu"] = extra["relinearize_us"] / (s / k * 1e6)
             extra["relinearize_limb_sharded_bit_exact"] = bool(max_over_ranks(1.0 - ok) == 0.0)
+            # the same keyswitch with the P2P data plane: pushes over NVLink into the peers' symmetric buffers + flags, weighted partition
+            try:
+                ex = sh.P2PExchange.from_symmetric_memory(L, n)
+                kp = sh.P2PLimbShardedKeyswitch(ctx, L, ex)
+                f2, c2, nct2 = kp.first, kp.count, kp.nct
+                shard2 = ctx.kswitch_key_shard(kh, L, f2, c2) if c2 else None
+                tl2 = cts[2, f2:f2 + nct2].contiguous() if nct2 else torch.zeros(2, dtype=torch.int64, device="cuda")
+                dl20 = cts[:2, f2:f2 + nct2].contiguous() if nct2 else torch.zeros(2, dtype=torch.int64, device="cuda")
+                dl2 = dl20.clone()
+
+                def relin_p2p():
+                    dl2.copy_(dl20)
+                    kp(tl2, True, shard2, dl2, b2.ASSIGN_ADD_INPLACE)
+                relin_p2p()
+                ok2 = 1 if (nct2 == 0 or torch.equal(dl2, want[:, f2:f2 + nct2])) else 0
+                for _ in range(3):
+                    relin_p2p()
+                barrier()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(k):
+                    relin_p2p()
+                a1.record(); barrier()
+                s2 = max_over_ranks(a0.elapsed_time(a1) * 1e-3)
+                limb_sharded = {"relinearize_us": s2 / k * 1e6, "ops_per_s": k / s2, "speedup_vs_1gpu": extra["relinearize_us"] / (s2 / k * 1e6),
+                                "bit_exact_vs_single_gpu": bool(max_over_ranks(1.0 - ok2) == 0.0), "scaling": "strong (one keyswitch cut over all GPUs by RNS limb)",
+                                "data_plane": "P2P pushes into the peers' symmetric buffers + system-scope flags (b2_shard_push / b2_shard_wait), no collective call",
+                                "partition": [p[1] for p in kp.parts], "nccl_path_us": s / k * 1e6}
+            except Exception as ex_:        # symmetric memory unavailable: the NCCL path above stands
+                limb_sharded = {"error": str(ex_)[:200], "nccl_path_us": s / k * 1e6}
             extra["limb_partition"] = [sh.partition(L + 1, world, r)[1] for r in range(world)]
 
     cpu = None
@@ -583,7 +614,7 @@ def main():
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
                 "clocks": sampler.summary() if sampler else None,
                 "relinearize": ksblocks.get("relinearize") if not args.no_extra else None, "rotate": ksblocks.get("rotate") if not args.no_extra else None,
-                "gpu_baseline": gpu_base, "extra": extra}
+                "gpu_baseline": gpu_base, "limb_sharded_keyswitch": limb_sharded, "extra": extra}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -141,6 +141,15 @@ b2_status b2_keyswitch_batched(b2_ctx *ctx, const uint64_t *const *targets, uint
  * ciphertext limbs ([poly][owned limbs][N]) and key rows.  Per keyswitch: prepare -> all-gather (caller, NCCL) ->
  * products -> broadcast of u from the special prime's owner (caller) -> finish.  Bit-identical to b2_keyswitch. */
 b2_status b2_limb_partition(size_t n_out_moduli, int world, int rank, size_t *first, size_t *count);
+/* partition weighted by modulus cost (integer-pipe moduli count double, the special prime's owner once more): contiguous ranges */
+b2_status b2_limb_partition_weighted(const b2_ctx *ctx, size_t decomp, int world, int rank, size_t *first, size_t *count);
+/* P2P exchange for the limb-sharded keyswitch (peer buffers mapped by the caller: symmetric memory / CUDA IPC; HOST arrays of `world`
+ * DEVICE pointers): push copies `words` (even) u64 from src to peer_dst[r] for every r, then stores `epoch` into peer_flags[r][flag_slot]
+ * with system-scope release; wait spins (on the device, stream-ordered) until flags[slots[i]] >= epoch for every i.
+ * b2_keyswitch_shard_products with world == 0 takes `gathered` as the complete coefficient-form target [decomp][N]. */
+b2_status b2_shard_push(b2_ctx *ctx, const uint64_t *src, uint64_t *const *peer_dst, int world, size_t words, uint64_t *const *peer_flags, size_t flag_slot,
+                        uint64_t epoch, void *stream);
+b2_status b2_shard_wait(b2_ctx *ctx, const uint64_t *flags, const int *slots, int n_slots, uint64_t epoch, void *stream);
 b2_status b2_kswitch_key_shard(b2_ctx *ctx, const b2_kswitch_key *full, size_t decomp, size_t first, size_t count, b2_kswitch_key **out);
 b2_status b2_keyswitch_shard_prepare(b2_ctx *ctx, const uint64_t *target_local /* [owned ct limbs][N] */, size_t decomp, int is_ntt,
                                      size_t first, size_t count, uint64_t *send /* [pad][N] */, void *stream);

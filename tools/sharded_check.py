@@ -62,6 +62,36 @@ if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
     print("sharded relinearize: world=%d N=2^%d L=%d  bit-exact vs single-GPU: %s   %.1f us per op (max over ranks)  owned moduli %s"
           % (world, log_n, L, "YES" if int(ok.item()) == 1 else "NO", float(t.item()), [sh.partition(L + 1, world, r)[1] for r in range(world)]), flush=True)
+# ---- the same keyswitch with the P2P data plane (b2_shard_push / b2_shard_wait over symmetric memory, weighted partition)
+ok2 = torch.tensor([1], device="cuda")
+if world > 1:
+    kfull = ctx.kswitch_key(key)
+    ex = sh.P2PExchange.from_symmetric_memory(L, n)
+    kp = sh.P2PLimbShardedKeyswitch(ctx, L, ex)
+    f, c, nct = kp.first, kp.count, kp.nct
+    shard2 = ctx.kswitch_key_shard(kfull, L, f, c) if c else None
+    del kfull
+    tl2 = ct[2, f:f + nct].contiguous() if nct else torch.zeros(2, dtype=torch.int64, device="cuda")
+    dl20 = ct[:2, f:f + nct].contiguous() if nct else torch.zeros(2, dtype=torch.int64, device="cuda")
+    dl2 = dl20.clone()
+    kp(tl2, True, shard2, dl2, b2.ASSIGN_ADD_INPLACE)
+    torch.cuda.synchronize()
+    ok2 = torch.tensor([1 if (nct == 0 or torch.equal(dl2, want[:, f:f + nct])) else 0], device="cuda")
+    dist.all_reduce(ok2, op=dist.ReduceOp.MIN)
+    def run2():
+        dl2.copy_(dl20)
+        kp(tl2, True, shard2, dl2, b2.ASSIGN_ADD_INPLACE)
+    for _ in range(5): run2()
+    dist.barrier(); torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters): run2()
+    e1.record(); torch.cuda.synchronize()
+    t2 = torch.tensor([e0.elapsed_time(e1) / iters * 1e3], device="cuda")
+    dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print("P2P sharded relinearize: world=%d  bit-exact: %s   %.1f us per op (max over ranks)  owned moduli %s (weighted)"
+              % (world, "YES" if int(ok2.item()) == 1 else "NO", float(t2.item()), [p[1] for p in kp.parts]), flush=True)
+    dist.barrier()
 if world > 1:
     dist.destroy_process_group()
-sys.exit(0 if int(ok.item()) == 1 else 1)
+sys.exit(0 if int(ok.item()) == 1 and int(ok2.item()) == 1 else 1)

@@ -69,6 +69,9 @@ _SIGS.update({
     "b2_keyswitch_host": (C.c_int, [vp, vp, C.c_size_t, C.c_int, vp, vp, C.c_int, vp]),
     "b2_keyswitch_batched": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.c_size_t, C.c_size_t, C.c_int, vp, C.c_int, vp]),
     "b2_limb_partition": (C.c_int, [C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "b2_limb_partition_weighted": (C.c_int, [vp, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "b2_shard_push": (C.c_int, [vp, vp, C.POINTER(vp), C.c_int, C.c_size_t, C.POINTER(vp), C.c_size_t, C.c_uint64, vp]),
+    "b2_shard_wait": (C.c_int, [vp, vp, C.POINTER(C.c_int), C.c_int, C.c_uint64, vp]),
     "b2_kswitch_key_shard": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(vp)]),
     "b2_keyswitch_shard_prepare": (C.c_int, [vp, vp, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t, vp, vp]),
     "b2_keyswitch_shard_products": (C.c_int, [vp, vp, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, vp, vp, vp]),
@@ -238,6 +241,21 @@ class Context:
         h = vp()
         _chk(self.L.b2_kswitch_key_shard(self.h, full_key.h, decomp, first, count, C.byref(h)))
         return KSwitchKey(self, h, None)
+
+    def limb_partition_weighted(self, decomp, world, rank):
+        f, c = C.c_size_t(), C.c_size_t()
+        _chk(self.L.b2_limb_partition_weighted(self.h, decomp, world, rank, C.byref(f), C.byref(c)))
+        return int(f.value), int(c.value)
+
+    def shard_push(self, src, peer_dst, words, peer_flags, flag_slot, epoch, stream=None):
+        """copy `words` u64 from src into every peer's buffer (raw device pointers), then raise flag `flag_slot` to `epoch` on every peer"""
+        w = len(peer_dst)
+        dp = (vp * w)(*[_dptr(p) for p in peer_dst]); fp = (vp * w)(*[_dptr(p) for p in peer_flags])
+        _chk(self.L.b2_shard_push(self.h, _dptr(src), dp, w, words, fp, flag_slot, epoch, self._stream(stream)))
+
+    def shard_wait(self, flags, slots, epoch, stream=None):
+        arr = (C.c_int * len(slots))(*slots)
+        _chk(self.L.b2_shard_wait(self.h, _dptr(flags), arr, len(slots), epoch, self._stream(stream)))
 
     def keyswitch_shard_prepare(self, target_local, decomp, is_ntt, first, count, send, stream=None):
         _chk(self.L.b2_keyswitch_shard_prepare(self.h, _dptr(target_local), decomp, int(is_ntt), first, count, _dptr(send), self._stream(stream)))

@@ -104,8 +104,9 @@ b2_status ensure_sync(b2_scratch *sc, size_t limbs, cudaStream_t stream) {
     if (sc->d_sync && sc->sync_limbs >= limbs) return B2_OK;
     if (sc->d_sync) { B2_CUDA(cudaStreamSynchronize(stream)); B2_CUDA(cudaFree(sc->d_sync)); sc->d_sync = nullptr; sc->sync_limbs = 0; }
     const size_t want = std::max<size_t>(limbs * 2, 4096);
-    B2_CUDA(cudaMalloc((void **)&sc->d_sync, (want + 2) * sizeof(unsigned)));
-    B2_CUDA(cudaMemsetAsync(sc->d_sync, 0, (want + 2) * sizeof(unsigned), stream));
+    // + 2 queue words in front, + 2 spare words behind (the last one is the block counter of b2_shard_push)
+    B2_CUDA(cudaMalloc((void **)&sc->d_sync, (want + 4) * sizeof(unsigned)));
+    B2_CUDA(cudaMemsetAsync(sc->d_sync, 0, (want + 4) * sizeof(unsigned), stream));
     sc->sync_limbs = want;
     return B2_OK;
 }

@@ -124,6 +124,47 @@ __global__ void __launch_bounds__(256) ks_compact_gathered_kernel(const u64 *__r
     for (u32 x = blockIdx.x * blockDim.x + threadIdx.x; x < n / 2; x += gridDim.x * blockDim.x) dst[x] = src[x];
 }
 
+// ---- P2P data plane of the limb-sharded keyswitch -------------------------------------------------------------------------
+// The peers' buffers are mapped into this process (symmetric memory / CUDA IPC): a rank PUSHES its part of an exchange into
+// every peer's buffer with plain stores over NVLink and then raises its flag in every peer's flag array; the consumer side
+// spins on its local flags.  No collective call, no staging copy, no compaction: the exchange is two small kernels ordered on
+// the compute stream (reference has no counterpart: it replicates whole contexts per device).
+constexpr int SHARD_MAX_WORLD = 16;
+struct PeerTab { u64 *p[SHARD_MAX_WORLD]; };
+__global__ void __launch_bounds__(256) shard_push_kernel(const ulonglong2 *__restrict__ src, PeerTab dst, PeerTab flags, u32 world, u64 chunks, u32 flag_slot, u64 epoch,
+                                                         u32 *__restrict__ counter) {
+    for (u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x; v < chunks; v += (u64)gridDim.x * blockDim.x) {
+        const ulonglong2 d = src[v];
+        for (u32 r = 0; r < world; r++) reinterpret_cast<ulonglong2 *>(dst.p[r])[v] = d;
+    }
+    __threadfence_system();                  // this thread's peer stores are performed system-wide ...
+    __shared__ u32 last;
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(counter, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (last) {                              // ... and the last block to get here publishes the epoch to every peer
+        __threadfence_system();
+        if (threadIdx.x < world) {
+            u64 *f = flags.p[threadIdx.x] + flag_slot;
+            asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(f), "l"(epoch) : "memory");
+        }
+        if (threadIdx.x == 0) *counter = 0;
+    }
+}
+struct SlotTab { int s[SHARD_MAX_WORLD]; };
+__global__ void shard_wait_kernel(const u64 *__restrict__ flags, SlotTab slots, u32 n_slots, u64 epoch) {
+    if (threadIdx.x < n_slots) {
+        const u64 *f = flags + slots.s[threadIdx.x];
+        u64 v = 0;
+        for (u32 spins = 0;; spins++) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(f) : "memory");
+            if (v >= epoch) break;
+            __nanosleep(100);
+            if (spins == (1u << 25)) { printf("b2 shard wait: flag slot %d stuck at %llu, waiting for %llu\n", slots.s[threadIdx.x], v, epoch); __trap(); }
+        }
+    }
+}
+
 struct SpecialLoad {      // step 4: the special-prime limb of prod[b][k], c = 2 b + k (row `decomp` of R rows)
     const u64 *prod; u32 R, decomp, n;
     __device__ __forceinline__ const u64 *src(int, int c, u64) const { return prod + ((u64)c * R + decomp) * n; }
@@ -459,6 +500,70 @@ b2_status b2_kswitch_key_shard(b2_ctx *ctx, const b2_kswitch_key *full, size_t d
     return B2_OK;
 }
 
+// Partition weighted by what a modulus costs its owner: a modulus above 41 bits runs on the integer pipe (~2 x a 40-bit one), and
+// the special prime's owner carries the serial tail (inverse transform of the special limb + its push), so it counts once more.
+// Contiguous ranges, maximal load minimised (dynamic programme over the decomp + 1 output moduli).
+b2_status b2_limb_partition_weighted(const b2_ctx *ctx, size_t decomp, int world, int rank, size_t *first, size_t *count) {
+    B2_REQUIRE(ctx && first && count && world >= 1 && rank >= 0 && rank < world && decomp >= 1 && decomp + 1 <= ctx->K, "bad arguments");
+    const size_t R = decomp + 1;
+    std::vector<unsigned> w(R);
+    for (size_t i = 0; i < R; i++) { const size_t ki = i == decomp ? ctx->K - 1 : i; w[i] = (ctx->h_mods[ki].use_f64 ? 1u : 2u) + (i == decomp ? 1u : 0u); }
+    std::vector<unsigned> pre(R + 1, 0);
+    for (size_t i = 0; i < R; i++) pre[i + 1] = pre[i] + w[i];
+    const size_t W = (size_t)world;
+    // best[k][i]: minimal maximal load of the first i moduli over k ranks (ranks may be empty when world > R)
+    std::vector<std::vector<unsigned>> best(W + 1, std::vector<unsigned>(R + 1, ~0u));
+    std::vector<std::vector<size_t>> cut(W + 1, std::vector<size_t>(R + 1, 0));
+    best[0][0] = 0;
+    for (size_t k = 1; k <= W; k++)
+        for (size_t i = 0; i <= R; i++)
+            for (size_t j = 0; j <= i; j++) {
+                if (best[k - 1][j] == ~0u) continue;
+                const unsigned load = std::max(best[k - 1][j], pre[i] - pre[j]);
+                if (load < best[k][i] || (load == best[k][i] && j > cut[k][i])) { best[k][i] = load; cut[k][i] = j; }
+            }
+    size_t hi = R;
+    for (size_t k = W; k >= 1; k--) {
+        const size_t lo = cut[k][hi];
+        if ((int)(k - 1) == rank) { *first = lo; *count = hi - lo; return B2_OK; }
+        hi = lo;
+    }
+    *first = 0; *count = 0;
+    return B2_OK;
+}
+
+b2_status b2_shard_push(b2_ctx *ctx, const uint64_t *src, uint64_t *const *peer_dst, int world, size_t words, uint64_t *const *peer_flags, size_t flag_slot,
+                        uint64_t epoch, void *stream_) {
+    B2_REQUIRE(ctx && peer_dst && peer_flags && world >= 1 && world <= SHARD_MAX_WORLD && (words == 0 || src) && (words & 1) == 0, "bad arguments");
+    B2_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PeerTab d, f;
+    for (int r = 0; r < SHARD_MAX_WORLD; r++) { d.p[r] = r < world ? (u64 *)peer_dst[r] : nullptr; f.p[r] = r < world ? (u64 *)peer_flags[r] : nullptr; }
+    for (int r = 0; r < world; r++) B2_REQUIRE(f.p[r] && (words == 0 || (d.p[r] && (((uintptr_t)d.p[r]) & 15) == 0)), "null or misaligned peer pointer");
+    Scratch sc(ctx, stream);
+    b2_status st = ensure_sync(sc.s, 0, stream);
+    if (st != B2_OK) return st;
+    // the push counter lives behind the transform queue's counters (zero between launches)
+    u32 *counter = sc->d_sync + sc->sync_limbs + 3;
+    const u64 chunks = words / 2;
+    const unsigned grid = (unsigned)std::max<u64>(1, std::min<u64>((chunks + 255) / 256, (u64)ctx->sm_count * 2));
+    shard_push_kernel<<<grid, 256, 0, stream>>>((const ulonglong2 *)src, d, f, (u32)world, chunks, (u32)flag_slot, epoch, counter);
+    count_launches(1);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+b2_status b2_shard_wait(b2_ctx *ctx, const uint64_t *flags, const int *slots, int n_slots, uint64_t epoch, void *stream_) {
+    B2_REQUIRE(ctx && flags && (n_slots == 0 || slots) && n_slots >= 0 && n_slots <= SHARD_MAX_WORLD, "bad arguments");
+    if (n_slots == 0) return B2_OK;
+    B2_CUDA(cudaSetDevice(ctx->device));
+    SlotTab t;
+    for (int i = 0; i < SHARD_MAX_WORLD; i++) t.s[i] = i < n_slots ? slots[i] : 0;
+    shard_wait_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>((const u64 *)flags, t, (u32)n_slots, epoch);
+    count_launches(1);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
 static inline size_t owned_ct_limbs(size_t decomp, size_t first, size_t count) {
     return first >= decomp ? 0 : std::min(first + count, decomp) - first;
 }
@@ -485,7 +590,7 @@ b2_status b2_keyswitch_shard_prepare(b2_ctx *ctx, const uint64_t *target_local, 
 // prod survives from `products` to `finish` (no other call on this context in between)
 b2_status b2_keyswitch_shard_products(b2_ctx *ctx, const uint64_t *gathered, int world, size_t pad, size_t decomp, size_t first, size_t count,
                                       const b2_kswitch_key *shard, uint64_t *u, void *stream_) {
-    B2_REQUIRE(ctx && gathered && shard && world >= 1, "null argument");
+    B2_REQUIRE(ctx && gathered && shard && world >= 0, "null argument");
     B2_REQUIRE(decomp >= 1 && decomp + 1 <= ctx->K && count >= 1 && first + count <= decomp + 1, "bad modulus range");
     B2_REQUIRE(shard->rows == count && shard->first == first && shard->decomp == decomp, "key shard does not match the modulus range");
     B2_REQUIRE((((uintptr_t)gathered | (uintptr_t)u) & 15) == 0, "operands must be 16-byte aligned");
@@ -499,8 +604,10 @@ b2_status b2_keyswitch_shard_products(b2_ctx *ctx, const uint64_t *gathered, int
     b2_status st = ensure_ws(sc, stream, (2 * count + 2 * nct + decomp + count * decomp) * n * 8);
     if (st != B2_OK) return st;
     u64 *prod = (u64 *)sc->ws, *tc = prod + (2 * count + 2 * nct) * n, *temp = tc + decomp * n;
+    // world == 0: `gathered` already IS the coefficient-form target [decomp][N] (P2P path: the peers pushed their limbs in place)
+    if (world == 0) tc = (u64 *)gathered;
     // the all-gather delivered [world][pad][N]: rank r's owned ciphertext limbs first_r .. ; compact to tc[decomp][N]
-    {
+    else {
         const size_t R = decomp + 1, base = R / (size_t)world, rem = R % (size_t)world;
         B2_REQUIRE(pad >= std::min<size_t>(base + (rem ? 1 : 0), decomp), "pad is smaller than a rank's share of the ciphertext limbs");
         if (base == 0) {    // more ranks than moduli: rank r < rem owns modulus r
