@@ -64,6 +64,13 @@ def test_host_mirror_script(po, scheme, tmp_path):
             ("multiply_plain", mp), ("relinearize_batched[0]", r), ("relinearize_batched[1]", relinearize(sq)),
             ("rotate_batched[0]", rot1), ("rotate_batched[1]", rot(rot1, 1)), ("rotate_batched NAF[0]", rot3), ("rotate_batched NAF[1]", rot(rot(rot1, -1), 4)),
             ("apply_keyswitching", ks)]
+    bn = b if is_ntt else o.ntt_fwd(b.copy(), 2, L)
+    mp_ntt = o.dyadic_broadcast(an, plain, 2, L)
+    mpb_ntt = o.dyadic_broadcast(bn, plain, 2, L)
+    both = o.add(mp_ntt, mpb_ntt, 2, L)
+    want += [("multiply_plain coefficient x coefficient", o.ntt_inv(mp_ntt.copy(), 2, L)), ("multiply_plain ntt x coefficient", mp_ntt),
+             ("multiply_plain_batched[0]", mp_ntt), ("multiply_plain_batched[1]", mpb_ntt),
+             ("multiply_plain_accumulate d0 (repeated destination)", both), ("multiply_plain_accumulate d1 (+= second call)", both)]
     pos = 0
     for name, exp in want:
         got = out[pos:pos + exp.size]; pos += exp.size

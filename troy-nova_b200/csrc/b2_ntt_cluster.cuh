@@ -45,47 +45,64 @@ struct DsmemStore {
     __device__ __forceinline__ void st2(const Prep &pc, u32 x, u64 v0, u64 v1) const { (*this)(pc, x, v0); (*this)(pc, x + 1, v1); }
 };
 
+template <class Next>
 struct ClusterHooks {
     NoHook mid;
     bool first;        // first pass: its stage buffer doubles as the receive buffer of the second pass
+    Next next;         // second pass: stages the first-pass tile of the cluster's next limb
     __device__ __forceinline__ void sync_stage() const { cp_async_wait_all(); __syncthreads(); }
     __device__ __forceinline__ void pre_exchange() const {}
-    // every thread of the CTA has read the staged tile: the buffer may now receive the other CTAs' intermediates
-    __device__ __forceinline__ void stage_free() const { if (first) asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory"); }
+    // every thread of the CTA has read the staged tile.  First pass: the buffer may now receive the other CTAs' intermediates.
+    // Second pass: the buffer is free for good (every remote store landed before the cluster barrier that precedes the pass).
+    __device__ __forceinline__ void stage_free() const {
+        if (first) asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+        else next();
+    }
 };
 
+// The grid is min(limbs, co-resident clusters) clusters: cluster k transforms limbs k, k + clusters, ... and stages the next limb's
+// tile under the second pass of the current one.
 template <bool FWD, class Load, class Store>
 __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_cluster_kernel(const __grid_constant__ NttJob J, Load ld, Store st) {
     extern __shared__ __align__(128) u64 smem[];
     u64 *const stage = smem, *const xch = smem + NTT_TILE, *const recv = stage;
     const u32 r = cluster_ctarank();
-    const u32 limb = blockIdx.x / CL_SIZE;
-    const u32 c = limb / (u32)J.n_groups, g = limb - c * (u32)J.n_groups;
-    const LimbGroup &grp = J.groups[g];
-    const u64 off = limb_offset(J, grp, c);
-    const ModInfo &M = J.mods[group_table(grp.table)];
-    const u32 path = group_path(grp.table, FWD);
-    const int ga = J.g_base + (int)g;
+    const u32 n_cl = gridDim.x / CL_SIZE;
+    u32 limb = blockIdx.x / CL_SIZE;
     // first-pass tile from the operand: forward = column tile r, inverse = row tile r
-    stage_tile<8, FWD>(stage, ld.src(ga, (int)c, off), (int)r);
-    cp_async_commit();
+    const auto stage_limb = [&](u32 lb) {
+        const u32 c = lb / (u32)J.n_groups, g = lb - c * (u32)J.n_groups;
+        stage_tile<8, FWD>(stage, ld.src(J.g_base + (int)g, (int)c, limb_offset(J, J.groups[g], c)), (int)r);
+        cp_async_commit();
+    };
+    stage_limb(limb);
     cluster_sync();            // every CTA of the cluster is resident before anyone writes into its shared memory
-    ClusterHooks hk; hk.first = true;
     const DsmemStore<FWD> xst{(u32)__cvta_generic_to_shared(recv)};
     const PlainLoad none{nullptr};
-    if (FWD) {
-        using Pl = FwdColPlan<8>;
-        pass_dispatch<8, true, true, true, false, Pl::LO0, Pl::NL0, Pl::LO1, Pl::NL1, Pl::LO2, Pl::NL2>(path, stage, xch, M, (int)r, ga, (int)c, off, 16, ld, xst, hk);
-    } else {
-        pass_dispatch<8, false, false, true, false, 0, 4, 4, 4, 0, 0>(path, stage, xch, M, (int)r, ga, (int)c, off, 16, ld, xst, hk);
-    }
-    cluster_sync();            // all intermediates have landed in the receive buffers
-    hk.first = false;
-    if (FWD) {
-        pass_dispatch<8, false, true, false, true, 4, 4, 0, 4, 0, 0>(path, recv, xch, M, (int)r, ga, (int)c, off, 16, none, st, hk);
-    } else {
-        using Pl = InvColPlan<8>;
-        pass_dispatch<8, true, false, false, true, Pl::LO0, Pl::NL0, Pl::LO1, Pl::NL1, Pl::LO2, Pl::NL2>(path, recv, xch, M, (int)r, ga, (int)c, off, 16, none, st, hk);
+    for (; limb < J.n_limbs; limb += n_cl) {
+        const u32 c = limb / (u32)J.n_groups, g = limb - c * (u32)J.n_groups;
+        const LimbGroup &grp = J.groups[g];
+        const u64 off = limb_offset(J, grp, c);
+        const ModInfo &M = J.mods[group_table(grp.table)];
+        const u32 path = group_path(grp.table, FWD);
+        const int ga = J.g_base + (int)g;
+        const u32 nxt = limb + n_cl;
+        const auto next = [&]() { if (nxt < J.n_limbs) stage_limb(nxt); };
+        ClusterHooks<decltype(next)> hk{NoHook(), true, next};
+        if (FWD) {
+            using Pl = FwdColPlan<8>;
+            pass_dispatch<8, true, true, true, false, Pl::LO0, Pl::NL0, Pl::LO1, Pl::NL1, Pl::LO2, Pl::NL2>(path, stage, xch, M, (int)r, ga, (int)c, off, 16, ld, xst, hk);
+        } else {
+            pass_dispatch<8, false, false, true, false, 0, 4, 4, 4, 0, 0>(path, stage, xch, M, (int)r, ga, (int)c, off, 16, ld, xst, hk);
+        }
+        cluster_sync();        // all intermediates have landed in the receive buffers
+        hk.first = false;
+        if (FWD) {
+            pass_dispatch<8, false, true, false, true, 4, 4, 0, 4, 0, 0>(path, recv, xch, M, (int)r, ga, (int)c, off, 16, none, st, hk);
+        } else {
+            using Pl = InvColPlan<8>;
+            pass_dispatch<8, true, false, false, true, Pl::LO0, Pl::NL0, Pl::LO1, Pl::NL1, Pl::LO2, Pl::NL2>(path, recv, xch, M, (int)r, ga, (int)c, off, 16, none, st, hk);
+        }
     }
 }
 

@@ -82,13 +82,8 @@ static cudaError_t launch_persistent(const NttJob &J, int device, unsigned grid,
 // N = 2^16, few limbs: one 16-CTA cluster per limb, intermediate in distributed shared memory (b2_ntt_cluster.cuh)
 template <bool FWD, class Load, class Store>
 static cudaError_t launch_cluster(const NttJob &J, int device, cudaStream_t s, Load ld, Store st) {
-    static bool configured[B2_MAX_DEVICES] = {};
-    if (!configured[device & (B2_MAX_DEVICES - 1)]) {
-        cudaError_t e = cudaFuncSetAttribute(ntt_cluster_kernel<FWD, Load, Store>, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(ntt_cluster_kernel<FWD, Load, Store>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        if (e != cudaSuccess) return e;
-        configured[device & (B2_MAX_DEVICES - 1)] = true;
-    }
+    static int resident[B2_MAX_DEVICES] = {};       // co-resident clusters of this instantiation on the device (0: not configured yet)
+    int &res = resident[device & (B2_MAX_DEVICES - 1)];
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(J.n_limbs * CL_SIZE, 1, 1);
     cfg.blockDim = dim3(NTT_THREADS, 1, 1);
@@ -98,6 +93,18 @@ static cudaError_t launch_cluster(const NttJob &J, int device, cudaStream_t s, L
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL_SIZE; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    if (!res) {
+        cudaError_t e = cudaFuncSetAttribute(ntt_cluster_kernel<FWD, Load, Store>, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ntt_cluster_kernel<FWD, Load, Store>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+        int n = 0;
+        e = cudaOccupancyMaxActiveClusters(&n, ntt_cluster_kernel<FWD, Load, Store>, &cfg);
+        if (e != cudaSuccess) return e;
+        if (n < 1) return cudaErrorInvalidConfiguration;
+        if (const char *cap = getenv("B2_NTT_CLUSTERS")) n = std::max(1, std::min(n, atoi(cap)));
+        res = n;
+    }
+    cfg.gridDim.x = std::min<unsigned>(J.n_limbs, (unsigned)res) * CL_SIZE;      // persistent above that: cluster k takes limbs k, k + res, ...
     return cudaLaunchKernelEx(&cfg, ntt_cluster_kernel<FWD, Load, Store>, J, ld, st);
 }
 // launches of at most this many limbs take the cluster kernel (latency-bound regime); B2_NTT_CLUSTER_MAX overrides (0 = never)

@@ -452,34 +452,86 @@ static void transform_batched(const HeContextPointer &ctx, const std::vector<Cip
 void Evaluator::transform_to_ntt_inplace_batched(const std::vector<Ciphertext *> &es) const { transform_batched(context_, es, true); }
 void Evaluator::transform_from_ntt_inplace_batched(const std::vector<Ciphertext *> &es) const { transform_batched(context_, es, false); }
 
+// Evaluator::multiply_plain (src/evaluator_multiply_plain.cu:309-328): the four form combinations of the reference.  A Plaintext of this
+// mirror is RNS-limbed (what transform_plain_to_ntt / the encoders hand to the evaluator), so the coefficient-form product is
+// NTT(ct), NTT(pt), dyadic product, INTT (multiply_plain_normal, :13-68, after its centralize step).
 void Evaluator::multiply_plain(const Ciphertext &e, const Plaintext &p, Ciphertext &d) const {
     check_ct("[Evaluator::multiply_plain]", e);
-    if (!e.is_ntt_form() || !p.is_ntt_form())
-        throw std::invalid_argument("[Evaluator::multiply_plain] This mirror covers the NTT-form path (multiply_plain_ntt); transform the operands first.");
     if (p.coeff_modulus_size() != e.coeff_modulus_size()) throw std::invalid_argument("[Evaluator::multiply_plain_ntt] Plaintext parms_id mismatch.");
-    Ciphertext r = Ciphertext::like(e, e.polynomial_count());
-    check(b2_dyadic_broadcast(context_->raw(), e.data(), p.data(), r.data(), e.polynomial_count(), e.coeff_modulus_size(), 0, context_->stream), "[Evaluator::multiply_plain]");
+    const size_t pc = e.polynomial_count(), L = e.coeff_modulus_size();
+    b2_ctx *c = context_->raw();
+    Ciphertext r = Ciphertext::like(e, pc);
+    const uint64_t *ct = e.data(), *pt = p.data();
+    DeviceArray pt_ntt;
+    if (!e.is_ntt_form()) {          // transform a copy of the ciphertext (into the result buffer)
+        check(b2_ntt_forward(c, e.data(), r.data(), 1, pc, L, B2_TABLES_COMPONENTWISE, 0, 0, context_->stream), "[Evaluator::multiply_plain]");
+        ct = r.data();
+    }
+    if (!p.is_ntt_form()) {
+        pt_ntt = DeviceArray(context_, L * context_->poly_modulus_degree());
+        check(b2_ntt_forward(c, p.data(), pt_ntt.data(), 1, 1, L, B2_TABLES_COMPONENTWISE, 0, 0, context_->stream), "[Evaluator::multiply_plain]");
+        pt = pt_ntt.data();
+    }
+    check(b2_dyadic_broadcast(c, ct, pt, r.data(), pc, L, 0, context_->stream), "[Evaluator::multiply_plain]");
+    if (!e.is_ntt_form()) check(b2_ntt_inverse(c, r.data(), r.data(), 1, pc, L, B2_TABLES_COMPONENTWISE, 0, 0, context_->stream), "[Evaluator::multiply_plain]");
+    if (pt_ntt.data()) check(b2_stream_sync(c, context_->stream), "[Evaluator::multiply_plain]");      // the temporary is freed on scope exit
     d = std::move(r);
 }
+static void check_plain_batch(const std::vector<const Ciphertext *> &es, const std::vector<const Plaintext *> &ps) {
+    for (size_t i = 0; i < es.size(); i++) {
+        if (!es[i] || !ps[i] || es[i]->empty()) throw std::invalid_argument("[Evaluator::multiply_plain_batched] Empty operand.");
+        if (!es[i]->is_ntt_form() || !ps[i]->is_ntt_form())
+            throw std::invalid_argument("[Evaluator::multiply_plain_batched] The batched forms cover NTT-form operands (multiply_plain_ntt_batched); transform the batch first.");
+        if (es[i]->polynomial_count() != es[0]->polynomial_count() || es[i]->coeff_modulus_size() != es[0]->coeff_modulus_size() ||
+            ps[i]->coeff_modulus_size() != es[0]->coeff_modulus_size())
+            throw std::invalid_argument("[Evaluator::multiply_plain_batched] Operand shape mismatch.");
+    }
+}
+// multiply_plain_ntt_batched (:216-256): ONE launch over the scattered operands
 void Evaluator::multiply_plain_batched(const std::vector<const Ciphertext *> &es, const std::vector<const Plaintext *> &ps, const std::vector<Ciphertext *> &ds) const {
     if (es.size() != ps.size() || es.size() != ds.size()) throw std::invalid_argument("[Evaluator::multiply_plain_batched] Size mismatch.");
-    // the operands are separate allocations (the reference's vector<Ciphertext*>): one launch per item; callers that keep a
-    // batch contiguous use b2_dyadic_broadcast_batched directly (one launch for the whole batch)
-    for (size_t i = 0; i < es.size(); i++) multiply_plain(*es[i], *ps[i], *ds[i]);
+    if (es.empty()) return;
+    check_plain_batch(es, ps);
+    std::vector<Ciphertext> out(es.size());
+    std::vector<const uint64_t *> c(es.size()), p(es.size());
+    std::vector<uint64_t *> o(es.size());
+    for (size_t i = 0; i < es.size(); i++) {
+        out[i] = Ciphertext::like(*es[i], es[i]->polynomial_count());
+        c[i] = es[i]->data(); p[i] = ps[i]->data(); o[i] = out[i].data();
+    }
+    check(b2_multiply_plain_accumulate(context_->raw(), c.data(), p.data(), o.data(), es.size(), es[0]->polynomial_count(), es[0]->coeff_modulus_size(), 0, 0, context_->stream),
+          "[Evaluator::multiply_plain_batched]");
+    for (size_t i = 0; i < es.size(); i++) *ds[i] = std::move(out[i]);
+}
+// multiply_plain_ntt_accumulate (:258-307): destination[i] (+)= encrypted[i] * plain[i]; destinations may REPEAT (all terms with the
+// same destination are summed into it); ONE launch.  set_zero: the destinations are (re)created and start from zero.
+void Evaluator::multiply_plain_accumulate(const std::vector<const Ciphertext *> &es, const std::vector<const Plaintext *> &ps, const std::vector<Ciphertext *> &ds,
+                                          bool set_zero) const {
+    if (es.size() != ps.size() || es.size() != ds.size()) throw std::invalid_argument("[Evaluator::multiply_plain_ntt_batched] Input vectors have different sizes.");
+    if (es.empty()) return;
+    check_plain_batch(es, ps);
+    std::vector<const uint64_t *> c(es.size()), p(es.size());
+    std::vector<uint64_t *> o(es.size());
+    for (size_t i = 0; i < es.size(); i++) {
+        if (!ds[i]) throw std::invalid_argument("[Evaluator::multiply_plain_accumulate] Null destination.");
+        if (set_zero) {
+            bool seen = false;
+            for (size_t k = 0; k < i && !seen; k++) seen = ds[k] == ds[i];
+            if (!seen) *ds[i] = Ciphertext::like(*es[i], es[i]->polynomial_count());
+        } else if (ds[i]->empty() || ds[i]->coeff_modulus_size() != es[i]->coeff_modulus_size() || ds[i]->polynomial_count() != es[i]->polynomial_count() ||
+                   ds[i]->is_ntt_form() != es[i]->is_ntt_form()) {
+            throw std::invalid_argument("[Evaluator::multiply_plain_normal_accumulate] Destination parameters do not match.");
+        }
+    }
+    for (size_t i = 0; i < es.size(); i++) { c[i] = es[i]->data(); p[i] = ps[i]->data(); o[i] = ds[i]->data(); }
+    check(b2_multiply_plain_accumulate(context_->raw(), c.data(), p.data(), o.data(), es.size(), es[0]->polynomial_count(), es[0]->coeff_modulus_size(), 0,
+                                       set_zero ? 0 : 1, context_->stream), "[Evaluator::multiply_plain_accumulate]");
 }
 void Evaluator::multiply_plain_accumulate(const std::vector<const Ciphertext *> &es, const std::vector<const Plaintext *> &ps, Ciphertext &d, bool set_zero) const {
     if (es.size() != ps.size()) throw std::invalid_argument("[Evaluator::multiply_plain_accumulate] Size mismatch.");
     if (es.empty()) return;
-    size_t first = 0;
-    if (set_zero || d.empty()) { multiply_plain(*es[0], *ps[0], d); first = 1; }
-    for (size_t i = first; i < es.size(); i++) {
-        check_ct("[Evaluator::multiply_plain_accumulate]", *es[i]);
-        if (!es[i]->is_ntt_form() || !ps[i]->is_ntt_form() || es[i]->coeff_modulus_size() != d.coeff_modulus_size() ||
-            es[i]->polynomial_count() != d.polynomial_count() || ps[i]->coeff_modulus_size() != d.coeff_modulus_size())
-            throw std::invalid_argument("[Evaluator::multiply_plain_accumulate] Operand shape / form mismatch.");
-        check(b2_dyadic_broadcast(context_->raw(), es[i]->data(), ps[i]->data(), d.data(), d.polynomial_count(), d.coeff_modulus_size(), 1, context_->stream),
-              "[Evaluator::multiply_plain_accumulate]");
-    }
+    std::vector<Ciphertext *> ds(es.size(), &d);
+    multiply_plain_accumulate(es, ps, ds, set_zero || d.empty());
 }
 
 void Evaluator::negacyclic_shift(const Ciphertext &e, size_t shift, Ciphertext &d) const {

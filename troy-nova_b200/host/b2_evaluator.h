@@ -254,12 +254,15 @@ public:
     void transform_to_ntt_inplace_batched(const std::vector<Ciphertext *> &encrypted) const;
     void transform_from_ntt_inplace_batched(const std::vector<Ciphertext *> &encrypted) const;
 
-    // ---- ct x pt on NTT-form operands (src/evaluator_multiply_plain.cu:13-383 multiply_plain_ntt / _accumulate)
+    // ---- ct x pt (src/evaluator_multiply_plain.cu:13-383): multiply_plain in all four form combinations, NTT-form batched / accumulate forms
     void multiply_plain(const Ciphertext &encrypted, const Plaintext &plain, Ciphertext &destination) const;
     void multiply_plain_inplace(Ciphertext &encrypted, const Plaintext &plain) const { Ciphertext d; multiply_plain(encrypted, plain, d); encrypted = std::move(d); }
     void multiply_plain_batched(const std::vector<const Ciphertext *> &encrypted, const std::vector<const Plaintext *> &plain, const std::vector<Ciphertext *> &destination) const;
     // destination += sum_i encrypted[i] * plain[i]   (multiply_plain_accumulate with set_zero)
     void multiply_plain_accumulate(const std::vector<const Ciphertext *> &encrypted, const std::vector<const Plaintext *> &plain, Ciphertext &destination, bool set_zero) const;
+    // the reference's signature (src/evaluator_multiply_plain.cu:258-307): one destination pointer per term, destinations may repeat; one launch
+    void multiply_plain_accumulate(const std::vector<const Ciphertext *> &encrypted, const std::vector<const Plaintext *> &plain,
+                                   const std::vector<Ciphertext *> &destination, bool set_zero) const;
 
     // ---- LWE-packing helper (src/evaluator_lwes.cu; utils::negacyclic_shift_ps)
     void negacyclic_shift(const Ciphertext &encrypted, size_t shift, Ciphertext &destination) const;

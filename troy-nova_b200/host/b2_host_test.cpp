@@ -47,7 +47,8 @@ int main(int argc, char **argv) {
         const double scale = scheme == SchemeType::CKKS ? 1048576.0 : 1.0;
         Ciphertext a = Ciphertext::from_host(ctx, take(2 * L * n), 2, L, ntt, scale);
         Ciphertext b = Ciphertext::from_host(ctx, take(2 * L * n), 2, L, ntt, scale);
-        Plaintext plain = Plaintext::from_host(ctx, take(L * n), L, true);
+        const uint64_t *plain_words = take(L * n);
+        Plaintext plain = Plaintext::from_host(ctx, plain_words, L, true);
         Evaluator ev(ctx);
 
         Ciphertext m = ev.multiply_new(a, b);                     emit(m);        // 1
@@ -80,6 +81,25 @@ int main(int argc, char **argv) {
         }
         {                                                                         // 18: apply_keyswitching with the relin key as a plain kswitch key
             Ciphertext ks; ev.apply_keyswitching(r, rk, ks); emit(ks);
+        }
+        {                                                                         // 19, 20: multiply_plain with coefficient-form operands
+            Ciphertext an = a.clone(), ac = a.clone();
+            if (!ntt) ev.transform_to_ntt_inplace(an); else ev.transform_from_ntt_inplace(ac);
+            Ciphertext pw = Ciphertext::from_host(ctx, plain_words, 1, L, true, 1.0);
+            ev.transform_from_ntt_inplace(pw);
+            Plaintext plain_c = Plaintext::from_host(ctx, pw.to_host().data(), L, false);
+            Ciphertext cc, nc;
+            ev.multiply_plain(ac, plain_c, cc); emit(cc);                         //   both coefficient form -> coefficient form
+            ev.multiply_plain(an, plain_c, nc); emit(nc);                         //   NTT-form ciphertext, coefficient-form plaintext -> NTT form
+            Ciphertext bn = b.clone();
+            if (!ntt) ev.transform_to_ntt_inplace(bn);
+            Ciphertext o0, o1;                                                    // 21, 22: multiply_plain_batched, one launch
+            ev.multiply_plain_batched({&an, &bn}, {&plain, &plain}, {&o0, &o1});
+            emit(o0); emit(o1);
+            Ciphertext d0, d1;                                                    // 23, 24: multiply_plain_accumulate with a repeated destination
+            ev.multiply_plain_accumulate({&an, &bn, &bn}, {&plain, &plain, &plain}, std::vector<Ciphertext *>{&d0, &d1, &d0}, true);
+            ev.multiply_plain_accumulate({&an}, {&plain}, d1, false);
+            emit(d0); emit(d1);
         }
         // error behaviour probes: 1 = std::invalid_argument thrown as the reference does
         auto probe = [&](auto &&fn) { try { fn(); out.push_back(0); } catch (const std::invalid_argument &) { out.push_back(1); } };
