@@ -188,6 +188,29 @@ b2_status b2_dyadic_broadcast_batched(b2_ctx *ctx, const uint64_t *a, const uint
  * One launch per 65535 distinct destinations; every operand word is read once. */
 b2_status b2_multiply_plain_accumulate(b2_ctx *ctx, const uint64_t *const *ct, const uint64_t *const *pt, uint64_t *const *dest, size_t n_terms,
                                        size_t pcount, size_t ncomp, size_t table_base, int add_to_dest, void *stream);
+/* ---- Decryptor ----
+ * sk_powers: DEVICE array [max_power][K][N], s, s^2, ... in NTT form at the key level — the reference's Decryptor::secret_key_array_
+ * (src/decryptor.h, filled by KeyGenerator::compute_secret_key_powers, src/key_generator.cu:84-110).  b2_secret_key_powers builds it
+ * from the secret key sk [K][N] (NTT form; out == sk + 0 is allowed: power 1 is copied unless out == sk). */
+b2_status b2_secret_key_powers(b2_ctx *ctx, const uint64_t *sk, size_t max_power, uint64_t *out, void *stream);
+/* Decryptor::dot_product_ct_sk_array[_batched] (src/decryptor.cu:27-231): phase[b] = c_0 + sum_{k=1}^{pcount-1} c_k s^k, [nl][N], in the
+ * form of the ciphertexts.  ct / phase: HOST arrays of `batch` DEVICE pointers (ct[b] [pcount][nl][N]).  NTT form: one launch;
+ * coefficient form: two launches (forward transform with the key product fused, inverse transform with the sum and c_0 fused). */
+b2_status b2_decrypt_phase(b2_ctx *ctx, const uint64_t *const *ct, uint64_t *const *phase, size_t batch, size_t pcount, size_t nl, int is_ntt_form,
+                           const uint64_t *sk_powers, void *stream);
+/* RNSTool::decrypt_scale_and_round[_batched] (src/utils/rns_tool.cu:1334-1430): BFV, phase[b] [nl][N] coefficient form ->
+ * plain[b] [N] = round(t/q * phase) mod t.  gamma is derived as the reference does (rns_tool.cu:68-76). */
+b2_status b2_decrypt_scale_and_round(b2_ctx *ctx, const uint64_t *const *phase, uint64_t *const *plain, size_t batch, size_t nl, void *stream);
+/* RNSTool::decrypt_mod_t (BaseConverter::exact_convey_array, src/utils/rns_base.cu:445-583) and the correction factor of
+ * scaling_variant::decentralize (src/utils/scaling_variant.cu:415-431): BGV, phase[b] [nl][N] coefficient form -> plain[b] [N].
+ * correction_factors: HOST array [batch] or NULL (all 1); B2_ERR_INVALID_ARG if one is not invertible modulo t. */
+b2_status b2_decrypt_mod_t(b2_ctx *ctx, const uint64_t *const *phase, uint64_t *const *plain, size_t batch, size_t nl, const uint64_t *correction_factors,
+                           void *stream);
+/* Decryptor::decrypt / decrypt_batched (src/decryptor.cu:233-535) for the scheme of the context: BFV (coefficient-form
+ * ciphertexts) and BGV (NTT form) -> plain[b] [N] modulo t; CKKS (NTT form) -> plain[b] [nl][N] in NTT form.
+ * 3 / 2 / 1 launches per call for any batch size. */
+b2_status b2_decrypt(b2_ctx *ctx, const uint64_t *const *ct, uint64_t *const *plain, size_t batch, size_t pcount, size_t nl, const uint64_t *sk_powers,
+                     const uint64_t *correction_factors, void *stream);
 /* Evaluator::bfv_multiply / bfv_square device branch (src/evaluator.cu:29-116,199-282) = BEHZ RNS multiplication:
  * RNSTool::fast_b_conv_m_tilde_sm_mrq + NTT + dyadic convolution + INTT + RNSTool::fast_floor_fast_b_conv_sk
  * (src/fgk/rns_tool.cu:7-343).  a, b [batch][2][nl][N] coefficient form -> out [batch][3][nl][N] coefficient form.

@@ -63,5 +63,35 @@ def main():
         print("wrote", name, {k: getattr(v, "shape", None) for k, v in list(g.items())[:4]})
 
 
+def main_decrypt():
+    """tests/golden/ref_decrypt_n256.npz: the reference's Decryptor (src/decryptor.cu) on random ciphertexts of two and three
+    polynomials at the first and the last level, under the reference's own secret key; BGV also with a correction factor."""
+    g = {"n": N, "bits": np.array(BITS)}
+    for scheme, name in ((po.BFV, "bfv"), (po.CKKS, "ckks"), (po.BGV, "bgv")):
+        r = po.Reference(scheme, N, BITS, t_bits=20, seed=0x123)
+        L = r.nm - 1
+        rng = np.random.default_rng(2000 + scheme)
+        g[name + "_moduli"] = r.moduli; g[name + "_t"] = np.uint64(r.t); g[name + "_sk"] = r.secret_key()
+        zero = r.encrypt_zero()
+        g[name + "_zero"] = zero; g[name + "_zero_dec"] = r.decrypt_raw(zero, 2, L)
+        for nl in (L, 1):
+            for pc in (2, 3):
+                ct = np.empty((pc, nl, N), dtype=np.uint64)
+                for j in range(nl):
+                    ct[:, j, :] = rng.integers(0, int(r.moduli[j]), size=(pc, N), dtype=np.uint64)
+                ct = ct.reshape(-1)
+                key = "%s_l%d_p%d" % (name, nl, pc)
+                g[key + "_ct"] = ct; g[key + "_dec"] = r.decrypt_raw(ct, pc, nl)
+                if scheme == po.BGV:
+                    g[key + "_dec_cf7"] = r.decrypt_raw(ct, pc, nl, 7)
+                if scheme == po.BFV:
+                    g[key + "_phase"] = r.decrypt_phase_raw(ct, pc, nl)
+    np.savez_compressed(os.path.join(OUT, "ref_decrypt_n256.npz"), **g)
+    print("wrote decrypt", len(g), "arrays")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "decrypt":
+        main_decrypt()
+    else:
+        main(); main_decrypt()

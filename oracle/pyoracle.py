@@ -98,6 +98,11 @@ def lib():
         L.ro_keygen_kswitch.argtypes = [C.c_void_p, u64p, u64p, C.c_uint64, u64p]
         L.ro_encrypt_zero_sym.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_int, C.c_uint64, u64p]
         L.ro_phase.argtypes = [C.c_void_p, u64p, u64p, C.c_size_t, C.c_size_t, C.c_int, u64p]
+        L.ro_secret_key_powers.argtypes = [C.c_void_p, u64p, C.c_size_t, u64p]
+        L.ro_decrypt_phase.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_size_t, C.c_int, u64p, u64p]
+        L.ro_decrypt_scale_and_round.argtypes = [C.c_void_p, u64p, C.c_size_t, u64p]
+        L.ro_decrypt_mod_t.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_uint64, u64p]
+        L.ro_decrypt.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_size_t, u64p, C.c_uint64, u64p]
         L.ro_fnv1a64.restype = C.c_uint64
         L.ro_fnv1a64.argtypes = [u64p, C.c_size_t]
         _lib = L
@@ -244,6 +249,30 @@ class Oracle:
         o = np.zeros(nl * self.n, dtype=np.uint64)
         self.L.ro_phase(self.h, _p(sk), _p(np.ascontiguousarray(ct, dtype=np.uint64)), pc, nl, int(is_ntt), _p(o)); return o
 
+    # ---- Decryptor
+    def secret_key_powers(self, sk, max_power):
+        o = np.zeros(max_power * self.nm * self.n, dtype=np.uint64)
+        self.L.ro_secret_key_powers(self.h, _p(np.ascontiguousarray(sk, dtype=np.uint64)), max_power, _p(o)); return o
+
+    def decrypt_phase(self, ct, pc, nl, is_ntt, sk_powers):
+        o = np.zeros(nl * self.n, dtype=np.uint64)
+        self.L.ro_decrypt_phase(self.h, _p(np.ascontiguousarray(ct, dtype=np.uint64)), pc, nl, int(is_ntt), _p(sk_powers), _p(o)); return o
+
+    def decrypt_scale_and_round(self, phase, nl):
+        o = np.zeros(self.n, dtype=np.uint64)
+        if self.L.ro_decrypt_scale_and_round(self.h, _p(np.ascontiguousarray(phase, dtype=np.uint64)), nl, _p(o)): raise RuntimeError("ro_decrypt_scale_and_round failed")
+        return o
+
+    def decrypt_mod_t(self, phase, nl, correction_factor=1):
+        o = np.zeros(self.n, dtype=np.uint64)
+        if self.L.ro_decrypt_mod_t(self.h, _p(np.ascontiguousarray(phase, dtype=np.uint64)), nl, correction_factor, _p(o)): raise RuntimeError("ro_decrypt_mod_t failed")
+        return o
+
+    def decrypt(self, ct, pc, nl, sk_powers, correction_factor=1):
+        o = np.zeros((nl if self.scheme == CKKS else 1) * self.n, dtype=np.uint64)
+        if self.L.ro_decrypt(self.h, _p(np.ascontiguousarray(ct, dtype=np.uint64)), pc, nl, _p(sk_powers), correction_factor, _p(o)): raise RuntimeError("ro_decrypt failed")
+        return o
+
     def random_poly(self, rng, pc, nl, base=0):
         """uniform residues, [pc][nl][N], limb j reduced mod moduli[base+j]"""
         out = np.empty((pc, nl, self.n), dtype=np.uint64)
@@ -303,6 +332,8 @@ def reflib():
             getattr(R, f).argtypes = [C.c_void_p, u64p, C.c_size_t, u64p, C.c_size_t]
         R.rs_multiply_plain_raw.argtypes = [C.c_void_p, u64p, C.c_size_t, u64p, u64p, C.c_size_t, C.c_int]
         R.rs_galois_raw.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_size_t, C.c_uint64, u64p, C.c_int]
+        R.rs_decrypt_raw.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_size_t, C.c_uint64, u64p]
+        R.rs_decrypt_phase_raw.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_size_t, u64p]
         R.rs_time_op.restype = C.c_double
         R.rs_time_op.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int]
         _ref = R
@@ -390,6 +421,14 @@ class Reference:
 
     def transform_from_ntt(self, a, pc, nl):
         o = np.zeros(pc * nl * self.n, dtype=np.uint64); self._chk(self.R.rs_transform_from_ntt(self.h, _p(a), pc, _p(o), nl)); return o
+
+    def decrypt_raw(self, a, pc, nl, correction_factor=1):
+        o = np.zeros((nl if self.scheme == 2 else 1) * self.n, dtype=np.uint64)
+        self._chk(self.R.rs_decrypt_raw(self.h, _p(np.ascontiguousarray(a, dtype=np.uint64)), pc, nl, correction_factor, _p(o))); return o
+
+    def decrypt_phase_raw(self, a, pc, nl):
+        o = np.zeros(nl * self.n, dtype=np.uint64)
+        self._chk(self.R.rs_decrypt_phase_raw(self.h, _p(np.ascontiguousarray(a, dtype=np.uint64)), pc, nl, _p(o))); return o
 
     def multiply_plain_raw(self, a, pc, plain, nl, ntt_form):
         o = np.zeros(pc * nl * self.n, dtype=np.uint64)

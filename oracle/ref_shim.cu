@@ -28,6 +28,7 @@ struct RefShim {
     std::unique_ptr<KeyGenerator> keygen;
     std::unique_ptr<Evaluator> eval;
     std::unique_ptr<Encryptor> enc;
+    std::unique_ptr<Decryptor> dec;
     RelinKeys rlk; bool has_rlk = false;
     GaloisKeys glk; bool has_glk = false;
     SchemeType scheme; size_t n; bool device; double ckks_scale = 1099511627776.0;
@@ -82,6 +83,7 @@ void *rs_create(int scheme, size_t n, const unsigned *bits, size_t nbits, unsign
         h->enc.reset(new Encryptor(h->ctx));
         h->enc->set_public_key(h->keygen->create_public_key(false));
         h->enc->set_secret_key(h->keygen->secret_key());
+        h->dec.reset(new Decryptor(h->ctx, h->keygen->secret_key()));
     } catch (const std::exception &e) { h->err = e.what(); }
     return h;
 }
@@ -241,6 +243,34 @@ int rs_galois_raw(void *hh, const uint64_t *a, size_t pc, size_t nl, uint64_t el
         else cd->galois_tool().apply_ps(in.const_reference(), pc, elt, cd->parms().coeff_modulus(), res.reference());
         if (h->device) { cudaDeviceSynchronize(); res.to_host_inplace(); }
         std::memcpy(out, res.raw_pointer(), total * 8);
+    })
+}
+
+/* ---- Decryptor::decrypt on a raw ciphertext (src/decryptor.cu:233-250): BFV / BGV -> out [N], CKKS -> out [nl][N] ---- */
+int rs_decrypt_raw(void *hh, const uint64_t *a, size_t pc, size_t nl, uint64_t correction_factor, uint64_t *out) {
+    RefShim *h = (RefShim *)hh;
+    RS_TRY({
+        Ciphertext ct = make_ct(h, a, pc, nl, default_ntt_form(h));
+        ct.correction_factor() = correction_factor;
+        Plaintext p = h->dec->decrypt_new(ct);
+        if (p.on_device()) p.to_host_inplace();
+        size_t words = h->scheme == SchemeType::CKKS ? nl * h->n : h->n;
+        if (p.data().size() < words) throw std::logic_error("plaintext smaller than expected");
+        std::memcpy(out, p.data().raw_pointer(), words * 8);
+    })
+}
+/* the phase alone, in the ciphertext's form: out [nl][N]  (Decryptor::dot_product_ct_sk_array is private; CKKS decrypt returns
+ * exactly it, and for BFV the reference exposes bfv_decrypt_without_scaling_down) */
+int rs_decrypt_phase_raw(void *hh, const uint64_t *a, size_t pc, size_t nl, uint64_t *out) {
+    RefShim *h = (RefShim *)hh;
+    RS_TRY({
+        Ciphertext ct = make_ct(h, a, pc, nl, default_ntt_form(h));
+        Plaintext p;
+        if (h->scheme == SchemeType::BFV) h->dec->bfv_decrypt_without_scaling_down(ct, p);
+        else if (h->scheme == SchemeType::CKKS) p = h->dec->decrypt_new(ct);
+        else throw std::invalid_argument("phase export: BFV / CKKS only");
+        if (p.on_device()) p.to_host_inplace();
+        std::memcpy(out, p.data().raw_pointer(), nl * h->n * 8);
     })
 }
 

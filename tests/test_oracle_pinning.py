@@ -117,6 +117,31 @@ def test_oracle_reproduces_reference_golden(po, name):
         assert max(min(int(v), q0 - int(v)) for v in c) < 2 ** 16
 
 
+def test_oracle_decryptor_reproduces_reference_golden(po):
+    """Decryptor (src/decryptor.cu:27-535, rns_tool.cu:1118-1430, rns_base.cu:445-583): golden vectors from the unmodified reference"""
+    g = np.load(os.path.join(GOLD, "ref_decrypt_n256.npz"))
+    n = int(g["n"])
+    for scheme, name in ((po.BFV, "bfv"), (po.CKKS, "ckks"), (po.BGV, "bgv")):
+        moduli = g[name + "_moduli"]
+        o = po.Oracle(8, moduli, int(g[name + "_t"]) if scheme != po.CKKS else 0, scheme)
+        L = o.nm - 1
+        skp = o.secret_key_powers(g[name + "_sk"], 2)
+        assert np.array_equal(o.decrypt(g[name + "_zero"], 2, L, skp), g[name + "_zero_dec"])
+        if scheme != po.CKKS:
+            assert not g[name + "_zero_dec"].any()
+        for nl in (L, 1):
+            for pc in (2, 3):
+                key = "%s_l%d_p%d" % (name, nl, pc)
+                ct = g[key + "_ct"]
+                assert np.array_equal(o.decrypt(ct, pc, nl, skp), g[key + "_dec"]), key
+                if scheme == po.BGV:
+                    assert np.array_equal(o.decrypt(ct, pc, nl, skp, 7), g[key + "_dec_cf7"]), key
+                if scheme == po.BFV:
+                    ph = o.decrypt_phase(ct, pc, nl, False, skp)
+                    assert np.array_equal(ph, g[key + "_phase"]), key
+                    assert np.array_equal(o.decrypt_scale_and_round(ph, nl), g[key + "_dec"]), key
+
+
 # ---- (iii) live against the compiled reference --------------------------------------------------
 SURVEY_FPR = {2: ("3866d51961505bd9", "c59ae60bda39e030", "a0e0a04249a08cd3", "4a186e8776597c7e", "eb819b8149c577a2"),
               3: ("82ff3df13af52835", "2046b27467209ab9", "a967cf538de6dc20", "def3d7ec042efe31", "e11839bb23d6a573"),
@@ -145,6 +170,27 @@ def test_live_reference_fingerprints_and_oracle_parity(po, scheme):
         assert np.array_equal(o.dyadic_convolute(c, 2, c, 2, L), m)
     else:
         assert np.array_equal(o.bfv_multiply(c, c, L), m)
+
+
+@pytest.mark.parametrize("scheme,log_n,bits,t_bits", [(1, 12, [40, 40, 50, 55], 20), (1, 10, [60, 60, 60], 33), (2, 11, [50, 40, 40, 55], 20),
+                                                        (3, 12, [40, 45, 50, 55], 20), (3, 10, [60, 60], 17), (1, 9, [60] * 6, 59)])
+def test_live_reference_decryptor(po, scheme, log_n, bits, t_bits):
+    """oracle Decryptor == unmodified reference, word for word, on random ciphertexts (2 and 3 polynomials, first and last level,
+    BGV correction factors) under the reference's secret key"""
+    if not po.ref_available():
+        pytest.skip("oracle/_ref not built")
+    n = 1 << log_n
+    r = po.Reference(scheme, n, bits, t_bits=t_bits, seed=11)
+    o = po.Oracle(log_n, r.moduli, r.t if scheme != po.CKKS else 0, scheme)
+    rng = np.random.default_rng(scheme * 100 + log_n)
+    skp = o.secret_key_powers(r.secret_key(), 2)
+    for nl in (len(bits) - 1, 1):
+        for pc in (2, 3):
+            ct = o.random_poly(rng, pc, nl)
+            for cf in ((1, 5) if scheme == po.BGV else (1,)):
+                assert np.array_equal(o.decrypt(ct, pc, nl, skp, cf), r.decrypt_raw(ct, pc, nl, cf)), (nl, pc, cf)
+            if scheme != po.BGV:
+                assert np.array_equal(o.decrypt_phase(ct, pc, nl, scheme == po.CKKS, skp), r.decrypt_phase_raw(ct, pc, nl))
 
 
 @pytest.mark.parametrize("log_n,bits,t_bits", [(6, [40, 40, 40], 20), (10, [60, 40, 40, 60], 20), (9, [50, 36, 45, 60, 55], 30), (7, [60] * 6, 59)])

@@ -90,6 +90,11 @@ _SIGS.update({
     "b2_bfv_multiply": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_size_t, vp]),
     "b2_behz_bases": (C.c_int, [vp, C.c_size_t, u64p, C.POINTER(C.c_size_t), u64p]),
     "b2_scale_inv_degree": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint64, vp]),
+    "b2_secret_key_powers": (C.c_int, [vp, vp, C.c_size_t, vp, vp]),
+    "b2_decrypt_phase": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, vp, vp]),
+    "b2_decrypt_scale_and_round": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.c_size_t, C.c_size_t, vp]),
+    "b2_decrypt_mod_t": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.c_size_t, C.c_size_t, u64p, vp]),
+    "b2_decrypt": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.c_size_t, C.c_size_t, C.c_size_t, vp, u64p, vp]),
 })
 MODSWITCH_BFV, MODSWITCH_CKKS, MODSWITCH_BGV, MODSWITCH_DROP = 0, 1, 2, 3
 
@@ -307,6 +312,29 @@ class Context:
         bsk = (C.c_uint64 * (self.K + 2))(); cnt = C.c_size_t(); g = C.c_uint64()
         _chk(self.L.b2_behz_bases(self.h, nl, bsk, C.byref(cnt), C.byref(g)))
         return [int(bsk[i]) for i in range(cnt.value)], int(g.value)
+
+    # ---- Decryptor (src/decryptor.cu): lists of device tensors / pointers
+    def secret_key_powers(self, sk, max_power, out, stream=None):
+        _chk(self.L.b2_secret_key_powers(self.h, _dptr(sk), max_power, _dptr(out), self._stream(stream))); return out
+
+    @staticmethod
+    def _ptrs(ts):
+        return (vp * len(ts))(*[_dptr(t) for t in ts])
+
+    def decrypt_phase(self, cts, outs, pcount, nl, is_ntt, sk_powers, stream=None):
+        _chk(self.L.b2_decrypt_phase(self.h, self._ptrs(cts), self._ptrs(outs), len(cts), pcount, nl, int(is_ntt), _dptr(sk_powers), self._stream(stream))); return outs
+
+    def decrypt_scale_and_round(self, phases, outs, nl, stream=None):
+        _chk(self.L.b2_decrypt_scale_and_round(self.h, self._ptrs(phases), self._ptrs(outs), len(phases), nl, self._stream(stream))); return outs
+
+    def decrypt_mod_t(self, phases, outs, nl, correction_factors=None, stream=None):
+        cf = None if correction_factors is None else (C.c_uint64 * len(phases))(*[int(c) for c in correction_factors])
+        _chk(self.L.b2_decrypt_mod_t(self.h, self._ptrs(phases), self._ptrs(outs), len(phases), nl, cf, self._stream(stream))); return outs
+
+    def decrypt(self, cts, outs, pcount, nl, sk_powers, correction_factors=None, stream=None):
+        """Decryptor::decrypt_batched: BFV / BGV -> [N] words mod t per ciphertext, CKKS -> [nl][N] (NTT form)"""
+        cf = None if correction_factors is None else (C.c_uint64 * len(cts))(*[int(c) for c in correction_factors])
+        _chk(self.L.b2_decrypt(self.h, self._ptrs(cts), self._ptrs(outs), len(cts), pcount, nl, _dptr(sk_powers), cf, self._stream(stream))); return outs
 
     def scale_inv_degree(self, data, count, ncomp, scalar=1, table_base=0, stream=None):
         _chk(self.L.b2_scale_inv_degree(self.h, _dptr(data), count, ncomp, table_base, scalar, self._stream(stream))); return data

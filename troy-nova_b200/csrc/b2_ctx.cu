@@ -151,7 +151,8 @@ extern "C" b2_status b2_ctx_create(int device, const b2_params *prm, b2_ctx **ou
             }
             if (c->t > 1) invt[a] = host::invmod(c->q[a] % c->t, c->t);
         }
-        if (c->t > 1) { host::u128 r = (~(host::u128)0) / c->t; c->t_r0 = (uint64_t)r; c->t_r1 = (uint64_t)(r >> 64); c->t_ratio = c->t_r1; }
+        if (c->t > 1) { host::u128 r = (~(host::u128)0) / c->t; if ((~(host::u128)0) % c->t == c->t - 1) r += 1;   /* floor(2^128 / t), exact for powers of two too */
+            c->t_r0 = (uint64_t)r; c->t_r1 = (uint64_t)(r >> 64); c->t_ratio = c->t_r1; }
         c->h_inv_mod_t = invt;
         B2_CUDA(cudaMalloc(&c->d_inv, K * K * sizeof(Tw)));
         B2_CUDA(cudaMalloc(&c->d_inv_mod_t, K * sizeof(uint64_t)));
@@ -166,6 +167,6 @@ extern "C" b2_status b2_ctx_create(int device, const b2_params *prm, b2_ctx **ou
 extern "C" void b2_ctx_destroy(b2_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaFree(c->d_tw); cudaFree(c->d_itw); cudaFree(c->d_twd); cudaFree(c->d_itwd); cudaFree(c->d_n5); cudaFree(c->d_mods); b2::behz_release(c); cudaFree(c->d_inv); cudaFree(c->d_inv_mod_t); b2::scratch_release_all(c);
+    cudaFree(c->d_tw); cudaFree(c->d_itw); cudaFree(c->d_twd); cudaFree(c->d_itwd); cudaFree(c->d_n5); cudaFree(c->d_mods); b2::behz_release(c); b2::decrypt_release(c); cudaFree(c->d_inv); cudaFree(c->d_inv_mod_t); b2::scratch_release_all(c);
     delete c;
 }

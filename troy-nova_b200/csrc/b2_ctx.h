@@ -38,6 +38,8 @@ struct b2_ctx {
     // BEHZ (BFV multiply) auxiliary base, built lazily by the first b2_bfv_multiply: ModInfo slots K .. 2K+1 hold
     // B_0 .. B_K (K+1 primes) and m_sk; per-level constant blobs keyed by the number of ciphertext limbs
     struct b2_behz *behz = nullptr;
+    // Decryptor constants (gamma, base conversions q -> {t, gamma}), built lazily per level by b2_decrypt.cu
+    struct b2_decrypt_state *dec = nullptr;
 };
 
 // Mutable state of one (stream, host thread).  `mu` is held by an entry point for the whole time it enqueues its launches,
@@ -80,6 +82,7 @@ b2_status ensure_side(b2_scratch *sc, size_t limbs, cudaStream_t stream);
 void scratch_release_all(b2_ctx *ctx);
 int build_modulus_tables(uint64_t p, unsigned logn, Tw *T, Tw *IT, double *TD, double *ITD, ModInfo &M, uint64_t &psi_out);
 void behz_release(b2_ctx *ctx);
+void decrypt_release(b2_ctx *ctx);
 #define B2_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return b2::cuda_fail(e__, #call); } while (0)
 #define B2_REQUIRE(cond, msg) do { if (!(cond)) { b2::set_error("%s: %s", __func__, msg); return B2_ERR_INVALID_ARG; } } while (0)
 
