@@ -211,6 +211,37 @@ b2_status b2_decrypt_mod_t(b2_ctx *ctx, const uint64_t *const *phase, uint64_t *
  * 3 / 2 / 1 launches per call for any batch size. */
 b2_status b2_decrypt(b2_ctx *ctx, const uint64_t *const *ct, uint64_t *const *plain, size_t batch, size_t pcount, size_t nl, const uint64_t *sk_powers,
                      const uint64_t *correction_factors, void *stream);
+/* ---- Encryptor / RLWE sampling and the plaintext lifts (rank 3) ----
+ * b2_prng mirrors utils::RandomGenerator (src/utils/random_generator.h:45-93): AES-128 in counter mode, key = the 128-bit seed, one
+ * 16-byte block per counter value.  Every call that draws from a generator advances its counter exactly as the reference does, so
+ * a sequence of calls with the same starting state reproduces the reference's ciphertext words. */
+typedef struct { uint64_t seed_lo, seed_hi, counter_lo, counter_hi; } b2_prng;
+typedef enum { B2_SAMPLE_TERNARY = 1, B2_SAMPLE_CENTERED_BINOMIAL = 2, B2_SAMPLE_UNIFORM = 3 } b2_sample_kind;
+/* RandomGenerator::fill_bytes (random_generator.cu:128-141): `bytes` bytes at the DEVICE address out */
+b2_status b2_prng_fill(b2_ctx *ctx, b2_prng *g, void *out, size_t bytes, void *stream);
+/* RandomGenerator::sample_uint64 (host) */
+uint64_t b2_prng_sample_uint64(b2_prng *g);
+/* sample_poly_ternary / _centered_binomial / _uniform (random_generator.cu:282-505), and their _batched forms: out [count][nl][N] */
+b2_status b2_sample_poly(b2_ctx *ctx, int kind, b2_prng *g, uint64_t *out, size_t count, size_t nl, void *stream);
+/* rlwe::asymmetric_with_u_prng (src/utils/rlwe.cu:11-92) with the level handling of Encryptor::encrypt_zero_internal
+ * (src/encryptor.cu:45-98: below the key level the encryption happens one level up and is switched down).
+ * pk: DEVICE [2][K][N], NTT form, key level.  ct: DEVICE [2][nl][N].  u_prng draws u, e_prng the two noise polynomials; both may be
+ * the same object (the reference's u_prng == nullptr: everything from the context's generator). */
+b2_status b2_encrypt_zero_asymmetric(b2_ctx *ctx, const uint64_t *pk, size_t nl, int is_ntt_form, b2_prng *u_prng, b2_prng *e_prng, uint64_t *ct, void *stream);
+/* rlwe::symmetric_with_c1_prng (src/utils/rlwe.cu:218-322): sk DEVICE [K][N] NTT form; ct = (-(a s + e), a).  *seed_out (may be NULL)
+ * receives the seed of a's generator, which the reference stores in the ciphertext when save_seed != 0. */
+b2_status b2_encrypt_zero_symmetric(b2_ctx *ctx, const uint64_t *sk, size_t nl, int is_ntt_form, int save_seed, b2_prng *c1_prng, b2_prng *e_prng, uint64_t *ct,
+                                    uint64_t *seed_out, void *stream);
+/* scaling_variant::scale_up = multiply_translate_plain (src/fgk/translate_plain.cu:6-70): BFV, plain = plain_count words modulo t;
+ * dest[j][x] = from[j][x] +/- round(q/t m_x) mod q_j for x < plain_count (from == NULL: zero; from == dest allowed), [nl][N].
+ * This is the c_0 update of Encryptor::encrypt and of Evaluator::add_plain / sub_plain. */
+b2_status b2_bfv_scale_up(b2_ctx *ctx, const uint64_t *plain, size_t plain_count, size_t nl, const uint64_t *from, int subtract, uint64_t *dest, void *stream);
+/* scaling_variant::centralize (src/utils/scaling_variant.cu:326-357): plain modulo t -> centred residues modulo q_j, out [nl][N] */
+b2_status b2_centralize(b2_ctx *ctx, const uint64_t *plain, size_t plain_count, size_t nl, uint64_t *out, void *stream);
+/* Encryptor::encrypt_internal (src/encryptor.cu:247-338): BFV / BGV plain = plain_count words modulo t (nl = first level);
+ * CKKS plain = [nl][N] NTT form.  key = pk (asymmetric != 0) or sk. */
+b2_status b2_encrypt(b2_ctx *ctx, const uint64_t *plain, size_t plain_count, const uint64_t *key, int asymmetric, size_t nl, b2_prng *u_prng, b2_prng *e_prng,
+                     uint64_t *ct, void *stream);
 /* Evaluator::bfv_multiply / bfv_square device branch (src/evaluator.cu:29-116,199-282) = BEHZ RNS multiplication:
  * RNSTool::fast_b_conv_m_tilde_sm_mrq + NTT + dyadic convolution + INTT + RNSTool::fast_floor_fast_b_conv_sk
  * (src/fgk/rns_tool.cu:7-343).  a, b [batch][2][nl][N] coefficient form -> out [batch][3][nl][N] coefficient form.

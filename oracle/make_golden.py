@@ -90,8 +90,41 @@ def main_decrypt():
     print("wrote decrypt", len(g), "arrays")
 
 
+def main_encrypt():
+    """tests/golden/ref_encrypt_n256.npz: the reference's generator, samplers and Encryptor (src/utils/random_generator.cu, src/utils/rlwe.cu,
+    src/encryptor.cu) with explicit seeds: AES-CTR bytes, the three samplers, zero encryptions (asymmetric / symmetric, with and without a
+    saved seed) at the key level, the first level and the last level, and encryptions of a message, under the reference's own keys."""
+    g = {"n": N, "bits": np.array(BITS)}
+    for scheme, name in ((po.BFV, "bfv"), (po.CKKS, "ckks"), (po.BGV, "bgv")):
+        r = po.Reference(scheme, N, BITS, t_bits=20, seed=0x123)
+        K = r.nm; L = K - 1
+        rng = np.random.default_rng(3000 + scheme)
+        g[name + "_moduli"] = r.moduli; g[name + "_t"] = np.uint64(r.t); g[name + "_sk"] = r.secret_key(); g[name + "_pk"] = r.public_key()
+        st = np.array([77, 3, 9, 0], dtype=np.uint64)
+        g[name + "_bytes"] = r.prng(0, st, nbytes=16 * 7 + 3)
+        for kind, kn in ((1, "ternary"), (2, "cbd"), (3, "uniform")):
+            g["%s_%s" % (name, kn)] = r.prng(kind, st, nl=K)
+        g[name + "_state_after"] = st.copy()
+        for nl in (K, L, 1):
+            g["%s_l%d_asym" % (name, nl)] = r.encrypt_seeded(None, True, nl, 1234, 5)[0]
+            for save in (0, 1):
+                ct, seed = r.encrypt_seeded(None, False, nl, 99, 0, save_seed=bool(save))
+                g["%s_l%d_sym%d" % (name, nl, save)] = ct; g["%s_l%d_sym%d_seed" % (name, nl, save)] = np.uint64(seed)
+        if scheme == po.CKKS:
+            plain = np.concatenate([rng.integers(0, int(r.moduli[j]), size=N, dtype=np.uint64) for j in range(L)])
+        else:
+            plain = rng.integers(0, r.t, size=N // 2 + 3, dtype=np.uint64)
+        g[name + "_plain"] = plain
+        for asym in (0, 1):
+            g["%s_enc%d" % (name, asym)] = r.encrypt_seeded(plain, bool(asym), L, 4242)[0]
+    np.savez_compressed(os.path.join(OUT, "ref_encrypt_n256.npz"), **g)
+    print("wrote encrypt", len(g), "arrays")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "decrypt":
         main_decrypt()
+    elif len(sys.argv) > 1 and sys.argv[1] == "encrypt":
+        main_encrypt()
     else:
-        main(); main_decrypt()
+        main(); main_decrypt(); main_encrypt()

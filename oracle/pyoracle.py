@@ -103,6 +103,18 @@ def lib():
         L.ro_decrypt_scale_and_round.argtypes = [C.c_void_p, u64p, C.c_size_t, u64p]
         L.ro_decrypt_mod_t.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_uint64, u64p]
         L.ro_decrypt.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_size_t, u64p, C.c_uint64, u64p]
+        u8p = C.POINTER(C.c_uint8)
+        L.ro_prng_fill_bytes.argtypes = [u64p, u8p, C.c_size_t]
+        L.ro_prng_sample_uint64.restype = C.c_uint64
+        L.ro_prng_sample_uint64.argtypes = [u64p]
+        for f in ("ro_sample_poly_ternary", "ro_sample_poly_cbd", "ro_sample_poly_uniform"):
+            getattr(L, f).argtypes = [C.c_void_p, u64p, u64p, C.c_size_t]
+        L.ro_encrypt_zero_asymmetric.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_int, u64p, u64p, u64p]
+        L.ro_encrypt_zero_symmetric.restype = C.c_uint64
+        L.ro_encrypt_zero_symmetric.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_int, C.c_int, u64p, u64p, u64p]
+        L.ro_bfv_scale_up.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_size_t, u64p, C.c_int, u64p]
+        L.ro_centralize.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_size_t, u64p]
+        L.ro_encrypt.argtypes = [C.c_void_p, u64p, C.c_size_t, u64p, C.c_int, C.c_size_t, u64p, u64p, u64p]
         L.ro_fnv1a64.restype = C.c_uint64
         L.ro_fnv1a64.argtypes = [u64p, C.c_size_t]
         _lib = L
@@ -273,6 +285,49 @@ class Oracle:
         if self.L.ro_decrypt(self.h, _p(np.ascontiguousarray(ct, dtype=np.uint64)), pc, nl, _p(sk_powers), correction_factor, _p(o)): raise RuntimeError("ro_decrypt failed")
         return o
 
+    # ---- generator (state = np.uint64[4]: seed_lo, seed_hi, counter_lo, counter_hi; advanced in place), samplers, Encryptor
+    @staticmethod
+    def prng_state(seed_lo, seed_hi=0, counter=0):
+        return np.array([seed_lo, seed_hi, counter, 0], dtype=np.uint64)
+
+    def prng_fill_bytes(self, st, nbytes):
+        o = np.zeros(nbytes, dtype=np.uint8)
+        self.L.ro_prng_fill_bytes(_p(st), o.ctypes.data_as(C.POINTER(C.c_uint8)), nbytes); return o
+
+    def sample_poly(self, kind, st, nl):
+        o = np.zeros(nl * self.n, dtype=np.uint64)
+        {"ternary": self.L.ro_sample_poly_ternary, "cbd": self.L.ro_sample_poly_cbd, "uniform": self.L.ro_sample_poly_uniform}[kind](self.h, _p(st), _p(o), nl); return o
+
+    def encrypt_zero_asymmetric(self, pk, nl, is_ntt, u_st, e_st=None):
+        ct = np.zeros(2 * nl * self.n, dtype=np.uint64)
+        e_st = u_st if e_st is None else e_st
+        if self.L.ro_encrypt_zero_asymmetric(self.h, _p(pk), nl, int(is_ntt), _p(u_st), _p(e_st), _p(ct)): raise RuntimeError("ro_encrypt_zero_asymmetric failed")
+        return ct
+
+    def encrypt_zero_symmetric(self, sk, nl, is_ntt, save_seed, c1_st, e_st=None):
+        ct = np.zeros(2 * nl * self.n, dtype=np.uint64)
+        e_st = c1_st if e_st is None else e_st
+        seed = self.L.ro_encrypt_zero_symmetric(self.h, _p(sk), nl, int(is_ntt), int(save_seed), _p(c1_st), _p(e_st), _p(ct))
+        return ct, int(seed)
+
+    def bfv_scale_up(self, plain, nl, frm=None, subtract=False):
+        plain = np.ascontiguousarray(plain, dtype=np.uint64)
+        o = np.zeros(nl * self.n, dtype=np.uint64)
+        self.L.ro_bfv_scale_up(self.h, _p(plain), plain.size, nl, None if frm is None else _p(np.ascontiguousarray(frm, dtype=np.uint64)), int(subtract), _p(o)); return o
+
+    def centralize(self, plain, nl):
+        plain = np.ascontiguousarray(plain, dtype=np.uint64)
+        o = np.zeros(nl * self.n, dtype=np.uint64)
+        self.L.ro_centralize(self.h, _p(plain), plain.size, nl, _p(o)); return o
+
+    def encrypt(self, plain, key, asymmetric, nl, u_st, e_st=None):
+        plain = np.ascontiguousarray(plain, dtype=np.uint64)
+        ct = np.zeros(2 * nl * self.n, dtype=np.uint64)
+        e_st = u_st if e_st is None else e_st
+        cnt = plain.size if self.scheme != CKKS else self.n
+        if self.L.ro_encrypt(self.h, _p(plain), cnt, _p(key), int(asymmetric), nl, _p(u_st), _p(e_st), _p(ct)): raise RuntimeError("ro_encrypt failed")
+        return ct
+
     def random_poly(self, rng, pc, nl, base=0):
         """uniform residues, [pc][nl][N], limb j reduced mod moduli[base+j]"""
         out = np.empty((pc, nl, self.n), dtype=np.uint64)
@@ -334,6 +389,9 @@ def reflib():
         R.rs_galois_raw.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_size_t, C.c_uint64, u64p, C.c_int]
         R.rs_decrypt_raw.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_size_t, C.c_uint64, u64p]
         R.rs_decrypt_phase_raw.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_size_t, u64p]
+        R.rs_prng.argtypes = [C.c_void_p, C.c_int, u64p, C.c_size_t, C.c_size_t, u64p]
+        R.rs_public_key.argtypes = [C.c_void_p, u64p]
+        R.rs_encrypt_seeded.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_int, C.c_int, C.c_size_t, C.c_uint64, C.c_uint64, u64p, u64p]
         R.rs_time_op.restype = C.c_double
         R.rs_time_op.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int]
         _ref = R
@@ -421,6 +479,25 @@ class Reference:
 
     def transform_from_ntt(self, a, pc, nl):
         o = np.zeros(pc * nl * self.n, dtype=np.uint64); self._chk(self.R.rs_transform_from_ntt(self.h, _p(a), pc, _p(o), nl)); return o
+
+    def prng(self, kind, st, nl=0, nbytes=0):
+        """kind 0: fill nbytes bytes; 1 ternary, 2 centered binomial, 3 uniform over nl limbs; st (np.uint64[4]) is advanced"""
+        words = (nbytes + 7) // 8 if kind == 0 else nl * self.n
+        o = np.zeros(words, dtype=np.uint64)
+        self._chk(self.R.rs_prng(self.h, kind, _p(st), nl, nbytes, _p(o)))
+        return o.view(np.uint8)[:nbytes] if kind == 0 else o
+
+    def public_key(self):
+        o = np.zeros(2 * self.nm * self.n, dtype=np.uint64); self._chk(self.R.rs_public_key(self.h, _p(o))); return o
+
+    def encrypt_seeded(self, plain, asymmetric, nl, seed_lo, seed_hi=0, save_seed=False):
+        o = np.zeros(2 * nl * self.n, dtype=np.uint64); sd = C.c_uint64(0)
+        if plain is None:
+            self._chk(self.R.rs_encrypt_seeded(self.h, None, 0, int(asymmetric), int(save_seed), nl, seed_lo, seed_hi, _p(o), C.byref(sd)))
+        else:
+            plain = np.ascontiguousarray(plain, dtype=np.uint64)
+            self._chk(self.R.rs_encrypt_seeded(self.h, _p(plain), plain.size, int(asymmetric), int(save_seed), nl, seed_lo, seed_hi, _p(o), C.byref(sd)))
+        return o, int(sd.value)
 
     def decrypt_raw(self, a, pc, nl, correction_factor=1):
         o = np.zeros((nl if self.scheme == 2 else 1) * self.n, dtype=np.uint64)

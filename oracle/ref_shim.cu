@@ -36,6 +36,8 @@ struct RefShim {
 };
 
 static ContextDataPointer level_with(RefShim *h, size_t nl) {
+    auto kd = h->ctx->key_context_data().value();
+    if (kd->parms().coeff_modulus().size() == nl) return kd;
     auto cd = h->ctx->first_context_data().value();
     while (cd->parms().coeff_modulus().size() != nl) {
         auto nx = cd->next_context_data();
@@ -271,6 +273,62 @@ int rs_decrypt_phase_raw(void *hh, const uint64_t *a, size_t pc, size_t nl, uint
         else throw std::invalid_argument("phase export: BFV / CKKS only");
         if (p.on_device()) p.to_host_inplace();
         std::memcpy(out, p.data().raw_pointer(), nl * h->n * 8);
+    })
+}
+
+/* ---- RandomGenerator / Encryptor with an explicit generator state (src/utils/random_generator.cu, src/encryptor.cu) ---- */
+static __uint128_t u128_of(uint64_t lo, uint64_t hi) { return ((__uint128_t)hi << 64) | lo; }
+/* kind: 0 fill_bytes(words * 8 bytes; `words` may be fractional via bytes), 1 ternary, 2 centered binomial, 3 uniform; nl limbs of the key-level base.
+ * st = {seed_lo, seed_hi, counter_lo, counter_hi}, updated */
+int rs_prng(void *hh, int kind, uint64_t *st, size_t nl, size_t bytes, uint64_t *out) {
+    RefShim *h = (RefShim *)hh;
+    RS_TRY({
+        utils::RandomGenerator g(u128_of(st[0], st[1]));
+        g.set_counter(u128_of(st[2], st[3]));
+        auto mods = h->ctx->key_context_data().value()->parms().coeff_modulus();
+        utils::Array<Modulus> hm = utils::Array<Modulus>::create_and_copy_from_slice(mods, false, nullptr);
+        if (kind == 0) g.fill_bytes(Slice<uint8_t>((uint8_t *)out, bytes, false, nullptr));
+        else {
+            Slice<uint64_t> d(out, nl * h->n, false, nullptr);
+            if (kind == 1) g.sample_poly_ternary(d, h->n, hm.const_slice(0, nl));
+            else if (kind == 2) g.sample_poly_centered_binomial(d, h->n, hm.const_slice(0, nl));
+            else g.sample_poly_uniform(d, h->n, hm.const_slice(0, nl));
+        }
+        __uint128_t c = g.get_counter();
+        st[2] = (uint64_t)c; st[3] = (uint64_t)(c >> 64);
+    })
+}
+int rs_public_key(void *hh, uint64_t *out) { /* [2][K][N], NTT form */
+    RefShim *h = (RefShim *)hh;
+    RS_TRY(export_ct(h->enc->public_key().as_ciphertext(), out))
+}
+/* the context's generator is reset to (seed, counter 0) first, so the call is a deterministic function of its arguments.
+ * plain == NULL: encryption of zero at the level with nl limbs.  Otherwise BFV / BGV: plain = plain_count words modulo t (no parms_id);
+ * CKKS: plain = [nl][N] NTT form at the level with nl limbs.  out [2][nl][N]; *seed_out = the saved seed (symmetric + save_seed) */
+int rs_encrypt_seeded(void *hh, const uint64_t *plain, size_t plain_count, int asymmetric, int save_seed, size_t nl, uint64_t seed_lo, uint64_t seed_hi,
+                      uint64_t *out, uint64_t *seed_out) {
+    RefShim *h = (RefShim *)hh;
+    RS_TRY({
+        h->ctx->random_generator().reset_seed(u128_of(seed_lo, seed_hi));
+        auto cd = level_with(h, nl);
+        Ciphertext c;
+        if (!plain) {
+            c = asymmetric ? h->enc->encrypt_zero_asymmetric_new(cd->parms_id()) : h->enc->encrypt_zero_symmetric_new(save_seed != 0, cd->parms_id());
+        } else {
+            Plaintext p;
+            if (h->scheme == SchemeType::CKKS) {
+                p.resize_rns(*h->ctx, cd->parms_id(), false, false);
+                std::memcpy(p.data().raw_pointer(), plain, nl * h->n * 8);
+                p.is_ntt_form() = true; p.scale() = h->ckks_scale;
+            } else {
+                p.resize(plain_count);
+                std::memcpy(p.data().raw_pointer(), plain, plain_count * 8);
+            }
+            if (h->device) p.to_device_inplace();
+            c = asymmetric ? h->enc->encrypt_asymmetric_new(p) : h->enc->encrypt_symmetric_new(p, save_seed != 0);
+        }
+        if (seed_out) *seed_out = c.seed();
+        export_ct(c, out);
     })
 }
 

@@ -640,3 +640,4 @@ u64 ro_fnv1a64(const u64 *w, size_t n) {
 
 #include "rns_oracle_behz.inc"
 #include "rns_oracle_decrypt.inc"
+#include "rns_oracle_encrypt.inc"

@@ -142,6 +142,35 @@ def test_oracle_decryptor_reproduces_reference_golden(po):
                     assert np.array_equal(o.decrypt_scale_and_round(ph, nl), g[key + "_dec"]), key
 
 
+def test_oracle_encryptor_reproduces_reference_golden(po):
+    """generator, samplers, Encryptor (src/utils/random_generator.cu:12-505, src/utils/rlwe.cu:11-322, src/encryptor.cu:12-338): golden
+    vectors from the unmodified reference with explicit seeds"""
+    g = np.load(os.path.join(GOLD, "ref_encrypt_n256.npz"))
+    for scheme, name in ((po.BFV, "bfv"), (po.CKKS, "ckks"), (po.BGV, "bgv")):
+        o = po.Oracle(8, g[name + "_moduli"], int(g[name + "_t"]) if scheme != po.CKKS else 0, scheme)
+        K = o.nm; L = K - 1
+        st = o.prng_state(77, 3, 9)
+        assert np.array_equal(o.prng_fill_bytes(st, 16 * 7 + 3), g[name + "_bytes"])
+        for kn in ("ternary", "cbd", "uniform"):
+            assert np.array_equal(o.sample_poly(kn, st, K), g["%s_%s" % (name, kn)]), kn
+        assert np.array_equal(st, g[name + "_state_after"])
+        pk, sk = g[name + "_pk"], g[name + "_sk"]
+        ntt = scheme != po.BFV
+        for nl in (K, L, 1):
+            assert np.array_equal(o.encrypt_zero_asymmetric(pk, nl, ntt, o.prng_state(1234, 5)), g["%s_l%d_asym" % (name, nl)]), (name, nl)
+            for save in (0, 1):
+                ct, seed = o.encrypt_zero_symmetric(sk, nl, ntt, save, o.prng_state(99))
+                assert np.array_equal(ct, g["%s_l%d_sym%d" % (name, nl, save)]), (name, nl, save)
+                assert (seed if save else 0) == int(g["%s_l%d_sym%d_seed" % (name, nl, save)])
+        for asym in (0, 1):
+            assert np.array_equal(o.encrypt(g[name + "_plain"], pk if asym else sk, asym, L, o.prng_state(4242)), g["%s_enc%d" % (name, asym)]), (name, asym)
+        # and the loop closes inside the oracle: decrypt(encrypt(m)) == m
+        if scheme != po.CKKS:
+            m = g[name + "_plain"]
+            dec = o.decrypt(g[name + "_enc1"], 2, L, o.secret_key_powers(sk, 1))
+            assert np.array_equal(dec[:m.size], m) and not dec[m.size:].any()
+
+
 # ---- (iii) live against the compiled reference --------------------------------------------------
 SURVEY_FPR = {2: ("3866d51961505bd9", "c59ae60bda39e030", "a0e0a04249a08cd3", "4a186e8776597c7e", "eb819b8149c577a2"),
               3: ("82ff3df13af52835", "2046b27467209ab9", "a967cf538de6dc20", "def3d7ec042efe31", "e11839bb23d6a573"),
@@ -191,6 +220,35 @@ def test_live_reference_decryptor(po, scheme, log_n, bits, t_bits):
                 assert np.array_equal(o.decrypt(ct, pc, nl, skp, cf), r.decrypt_raw(ct, pc, nl, cf)), (nl, pc, cf)
             if scheme != po.BGV:
                 assert np.array_equal(o.decrypt_phase(ct, pc, nl, scheme == po.CKKS, skp), r.decrypt_phase_raw(ct, pc, nl))
+
+
+@pytest.mark.parametrize("scheme,bits,t_bits", [(1, [40, 40, 50, 55], 20), (2, [50, 40, 40, 55], 20), (3, [40, 45, 50, 55], 20), (1, [60, 60, 60], 33), (3, [60] * 4, 59)])
+def test_live_reference_encryptor(po, scheme, bits, t_bits):
+    """oracle generator / samplers / Encryptor == unmodified reference with the same seeds, word for word"""
+    if not po.ref_available():
+        pytest.skip("oracle/_ref not built")
+    n, logn = 1024, 10
+    r = po.Reference(scheme, n, bits, t_bits=t_bits)
+    o = po.Oracle(logn, r.moduli, r.t if scheme != po.CKKS else 0, scheme)
+    K, L = r.nm, r.nm - 1
+    st = o.prng_state(77, 3, 2 ** 64 - 3); st2 = st.copy()          # the counter crosses a 64-bit boundary
+    assert np.array_equal(r.prng(0, st, nbytes=16 * 7 + 3), o.prng_fill_bytes(st2, 16 * 7 + 3)) and np.array_equal(st, st2)
+    for kind, name in ((1, "ternary"), (2, "cbd"), (3, "uniform")):
+        assert np.array_equal(r.prng(kind, st, nl=K), o.sample_poly(name, st2, K)), name
+        assert np.array_equal(st, st2), name
+    pk, sk = r.public_key(), r.secret_key()
+    ntt = scheme != po.BFV
+    for nl in (K, L, 1):
+        assert np.array_equal(r.encrypt_seeded(None, True, nl, 1234, 5)[0], o.encrypt_zero_asymmetric(pk, nl, ntt, o.prng_state(1234, 5))), ("asym", nl)
+        for save in (False, True):
+            want, seed = r.encrypt_seeded(None, False, nl, 99, 0, save_seed=save)
+            got, gseed = o.encrypt_zero_symmetric(sk, nl, ntt, save, o.prng_state(99))
+            assert np.array_equal(want, got) and seed == (gseed if save else 0), ("sym", nl, save)
+    rng = np.random.default_rng(scheme)
+    plains = [o.random_poly(rng, 1, L)] if scheme == po.CKKS else [rng.integers(0, r.t, size=c, dtype=np.uint64) for c in (n, n // 2 + 3)]
+    for plain in plains:
+        for asym in (True, False):
+            assert np.array_equal(r.encrypt_seeded(plain, asym, L, 4242)[0], o.encrypt(plain, pk if asym else sk, asym, L, o.prng_state(4242))), ("enc", asym)
 
 
 @pytest.mark.parametrize("log_n,bits,t_bits", [(6, [40, 40, 40], 20), (10, [60, 40, 40, 60], 20), (9, [50, 36, 45, 60, 55], 30), (7, [60] * 6, 59)])

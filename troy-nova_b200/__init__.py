@@ -90,6 +90,14 @@ _SIGS.update({
     "b2_bfv_multiply": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_size_t, vp]),
     "b2_behz_bases": (C.c_int, [vp, C.c_size_t, u64p, C.POINTER(C.c_size_t), u64p]),
     "b2_scale_inv_degree": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint64, vp]),
+    "b2_prng_fill": (C.c_int, [vp, vp, vp, C.c_size_t, vp]),
+    "b2_prng_sample_uint64": (C.c_uint64, [vp]),
+    "b2_sample_poly": (C.c_int, [vp, C.c_int, vp, vp, C.c_size_t, C.c_size_t, vp]),
+    "b2_encrypt_zero_asymmetric": (C.c_int, [vp, vp, C.c_size_t, C.c_int, vp, vp, vp, vp]),
+    "b2_encrypt_zero_symmetric": (C.c_int, [vp, vp, C.c_size_t, C.c_int, C.c_int, vp, vp, vp, u64p, vp]),
+    "b2_bfv_scale_up": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, vp, C.c_int, vp, vp]),
+    "b2_centralize": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, vp, vp]),
+    "b2_encrypt": (C.c_int, [vp, vp, C.c_size_t, vp, C.c_int, C.c_size_t, vp, vp, vp, vp]),
     "b2_secret_key_powers": (C.c_int, [vp, vp, C.c_size_t, vp, vp]),
     "b2_decrypt_phase": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, vp, vp]),
     "b2_decrypt_scale_and_round": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.c_size_t, C.c_size_t, vp]),
@@ -97,6 +105,18 @@ _SIGS.update({
     "b2_decrypt": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.c_size_t, C.c_size_t, C.c_size_t, vp, u64p, vp]),
 })
 MODSWITCH_BFV, MODSWITCH_CKKS, MODSWITCH_BGV, MODSWITCH_DROP = 0, 1, 2, 3
+SAMPLE_TERNARY, SAMPLE_CENTERED_BINOMIAL, SAMPLE_UNIFORM = 1, 2, 3
+
+
+class Prng(C.Structure):
+    """utils::RandomGenerator state (src/utils/random_generator.h:45-93): AES-128-CTR, advanced in place by every call that draws from it"""
+    _fields_ = [("seed_lo", C.c_uint64), ("seed_hi", C.c_uint64), ("counter_lo", C.c_uint64), ("counter_hi", C.c_uint64)]
+
+    def __init__(self, seed_lo=0, seed_hi=0, counter=0):
+        super().__init__(seed_lo, seed_hi, counter & 0xFFFFFFFFFFFFFFFF, counter >> 64)
+
+    def state(self):
+        return (self.seed_lo, self.seed_hi, self.counter_lo, self.counter_hi)
 
 
 class _Params(C.Structure):
@@ -312,6 +332,36 @@ class Context:
         bsk = (C.c_uint64 * (self.K + 2))(); cnt = C.c_size_t(); g = C.c_uint64()
         _chk(self.L.b2_behz_bases(self.h, nl, bsk, C.byref(cnt), C.byref(g)))
         return [int(bsk[i]) for i in range(cnt.value)], int(g.value)
+
+    # ---- generator, samplers, Encryptor (src/utils/random_generator.cu, src/utils/rlwe.cu, src/encryptor.cu)
+    def prng_fill(self, g, out, nbytes, stream=None):
+        _chk(self.L.b2_prng_fill(self.h, C.byref(g), _dptr(out), nbytes, self._stream(stream))); return out
+
+    def prng_sample_uint64(self, g):
+        return int(self.L.b2_prng_sample_uint64(C.byref(g)))
+
+    def sample_poly(self, kind, g, out, nl, count=1, stream=None):
+        _chk(self.L.b2_sample_poly(self.h, kind, C.byref(g), _dptr(out), count, nl, self._stream(stream))); return out
+
+    def encrypt_zero_asymmetric(self, pk, nl, is_ntt, ct, u_prng, e_prng=None, stream=None):
+        e_prng = u_prng if e_prng is None else e_prng
+        _chk(self.L.b2_encrypt_zero_asymmetric(self.h, _dptr(pk), nl, int(is_ntt), C.byref(u_prng), C.byref(e_prng), _dptr(ct), self._stream(stream))); return ct
+
+    def encrypt_zero_symmetric(self, sk, nl, is_ntt, ct, c1_prng, e_prng=None, save_seed=False, stream=None):
+        e_prng = c1_prng if e_prng is None else e_prng
+        seed = C.c_uint64(0)
+        _chk(self.L.b2_encrypt_zero_symmetric(self.h, _dptr(sk), nl, int(is_ntt), int(save_seed), C.byref(c1_prng), C.byref(e_prng), _dptr(ct), C.byref(seed), self._stream(stream)))
+        return int(seed.value)
+
+    def bfv_scale_up(self, plain, plain_count, nl, dest, frm=None, subtract=False, stream=None):
+        _chk(self.L.b2_bfv_scale_up(self.h, _dptr(plain), plain_count, nl, None if frm is None else _dptr(frm), int(subtract), _dptr(dest), self._stream(stream))); return dest
+
+    def centralize(self, plain, plain_count, nl, out, stream=None):
+        _chk(self.L.b2_centralize(self.h, _dptr(plain), plain_count, nl, _dptr(out), self._stream(stream))); return out
+
+    def encrypt(self, plain, plain_count, key, asymmetric, nl, ct, u_prng, e_prng=None, stream=None):
+        e_prng = u_prng if e_prng is None else e_prng
+        _chk(self.L.b2_encrypt(self.h, _dptr(plain), plain_count, _dptr(key), int(asymmetric), nl, C.byref(u_prng), C.byref(e_prng), _dptr(ct), self._stream(stream))); return ct
 
     # ---- Decryptor (src/decryptor.cu): lists of device tensors / pointers
     def secret_key_powers(self, sk, max_power, out, stream=None):

@@ -83,6 +83,7 @@ void scratch_release_all(b2_ctx *ctx);
 int build_modulus_tables(uint64_t p, unsigned logn, Tw *T, Tw *IT, double *TD, double *ITD, ModInfo &M, uint64_t &psi_out);
 void behz_release(b2_ctx *ctx);
 void decrypt_release(b2_ctx *ctx);
+b2_status mod_switch_locked(b2_ctx *ctx, b2_scratch *sc, const u64 *in, u64 *out, size_t count, size_t nl, int kind, size_t ws_off, cudaStream_t stream);
 #define B2_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return b2::cuda_fail(e__, #call); } while (0)
 #define B2_REQUIRE(cond, msg) do { if (!(cond)) { b2::set_error("%s: %s", __func__, msg); return B2_ERR_INVALID_ARG; } } while (0)
 
