@@ -35,7 +35,9 @@ def test_host_mirror_script(po, scheme, tmp_path):
     a = o.random_poly(rng, 2, L); b = o.random_poly(rng, 2, L)
     plain = o.random_poly(rng, 1, L)
     hdr = np.array([scheme, o.log_n, K, o.t, len(gelts)] + gelts + [int(m) for m in o.moduli], dtype=np.uint64)
-    blob = np.concatenate([hdr, relin] + [gkeys[g] for g in gelts] + [a, b, plain])
+    sk, pk = o.random_poly(rng, 1, K), o.random_poly(rng, 2, K)
+    msg = o.random_poly(rng, 1, L) if scheme == 2 else rng.integers(0, o.t, size=n, dtype=np.uint64)
+    blob = np.concatenate([hdr, relin] + [gkeys[g] for g in gelts] + [a, b, plain, sk, pk, msg])
     fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
     blob.tofile(fin)
     res = subprocess.run([DRIVER, str(fin), str(fout)], capture_output=True, text=True, timeout=300)
@@ -71,9 +73,23 @@ def test_host_mirror_script(po, scheme, tmp_path):
     want += [("multiply_plain coefficient x coefficient", o.ntt_inv(mp_ntt.copy(), 2, L)), ("multiply_plain ntt x coefficient", mp_ntt),
              ("multiply_plain_batched[0]", mp_ntt), ("multiply_plain_batched[1]", mpb_ntt),
              ("multiply_plain_accumulate d0 (repeated destination)", both), ("multiply_plain_accumulate d1 (+= second call)", both)]
+    # ---- Encryptor / Decryptor / add_plain: one generator (seed 4242) drives the three encryptions in order
+    st = o.prng_state(4242)
+    c1 = o.encrypt(msg, pk, True, L, st)
+    c2 = o.encrypt(msg, sk, False, L, st)
+    z, zseed = o.encrypt_zero_symmetric(sk, 1, is_ntt, True, st)
+    skp = o.secret_key_powers(sk, 2)
+    prod = mul(c1, c2)
+    want += [("encrypt_asymmetric", c1), ("encrypt_symmetric", c2), ("encrypt_zero_symmetric (saved seed, last level)", z), ("saved seed", np.array([zseed], dtype=np.uint64)),
+             ("decrypt", o.decrypt(c1, 2, L, skp)), ("decrypt of a product", o.decrypt(prod, 3, L, skp)),
+             ("decrypt_batched[0]", o.decrypt(c2, 2, L, skp)), ("decrypt_batched[1]", o.decrypt(c1, 2, L, skp))]
+    if scheme == 1:
+        want += [("add_plain", np.concatenate([o.bfv_scale_up(msg, L, c1[:w]), c1[w:]])), ("sub_plain", np.concatenate([o.bfv_scale_up(msg, L, c1[:w], True), c1[w:]]))]
+    elif scheme == 2:
+        want += [("add_plain", np.concatenate([o.add(c1[:w], msg, 1, L), c1[w:]])), ("sub_plain", np.concatenate([o.sub(c1[:w], msg, 1, L), c1[w:]]))]
     pos = 0
     for name, exp in want:
         got = out[pos:pos + exp.size]; pos += exp.size
         assert np.array_equal(got, exp), f"{name} differs from the oracle (scheme {scheme})"
     probes = out[pos:]
-    assert probes.tolist() == [1, 0, 1, 1, 1, 1], f"error behaviour probes: {probes.tolist()}"
+    assert probes.tolist() == [1, 0, 1, 1, 1, 1] + [1, 1, 1, 1], f"error behaviour probes: {probes.tolist()}"

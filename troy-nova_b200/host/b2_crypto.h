@@ -1,0 +1,103 @@
+// b2_crypto.h — C++ host mirror of the reference's key holders, RandomGenerator, Encryptor and Decryptor on the C ABI
+// of libb2rns.so.  Same names, argument meaning and error behaviour as src/encryptor.h / src/encryptor.cu, src/decryptor.h /
+// src/decryptor.cu, src/utils/random_generator.h, src/key.h.  With the same generator state the ciphertext words equal the reference's.
+// Keys are imported as raw words in the reference's layouts: secret key [K][N] and public key [2][K][N], NTT form at the key level
+// (src/key.h:9-160).  Key GENERATION stays with the reference (KeyGenerator is host-side set-up code); a public key can be
+// derived here from a secret key because it is one symmetric encryption of zero at the key level (KeyGenerator::create_public_key,
+// src/key_generator.cu:57-66).
+#pragma once
+#include <mutex>
+
+#include "b2_evaluator.h"
+
+namespace b2troy {
+
+// utils::RandomGenerator (src/utils/random_generator.h:45-93): AES-128 in counter mode keyed by a 128-bit seed
+class RandomGenerator {
+public:
+    RandomGenerator() : RandomGenerator(0, 0) {}
+    explicit RandomGenerator(uint64_t seed_lo, uint64_t seed_hi = 0) { st_.seed_lo = seed_lo; st_.seed_hi = seed_hi; st_.counter_lo = 0; st_.counter_hi = 0; }
+    void reset_seed(uint64_t seed_lo, uint64_t seed_hi = 0) { st_.seed_lo = seed_lo; st_.seed_hi = seed_hi; st_.counter_lo = 0; st_.counter_hi = 0; }
+    void set_counter(uint64_t lo, uint64_t hi = 0) { st_.counter_lo = lo; st_.counter_hi = hi; }
+    uint64_t counter_lo() const { return st_.counter_lo; }
+    uint64_t counter_hi() const { return st_.counter_hi; }
+    uint64_t sample_uint64() { return b2_prng_sample_uint64(&st_); }
+    b2_prng *raw() { return &st_; }
+
+private:
+    b2_prng st_;
+};
+
+// src/key.h: SecretKey = plaintext [K][N] in NTT form; PublicKey = ciphertext [2][K][N] in NTT form, both at the key level
+class SecretKey {
+public:
+    SecretKey() = default;
+    static SecretKey from_host(const HeContextPointer &ctx, const uint64_t *words);
+    const uint64_t *data() const { return buf_.data(); }
+    const HeContextPointer &context() const { return ctx_; }
+    bool empty() const { return buf_.size() == 0; }
+private:
+    HeContextPointer ctx_;
+    DeviceArray buf_;
+};
+class PublicKey {
+public:
+    PublicKey() = default;
+    static PublicKey from_host(const HeContextPointer &ctx, const uint64_t *words);
+    // KeyGenerator::create_public_key: one symmetric zero encryption at the key level, NTT form (src/key_generator.cu:57-66)
+    static PublicKey create(const HeContextPointer &ctx, const SecretKey &sk, RandomGenerator &prng);
+    const uint64_t *data() const { return buf_.data(); }
+    std::vector<uint64_t> to_host() const;
+    bool empty() const { return buf_.size() == 0; }
+private:
+    HeContextPointer ctx_;
+    DeviceArray buf_;
+};
+
+// src/encryptor.h.  `prng` is the context's generator of the reference (HeContext::random_generator()): it supplies the noise and, when no
+// u_prng is passed, everything else.  Levels are named by their number of limbs (the reference's parms_id); 0 = the first level.
+class Encryptor {
+public:
+    Encryptor(HeContextPointer context, uint64_t seed_lo = 0, uint64_t seed_hi = 0) : context_(std::move(context)), prng_(seed_lo, seed_hi) {}
+    void set_public_key(PublicKey pk) { public_key_ = std::move(pk); }
+    void set_secret_key(SecretKey sk) { secret_key_ = std::move(sk); }
+    RandomGenerator &random_generator() { return prng_; }
+
+    void encrypt_zero_asymmetric(Ciphertext &destination, size_t coeff_modulus_size = 0, RandomGenerator *u_prng = nullptr);
+    void encrypt_zero_symmetric(bool save_seed, Ciphertext &destination, size_t coeff_modulus_size = 0, RandomGenerator *u_prng = nullptr);
+    void encrypt_asymmetric(const Plaintext &plain, Ciphertext &destination, RandomGenerator *u_prng = nullptr);
+    void encrypt_symmetric(const Plaintext &plain, bool save_seed, Ciphertext &destination, RandomGenerator *u_prng = nullptr);
+    Ciphertext encrypt_zero_asymmetric_new(size_t coeff_modulus_size = 0, RandomGenerator *u_prng = nullptr) { Ciphertext d; encrypt_zero_asymmetric(d, coeff_modulus_size, u_prng); return d; }
+    Ciphertext encrypt_zero_symmetric_new(bool save_seed, size_t coeff_modulus_size = 0, RandomGenerator *u_prng = nullptr) { Ciphertext d; encrypt_zero_symmetric(save_seed, d, coeff_modulus_size, u_prng); return d; }
+    Ciphertext encrypt_asymmetric_new(const Plaintext &plain, RandomGenerator *u_prng = nullptr) { Ciphertext d; encrypt_asymmetric(plain, d, u_prng); return d; }
+    Ciphertext encrypt_symmetric_new(const Plaintext &plain, bool save_seed, RandomGenerator *u_prng = nullptr) { Ciphertext d; encrypt_symmetric(plain, save_seed, d, u_prng); return d; }
+
+private:
+    void encrypt_zero_internal(size_t nl, bool is_ntt_form, bool is_asymmetric, bool save_seed, RandomGenerator *u_prng, Ciphertext &destination);
+    void encrypt_internal(const Plaintext &plain, bool is_asymmetric, bool save_seed, RandomGenerator *u_prng, Ciphertext &destination);
+    HeContextPointer context_;
+    RandomGenerator prng_;
+    PublicKey public_key_;
+    SecretKey secret_key_;
+};
+
+// src/decryptor.h: holds the powers of the secret key (NTT form), extended on demand under a lock as the reference does
+class Decryptor {
+public:
+    Decryptor(HeContextPointer context, const SecretKey &secret_key);
+    void decrypt(const Ciphertext &encrypted, Plaintext &destination) const;
+    Plaintext decrypt_new(const Ciphertext &encrypted) const { Plaintext p; decrypt(encrypted, p); return p; }
+    // one call for the whole batch: 3 (BFV) / 2 (BGV) / 1 (CKKS) launches; all ciphertexts of one level and size
+    void decrypt_batched(const std::vector<const Ciphertext *> &encrypted, const std::vector<Plaintext *> &destination) const;
+    // c_0 + sum c_k s^k in the form of the ciphertext (bfv_decrypt_without_scaling_down / the CKKS result), as an RNS plaintext
+    void phase(const Ciphertext &encrypted, Plaintext &destination) const;
+
+private:
+    const uint64_t *powers(size_t max_power) const;
+    HeContextPointer context_;
+    mutable std::mutex mu_;
+    mutable DeviceArray powers_;
+    mutable size_t n_powers_ = 0;
+};
+
+}  // namespace b2troy

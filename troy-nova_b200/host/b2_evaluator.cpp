@@ -80,7 +80,7 @@ Ciphertext Ciphertext::from_host(const HeContextPointer &ctx, const uint64_t *wo
 }
 Ciphertext Ciphertext::clone() const {
     Ciphertext r;
-    r.ctx_ = ctx_; r.polys_ = polys_; r.limbs_ = limbs_; r.ntt_ = ntt_; r.scale_ = scale_; r.cf_ = cf_;
+    r.ctx_ = ctx_; r.polys_ = polys_; r.limbs_ = limbs_; r.ntt_ = ntt_; r.scale_ = scale_; r.cf_ = cf_; r.seed_ = seed_;
     r.buf_ = buf_.clone();
     return r;
 }
@@ -89,12 +89,34 @@ std::vector<uint64_t> Ciphertext::to_host() const {
     if (!v.empty()) buf_.download(v.data(), v.size());
     return v;
 }
-Plaintext Plaintext::from_host(const HeContextPointer &ctx, const uint64_t *words, size_t coeff_modulus_size, bool is_ntt_form) {
+Plaintext Plaintext::rns(const HeContextPointer &ctx, size_t coeff_modulus_size, bool is_ntt_form) {
+    if (coeff_modulus_size == 0 || coeff_modulus_size > ctx->key_modulus_size()) throw std::invalid_argument("[Plaintext::rns] coeff_modulus_size out of range for this context.");
     Plaintext p;
-    p.ctx_ = ctx; p.limbs_ = coeff_modulus_size; p.ntt_ = is_ntt_form;
+    p.ctx_ = ctx; p.limbs_ = coeff_modulus_size; p.coeff_count_ = ctx->poly_modulus_degree(); p.ntt_ = is_ntt_form;
     p.buf_ = DeviceArray(ctx, coeff_modulus_size * ctx->poly_modulus_degree());
+    return p;
+}
+Plaintext Plaintext::mod_t(const HeContextPointer &ctx, size_t coeff_count) {
+    if (coeff_count == 0 || coeff_count > ctx->poly_modulus_degree()) throw std::invalid_argument("[Plaintext::mod_t] coeff_count must be in [1, N].");
+    Plaintext p;
+    p.ctx_ = ctx; p.limbs_ = 0; p.coeff_count_ = coeff_count; p.ntt_ = false;
+    p.buf_ = DeviceArray(ctx, (coeff_count + 1) & ~(size_t)1);
+    return p;
+}
+Plaintext Plaintext::from_host(const HeContextPointer &ctx, const uint64_t *words, size_t coeff_modulus_size, bool is_ntt_form) {
+    Plaintext p = rns(ctx, coeff_modulus_size, is_ntt_form);
     p.buf_.upload(words, p.buf_.size());
     return p;
+}
+Plaintext Plaintext::from_host_mod_t(const HeContextPointer &ctx, const uint64_t *words, size_t coeff_count) {
+    Plaintext p = mod_t(ctx, coeff_count);
+    p.buf_.upload(words, coeff_count);
+    return p;
+}
+std::vector<uint64_t> Plaintext::to_host() const {
+    std::vector<uint64_t> v(is_mod_t() ? coeff_count_ : buf_.size());
+    if (!v.empty()) buf_.download(v.data(), v.size());
+    return v;
 }
 
 // ---- keys -------------------------------------------------------------------------------------------------------------------
@@ -451,6 +473,28 @@ static void transform_batched(const HeContextPointer &ctx, const std::vector<Cip
 }
 void Evaluator::transform_to_ntt_inplace_batched(const std::vector<Ciphertext *> &es) const { transform_batched(context_, es, true); }
 void Evaluator::transform_from_ntt_inplace_batched(const std::vector<Ciphertext *> &es) const { transform_batched(context_, es, false); }
+
+// Evaluator::translate_plain (src/evaluator_translate_plain.cu:95-170)
+void Evaluator::translate_plain(const Ciphertext &e, const Plaintext &p, Ciphertext &d, bool subtract) const {
+    check_ct("[Evaluator::translate_plain]", e);
+    if (e.contains_seed()) throw std::invalid_argument("[Evaluator::translate_plain] Ciphertext contains a seed; expand it first.");
+    const SchemeType scheme = context_->scheme();
+    if (scheme == SchemeType::BGV) throw std::logic_error("[Evaluator::translate_plain] BGV add_plain is not mirrored (needs the scalar product modulo t).");
+    if (e.is_ntt_form() != p.is_ntt_form()) throw std::invalid_argument("[Evaluator::translate_plain] Plaintext and ciphertext are not in the same NTT form.");
+    if (scheme == SchemeType::BFV && p.is_mod_t() && e.is_ntt_form()) throw std::invalid_argument("[Evaluator::translate_plain] When plain is mod t, encrypted must not be in NTT form.");
+    if (scheme == SchemeType::CKKS) {
+        if (!e.is_ntt_form()) throw std::invalid_argument("[Evaluator::translate_plain_inplace] Ciphertext is not in NTT form.");
+        if (std::fabs(p.scale() - e.scale()) > 1e-9 * std::fabs(e.scale())) throw std::invalid_argument("[Evaluator::translate_plain] Plaintext scale is not equal to the scale of the ciphertext.");
+    }
+    if (!p.is_mod_t() && p.coeff_modulus_size() != e.coeff_modulus_size()) throw std::invalid_argument("[Evaluator::translate_plain] Plaintext and ciphertext parameters do not match.");
+    const size_t L = e.coeff_modulus_size();
+    b2_ctx *c = context_->raw();
+    Ciphertext r = e.clone();
+    if (p.is_mod_t()) check(b2_bfv_scale_up(c, p.data(), p.coeff_count(), L, r.poly(0), subtract ? 1 : 0, r.poly(0), context_->stream), "[Evaluator::translate_plain]");
+    else if (subtract) check(b2_sub(c, r.poly(0), p.data(), r.poly(0), 1, L, 0, context_->stream), "[Evaluator::translate_plain]");
+    else check(b2_add(c, r.poly(0), p.data(), r.poly(0), 1, L, 0, context_->stream), "[Evaluator::translate_plain]");
+    d = std::move(r);
+}
 
 // Evaluator::multiply_plain (src/evaluator_multiply_plain.cu:309-328): the four form combinations of the reference.  A Plaintext of this
 // mirror is RNS-limbed (what transform_plain_to_ntt / the encoders hand to the evaluator), so the coefficient-form product is

@@ -9,8 +9,8 @@
 //   Evaluator::{negate, add, sub, multiply, square, relinearize, apply_keyswitching, apply_galois, rotate_rows, rotate_vector,
 //               rotate_columns, complex_conjugate, mod_switch_to_next, rescale_to_next, transform_to_ntt, transform_from_ntt,
 //               multiply_plain, negacyclic_shift} with their _inplace / _new / _batched forms where the reference has them.
-// Not here (SURVEY §8f "next" rows): encoders, Encryptor / Decryptor / KeyGenerator, serialisation, the coefficient-form
-// plaintext pipeline (scale-up / centralize).  Keys and ciphertexts are imported as raw RNS words in the reference's own
+// Encryptor / Decryptor / RandomGenerator and the key holders are in b2_crypto.h.  Not here (SURVEY §8f "next" rows): encoders,
+// KeyGenerator, serialisation.  Keys and ciphertexts are imported as raw RNS words in the reference's own
 // layouts (ciphertext [poly][limb][N], src/ciphertext.h:211-252; key digit j = [2][K][N], src/kswitch_keys.h:36-57).
 #pragma once
 #include <cstddef>
@@ -107,6 +107,9 @@ public:
     double &scale() { return scale_; }
     uint64_t correction_factor() const { return cf_; }
     uint64_t &correction_factor() { return cf_; }
+    uint64_t seed() const { return seed_; }              // != 0: c_1 is to be re-expanded from this seed (src/ciphertext.h contains_seed)
+    uint64_t &seed() { return seed_; }
+    bool contains_seed() const { return seed_ != 0; }
     uint64_t *data() { return buf_.data(); }
     const uint64_t *data() const { return buf_.data(); }
     uint64_t *poly(size_t k) { return buf_.data() + k * limbs_ * poly_modulus_degree(); }
@@ -118,24 +121,37 @@ private:
     size_t polys_ = 0, limbs_ = 0;
     bool ntt_ = false;
     double scale_ = 1.0;
-    uint64_t cf_ = 1;
+    uint64_t cf_ = 1, seed_ = 0;
     DeviceArray buf_;
 };
 
-// src/plaintext.h — only the form the hot path consumes: an RNS plaintext [coeff_modulus_size][N] (NTT form for
-// multiply_plain; what Evaluator::transform_plain_to_ntt / the encoders produce in the reference).
+// src/plaintext.h, the two forms the reference has:
+//   RNS form  (parms_id set)      [coeff_modulus_size][N] words, coefficient or NTT form — what multiply_plain / CKKS encryption consume
+//   mod-t form (parms_id zero)    coeff_count <= N words modulo the plain modulus — BFV / BGV messages, what Decryptor returns
 class Plaintext {
 public:
     Plaintext() = default;
     static Plaintext from_host(const HeContextPointer &ctx, const uint64_t *words, size_t coeff_modulus_size, bool is_ntt_form);
+    static Plaintext from_host_mod_t(const HeContextPointer &ctx, const uint64_t *words, size_t coeff_count);
+    static Plaintext rns(const HeContextPointer &ctx, size_t coeff_modulus_size, bool is_ntt_form);      // uninitialised
+    static Plaintext mod_t(const HeContextPointer &ctx, size_t coeff_count);                             // uninitialised
+    std::vector<uint64_t> to_host() const;
+    const HeContextPointer &context() const { return ctx_; }
+    bool is_mod_t() const { return limbs_ == 0; }                        // the reference's parms_id == parms_id_zero
     size_t coeff_modulus_size() const { return limbs_; }
+    size_t coeff_count() const { return coeff_count_; }
     bool is_ntt_form() const { return ntt_; }
+    double scale() const { return scale_; }
+    double &scale() { return scale_; }
     const uint64_t *data() const { return buf_.data(); }
+    uint64_t *data() { return buf_.data(); }
+    bool empty() const { return buf_.size() == 0; }
 
 private:
     HeContextPointer ctx_;
-    size_t limbs_ = 0;
+    size_t limbs_ = 0, coeff_count_ = 0;
     bool ntt_ = false;
+    double scale_ = 1.0;
     DeviceArray buf_;
 };
 
@@ -254,6 +270,13 @@ public:
     void transform_to_ntt_inplace_batched(const std::vector<Ciphertext *> &encrypted) const;
     void transform_from_ntt_inplace_batched(const std::vector<Ciphertext *> &encrypted) const;
 
+    // ---- ct +/- pt (src/evaluator_translate_plain.cu:13-170): BFV with a mod-t plaintext (scale-up fused with the addition, one launch)
+    //      or an RNS plaintext of the same form; CKKS with an NTT-form RNS plaintext of equal scale
+    void add_plain(const Ciphertext &encrypted, const Plaintext &plain, Ciphertext &destination) const { translate_plain(encrypted, plain, destination, false); }
+    void sub_plain(const Ciphertext &encrypted, const Plaintext &plain, Ciphertext &destination) const { translate_plain(encrypted, plain, destination, true); }
+    void add_plain_inplace(Ciphertext &encrypted, const Plaintext &plain) const { Ciphertext d; translate_plain(encrypted, plain, d, false); encrypted = std::move(d); }
+    void sub_plain_inplace(Ciphertext &encrypted, const Plaintext &plain) const { Ciphertext d; translate_plain(encrypted, plain, d, true); encrypted = std::move(d); }
+
     // ---- ct x pt (src/evaluator_multiply_plain.cu:13-383): multiply_plain in all four form combinations, NTT-form batched / accumulate forms
     void multiply_plain(const Ciphertext &encrypted, const Plaintext &plain, Ciphertext &destination) const;
     void multiply_plain_inplace(Ciphertext &encrypted, const Plaintext &plain) const { Ciphertext d; multiply_plain(encrypted, plain, d); encrypted = std::move(d); }
@@ -270,6 +293,7 @@ public:
 private:
     HeContextPointer context_;
     void check_ct(const char *who, const Ciphertext &c) const;
+    void translate_plain(const Ciphertext &encrypted, const Plaintext &plain, Ciphertext &destination, bool subtract) const;
     void translate(const Ciphertext &a, const Ciphertext &b, Ciphertext &destination, bool subtract) const;
     void translate_inplace(Ciphertext &a, const Ciphertext &b, bool subtract) const;
     void switch_key_internal(const Ciphertext &encrypted, const uint64_t *target, const KSwitchKeys &keys, size_t index,

@@ -1,7 +1,8 @@
 // b2_host_test.cpp — scripted driver of the C++ host mirror (b2_evaluator.h) for tests/test_host_mirror_gpu.py.
 //   b2_host_test <input.bin> <output.bin>
 // input  (uint64 words): scheme, log_n, K, t, G, galois_element[G], moduli[K], relin key [L][2][K][N],
-//                        galois keys G x [L][2][K][N], ct a [2][L][N], ct b [2][L][N], plain [L][N] (NTT form)
+//                        galois keys G x [L][2][K][N], ct a [2][L][N], ct b [2][L][N], plain [L][N] (NTT form),
+//                        secret key [K][N], public key [2][K][N], message (BFV / BGV: [N] words modulo t; CKKS: [L][N] NTT form)
 // output (uint64 words): the result ciphertexts of the script below, concatenated, then one word per error-behaviour probe.
 // The python test recomputes every result with the CPU oracle and compares bit for bit.
 #include <cstdio>
@@ -9,7 +10,7 @@
 #include <fstream>
 #include <iostream>
 
-#include "b2_evaluator.h"
+#include "b2_crypto.h"
 
 using namespace b2troy;
 
@@ -101,6 +102,41 @@ int main(int argc, char **argv) {
             ev.multiply_plain_accumulate({&an}, {&plain}, d1, false);
             emit(d0); emit(d1);
         }
+        std::vector<uint64_t> crypto_probes;
+        {                                                                         // 25..: Encryptor / Decryptor / add_plain
+            const uint64_t *sk_words = take(K * n), *pk_words = take(2 * K * n);
+            const bool ckks = scheme == SchemeType::CKKS;
+            const uint64_t *msg_words = take(ckks ? L * n : n);
+            SecretKey sk = SecretKey::from_host(ctx, sk_words);
+            Encryptor enc(ctx, 4242);
+            auto cprobe = [&](auto &&fn) { try { fn(); crypto_probes.push_back(0); } catch (const std::invalid_argument &) { crypto_probes.push_back(1); } };
+            Plaintext msg = ckks ? Plaintext::from_host(ctx, msg_words, L, true) : Plaintext::from_host_mod_t(ctx, msg_words, n);
+            cprobe([&] { Ciphertext d; enc.encrypt_asymmetric(msg, d); });               // no public key set
+            cprobe([&] { Ciphertext d; enc.encrypt_zero_symmetric(false, d); });         // no secret key set
+            enc.set_public_key(PublicKey::from_host(ctx, pk_words));
+            enc.set_secret_key(SecretKey::from_host(ctx, sk_words));
+            Ciphertext c1 = enc.encrypt_asymmetric_new(msg);            emit(c1);        // 25
+            Ciphertext c2 = enc.encrypt_symmetric_new(msg, false);      emit(c2);        // 26: the same generator continues
+            Ciphertext z = enc.encrypt_zero_symmetric_new(true, 1);     emit(z);         // 27: last level, seed saved
+            out.push_back(z.seed());
+            Decryptor dec(ctx, sk);
+            auto emit_plain = [&](const Plaintext &p) { const std::vector<uint64_t> h = p.to_host(); out.insert(out.end(), h.begin(), h.end()); };
+            emit_plain(dec.decrypt_new(c1));                                            // 28
+            Ciphertext prod = ev.multiply_new(c1, c2);
+            emit_plain(dec.decrypt_new(prod));                                          // 29: three polynomials, s^2 computed on demand
+            {
+                Plaintext p0, p1;                                                       // 30, 31: decrypt_batched
+                dec.decrypt_batched({&c2, &c1}, {&p0, &p1});
+                emit_plain(p0); emit_plain(p1);
+            }
+            if (scheme != SchemeType::BGV) {                                            // 32, 33: add_plain / sub_plain
+                Ciphertext ap, sp;
+                ev.add_plain(c1, msg, ap); ev.sub_plain(c1, msg, sp);
+                emit(ap); emit(sp);
+            }
+            cprobe([&] { Plaintext d; dec.decrypt(z, d); });                             // contains a seed
+            cprobe([&] { Ciphertext t2 = c1.clone(); t2.is_ntt_form() = !t2.is_ntt_form(); Plaintext d; dec.decrypt(t2, d); });   // wrong form for the scheme
+        }
         // error behaviour probes: 1 = std::invalid_argument thrown as the reference does
         auto probe = [&](auto &&fn) { try { fn(); out.push_back(0); } catch (const std::invalid_argument &) { out.push_back(1); } };
         probe([&] { Ciphertext d; ev.relinearize(m, RelinKeys(ctx), d); });                       // key not present
@@ -109,6 +145,7 @@ int main(int argc, char **argv) {
         probe([&] { Ciphertext d; ev.add(a, down, d); });                                          // level mismatch
         probe([&] { Ciphertext d; if (scheme == SchemeType::CKKS) ev.rotate_rows(r, 1, gk, d); else ev.rotate_vector(r, 1, gk, d); });   // wrong scheme
         probe([&] { Ciphertext c3 = m.clone(); Ciphertext d; ev.apply_galois(c3, (size_t)gelts[0], gk, d); });                           // size-3 ciphertext
+        out.insert(out.end(), crypto_probes.begin(), crypto_probes.end());
         ctx->synchronize();
     } catch (const std::exception &e) {
         std::fprintf(stderr, "b2_host_test: %s\n", e.what());
