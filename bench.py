@@ -185,7 +185,7 @@ def gpu_reference_baseline():
     tf = r.time_op(0, NCOMP, PCOUNT, 2, 10); ti = r.time_op(1, NCOMP, PCOUNT, 2, 10)
     g = {"kind": "reference device branch (sm_100 recompile of the reference kernels, oracle/_ref)",
          "ntt_limbs_per_s": 2 * PCOUNT * NCOMP / (tf + ti), "ntt_forward_us": tf * 1e6, "ntt_inverse_us": ti * 1e6}
-    for op, name in ((3, "relinearize"), (4, "rotate"), (2, "multiply"), (5, "rescale")):
+    for op, name in ((3, "relinearize"), (4, "rotate"), (2, "multiply"), (5, "rescale"), (7, "encrypt_zero_asymmetric"), (8, "decrypt")):
         t = r.time_op(op, NCOMP - 1, 1, 2, 10)
         g[name + "_us"] = t * 1e6; g[name + "_ops_per_s"] = 1.0 / t
     return g
@@ -508,6 +508,20 @@ def main():
         extra["ntt_4200_limbs"] = {"forward_limbs_per_s": world * 4200 / tf, "inverse_limbs_per_s": world * 4200 / ti,
                                    "forward_hbm_frac": 4200 * n * 16 / tf / 1e9 / peak, "inverse_hbm_frac": 4200 * n * 16 / ti / 1e9 / peak}
         del big
+        # SURVEY §8f rank 2 on the same parameter set: Encryptor (asymmetric encryption of zero at the first level: sample u, e0, e1 with the
+        # AES-CTR generator, NTT, products with the public key, noise, switch down from the key level) and Decryptor (c0 + c1 s), data resident
+        pk = torch.empty((2, NCOMP, n), dtype=torch.int64, device="cuda")
+        for i in range(NCOMP):
+            pk[:, i, :] = torch.randint(0, moduli[i], (2, n), dtype=torch.int64, device="cuda", generator=g)
+        skp = pk[0].contiguous()
+        fresh = torch.empty((2, L, n), dtype=torch.int64, device="cuda")
+        dec = torch.empty((L, n), dtype=torch.int64, device="cuda")
+        prng = b2.Prng(2026, 7)
+        te = timed(lambda: ctx.encrypt_zero_asymmetric(pk, L, True, fresh, prng), max(3, args.steps // 2))
+        td = timed(lambda: ctx.decrypt([fresh], [dec], 2, L, skp), max(3, args.steps // 2))
+        extra["encrypt_zero_asymmetric_us"] = te * 1e6; extra["encrypt_zero_asymmetric_ops_per_s"] = world / te
+        extra["decrypt_us"] = td * 1e6; extra["decrypt_ops_per_s"] = world / td
+        del pk, skp, fresh, dec
         # the other named parameter sets (BASELINE.json configs 2 and 4), data resident, per GPU x world
         extra["c2_bfv_n16384_batch256"] = bench_c2(b2, torch, timed, local, world)
         extra["c4_bgv_n32768"] = bench_c4(b2, torch, timed, local, world)

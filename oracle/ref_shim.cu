@@ -334,7 +334,7 @@ int rs_encrypt_seeded(void *hh, const uint64_t *plain, size_t plain_count, int a
 
 /* ---- timing helper: seconds per op, averaged over iters, data resident where the context is ----
  * op: 0 ntt_fwd(pc*nc limbs, componentwise key tables base 0) 1 ntt_inv 2 multiply 3 relinearize
- *     4 rotate(1) 5 rescale/modswitch_to_next 6 square */
+ *     4 rotate(1) 5 rescale/modswitch_to_next 6 square 7 encrypt_zero_asymmetric (level nl) 8 decrypt (2 polynomials, level nl) */
 double rs_time_op(void *hh, int op, size_t nl, size_t pc, int warmup, int iters) {
     RefShim *h = (RefShim *)hh;
     try {
@@ -357,6 +357,8 @@ double rs_time_op(void *hh, int op, size_t nl, size_t pc, int warmup, int iters)
             case 4: { Ciphertext r = (h->scheme == SchemeType::CKKS) ? h->eval->rotate_vector_new(c2, 1, h->glk) : h->eval->rotate_rows_new(c2, 1, h->glk); } break;
             case 5: { Ciphertext r = (h->scheme == SchemeType::CKKS) ? h->eval->rescale_to_next_new(c2) : h->eval->mod_switch_to_next_new(c2); } break;
             case 6: { Ciphertext r = h->eval->square_new(c2); } break;
+            case 7: { Ciphertext r = h->enc->encrypt_zero_asymmetric_new(level_with(h, nl)->parms_id()); } break;
+            case 8: { Plaintext r = h->dec->decrypt_new(c2); } break;
             default: throw std::invalid_argument("bad op");
             }
             if (h->device) cudaDeviceSynchronize();

@@ -5,7 +5,7 @@
 set -u
 TAG=${1:-r02}; OUT=gpurun_out/$TAG; mkdir -p "$OUT"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > "$OUT/gpu.txt" 2>&1
-echo "== pytest -m gpu"; (time timeout -s KILL 900 python -m pytest tests -m gpu -x -q --durations=6) > "$OUT/pytest_gpu.log" 2>&1; tail -12 "$OUT/pytest_gpu.log"
+echo "== pytest -m gpu"; (time timeout -s KILL 1500 python -m pytest tests -m gpu -x -q --durations=6) > "$OUT/pytest_gpu.log" 2>&1; tail -12 "$OUT/pytest_gpu.log"
 echo "== smoke"; timeout -s KILL 200 python -c "import __graft_entry__ as g; g.smoke()" > "$OUT/smoke.log" 2>&1; tail -2 "$OUT/smoke.log"
 echo "== bench"; timeout -s KILL 700 python bench.py > "$OUT/bench.json" 2> "$OUT/bench.err"; tail -3 "$OUT/bench.err"; head -c 600 "$OUT/bench.json"; echo
 echo "== bench --impl reference"; timeout -s KILL 400 python bench.py --impl reference --steps 3 --warmup 1 > "$OUT/bench_reference.json" 2> "$OUT/bench_reference.err"; head -c 400 "$OUT/bench_reference.json"; echo

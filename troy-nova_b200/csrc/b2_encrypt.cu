@@ -94,39 +94,38 @@ __device__ __forceinline__ void dev_block(const AesKey &K, const uint8_t *sb, Ct
     for (int i = threadIdx.x; i < 256; i += blockDim.x) sb[i] = (K).sbox[i]; \
     __syncthreads();
 
-// out [count][nl][N]: polynomial c uses counter blocks [c * per, (c + 1) * per)
+// out [count][nl][N]: polynomial c uses counter blocks [c * per, (c + 1) * per).  One thread per coefficient (the 16 / 2 threads that share
+// a block each encrypt it: ~400 integer instructions, far cheaper than serialising the nl stores of 16 coefficients in one thread), so the
+// stores of a warp are 32 consecutive words per limb.
 // ternary: one block per 16 coefficients; byte % 3 -> {0, 1, q - 1}
 __global__ void __launch_bounds__(256) sample_ternary_kernel(const __grid_constant__ AesKey K, Ctr ctr, u64 *__restrict__ out, const ModInfo *__restrict__ mods,
                                                              u32 nl, u32 n, u32 count) {
     B2_AES_SMEM(K)
     const u32 per = (n + 15) / 16;
     const u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (u64)per * count) return;
-    const u32 c = (u32)(idx / per), b = (u32)(idx % per);
+    if (idx >= (u64)n * count) return;
+    const u32 c = (u32)(idx / n), x = (u32)(idx % n);
     u64 w[2];
-    dev_block(K, sb, ctr, idx, w[0], w[1]);
-    for (u32 k = 0; k < 16 && 16 * b + k < n; k++) {
-        const u32 r = (u32)((w[k >> 3] >> (8 * (k & 7))) & 0xff) % 3;
-        for (u32 j = 0; j < nl; j++) out[((u64)c * nl + j) * n + 16 * b + k] = r == 2 ? mods[j].p - 1 : r;
-    }
+    dev_block(K, sb, ctr, (u64)c * per + x / 16, w[0], w[1]);
+    const u32 k = x & 15;
+    const u32 r = (u32)((w[k >> 3] >> (8 * (k & 7))) & 0xff) % 3;
+    for (u32 j = 0; j < nl; j++) out[((u64)c * nl + j) * n + x] = r == 2 ? mods[j].p - 1 : r;
 }
 __device__ __forceinline__ int cbd_of(u64 w) {      // random_generator.cu:369-380: bytes 0-2 (21 bits) minus bytes 3-5 (21 bits)
     return __popcll(w & 0x1fffffull) - __popcll((w >> 24) & 0x1fffffull);
 }
-// centred binomial: one block per 2 coefficients; scale != 1 multiplies the sample (BGV: t e) when scaled != 0
+// centred binomial: one block per 2 coefficients
 __global__ void __launch_bounds__(256) sample_cbd_kernel(const __grid_constant__ AesKey K, Ctr ctr, u64 *__restrict__ out, const ModInfo *__restrict__ mods,
                                                          u32 nl, u32 n, u32 count) {
     B2_AES_SMEM(K)
     const u32 per = (n + 1) / 2;
     const u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (u64)per * count) return;
-    const u32 c = (u32)(idx / per), b = (u32)(idx % per);
+    if (idx >= (u64)n * count) return;
+    const u32 c = (u32)(idx / n), x = (u32)(idx % n);
     u64 w[2];
-    dev_block(K, sb, ctr, idx, w[0], w[1]);
-    for (u32 k = 0; k < 2 && 2 * b + k < n; k++) {
-        const int r = cbd_of(w[k]);
-        for (u32 j = 0; j < nl; j++) out[((u64)c * nl + j) * n + 2 * b + k] = r >= 0 ? (u64)r : mods[j].p - (u64)(-r);
-    }
+    dev_block(K, sb, ctr, (u64)c * per + x / 2, w[0], w[1]);
+    const int r = cbd_of(w[x & 1]);
+    for (u32 j = 0; j < nl; j++) out[((u64)c * nl + j) * n + x] = r >= 0 ? (u64)r : mods[j].p - (u64)(-r);
 }
 // uniform: [nl][N] words = nl * N / 2 blocks in memory order, each word reduced modulo its limb's modulus (fill_uint64s + modulo_inplace_p)
 __global__ void __launch_bounds__(256) sample_uniform_kernel(const __grid_constant__ AesKey K, Ctr ctr, u64 *__restrict__ out, const ModInfo *__restrict__ mods,
@@ -276,13 +275,13 @@ static b2_status sample_locked(b2_ctx *ctx, int kind, b2_prng *g, u64 *out, size
     const AesKey K = aes_expand(g->seed_lo, g->seed_hi);
     const Ctr c{g->counter_lo, g->counter_hi};
     if (kind == B2_SAMPLE_TERNARY) {
-        const u64 per = (n + 15) / 16, total = per * count;
-        sample_ternary_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(K, c, out, ctx->d_mods, (u32)nl, (u32)n, (u32)count);
-        advance(g, total);
+        const u64 per = (n + 15) / 16, threads = (u64)n * count;
+        sample_ternary_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(K, c, out, ctx->d_mods, (u32)nl, (u32)n, (u32)count);
+        advance(g, per * count);
     } else if (kind == B2_SAMPLE_CENTERED_BINOMIAL) {
-        const u64 per = (n + 1) / 2, total = per * count;
-        sample_cbd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(K, c, out, ctx->d_mods, (u32)nl, (u32)n, (u32)count);
-        advance(g, total);
+        const u64 per = (n + 1) / 2, threads = (u64)n * count;
+        sample_cbd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(K, c, out, ctx->d_mods, (u32)nl, (u32)n, (u32)count);
+        advance(g, per * count);
     } else {
         // consecutive polynomials are consecutive in the stream: nl * N / 2 blocks each; the limb of a word follows from its position
         const u64 per = (u64)nl * n / 2;
