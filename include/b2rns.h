@@ -242,6 +242,25 @@ b2_status b2_centralize(b2_ctx *ctx, const uint64_t *plain, size_t plain_count, 
  * CKKS plain = [nl][N] NTT form.  key = pk (asymmetric != 0) or sk. */
 b2_status b2_encrypt(b2_ctx *ctx, const uint64_t *plain, size_t plain_count, const uint64_t *key, int asymmetric, size_t nl, b2_prng *u_prng, b2_prng *e_prng,
                      uint64_t *ct, void *stream);
+/* ---- RLWE packing ----
+ * One layer of Evaluator::pack_rlwe_ciphertexts_new (src/evaluator_lwes.cu:437-479) over `pairs` (even, odd) pairs, coefficient form:
+ *   out[b] = (even + x^shift odd) + apply_galois(even - x^shift odd, galois_element)
+ * as ONE element-wise launch (shift, add, sub and the automorphism fused; the reference issues six) and ONE batched keyswitch.
+ * in: DEVICE [2 pairs][2][nl][N] (pair b = slots 2b, 2b+1); out: DEVICE [pairs][2][nl][N]; target: DEVICE scratch [pairs][nl][N]. */
+b2_status b2_pack_layer(b2_ctx *ctx, const uint64_t *in, uint64_t *out, uint64_t *target, size_t pairs, size_t nl, size_t shift, uint64_t galois_element,
+                        const b2_kswitch_key *key, void *stream);
+/* Evaluator::pack_rlwe_ciphertexts_new / pack_rlwe_ciphertexts_batched (src/evaluator_lwes.cu:305-700; what pack_lwe_ciphertexts_new :201-229
+ * and the BumbleBee / Cheetah output packing src/app/matmul.cu:572-619 call) including field_trace_inplace[_batched] (:96-130), for `groups`
+ * groups packed side by side: every layer is one fused launch + one batched keyswitch over all groups.
+ * ciphers: HOST array of sum(counts) DEVICE pointers, group after group, each [2][nl][N]; counts: HOST [groups];
+ * galois_elements / keys: the automorphism keys as parallel HOST arrays (B2_ERR_INVALID_ARG "Galois key not present" if one is missing);
+ * outs: HOST array of `groups` DEVICE pointers, each [2][nl][N], NTT form iff output_ntt_form (the reference: CKKS / BGV).
+ * The tree runs in coefficient form (CKKS too: the automorphism and the keyswitch compute the same ring element in either form, which drops
+ * the two transforms per layer of the reference's CKKS branch; BGV transforms the keyswitch operand per layer as the reference does); the
+ * stored words are the reference's. */
+b2_status b2_pack_rlwes(b2_ctx *ctx, const uint64_t *const *ciphers, const size_t *counts, size_t groups, int input_ntt_form, size_t nl, size_t shift,
+                        size_t input_interval, size_t output_interval, const uint64_t *galois_elements, const b2_kswitch_key *const *keys, size_t n_keys,
+                        int apply_field_trace, int output_ntt_form, uint64_t *const *outs, void *stream);
 /* Evaluator::bfv_multiply / bfv_square device branch (src/evaluator.cu:29-116,199-282) = BEHZ RNS multiplication:
  * RNSTool::fast_b_conv_m_tilde_sm_mrq + NTT + dyadic convolution + INTT + RNSTool::fast_floor_fast_b_conv_sk
  * (src/fgk/rns_tool.cu:7-343).  a, b [batch][2][nl][N] coefficient form -> out [batch][3][nl][N] coefficient form.

@@ -121,10 +121,44 @@ def main_encrypt():
     print("wrote encrypt", len(g), "arrays")
 
 
+PACK_CASES = ((4, 0, 64, 16, 1), (3, 0, 64, 16, 1), (8, 5, 64, 8, 0), (2, 0, 32, 16, 1), (1, 0, 64, 64, 1), (5, 3, 64, 8, 1))
+
+
+def main_pack():
+    """tests/golden/ref_pack_n64.npz: Evaluator::pack_rlwe_ciphertexts_new (src/evaluator_lwes.cu:305-491) of the unmodified reference at N = 64,
+    moduli {40, 40, 50}: random input ciphertexts, the Galois keys it used, its outputs (count, shift, input_interval, output_interval, trace)."""
+    n = 64
+    g = {"n": n, "bits": np.array([40, 40, 50]), "cases": np.array(PACK_CASES)}
+    for scheme, name in ((po.BFV, "bfv"), (po.CKKS, "ckks"), (po.BGV, "bgv")):
+        r = po.Reference(scheme, n, [40, 40, 50], t_bits=20, seed=0x123)
+        L = r.nm - 1
+        elts = sorted({(n >> k) + 1 for k in range(0, 6)} | {2 ** k + 1 for k in range(1, 7)})
+        elts = [e for e in elts if e < 2 * n]
+        r.gen_galois(elts)
+        g[name + "_moduli"] = r.moduli; g[name + "_t"] = np.uint64(r.t); g[name + "_elts"] = np.array(elts, dtype=np.uint64)
+        for e in elts:
+            g["%s_key_%d" % (name, e)] = r.galois_key(e)
+        rng = np.random.default_rng(4000 + scheme)
+        for ci, (count, shift, ii, oi, ft) in enumerate(PACK_CASES):
+            cts = []
+            for _ in range(count):
+                c = np.empty((2, L, n), dtype=np.uint64)
+                for j in range(L):
+                    c[:, j, :] = rng.integers(0, int(r.moduli[j]), size=(2, n), dtype=np.uint64)
+                cts.append(c.reshape(-1))
+            g["%s_c%d_in" % (name, ci)] = np.concatenate(cts)
+            for inp_ntt in ((0, 1) if scheme != po.BFV else (0,)):
+                g["%s_c%d_out%d" % (name, ci, inp_ntt)] = r.pack_rlwes(cts, L, bool(inp_ntt), shift, ii, oi, bool(ft))
+    np.savez_compressed(os.path.join(OUT, "ref_pack_n64.npz"), **g)
+    print("wrote pack", len(g), "arrays")
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "decrypt":
+    if len(sys.argv) > 1 and sys.argv[1] == "pack":
+        main_pack()
+    elif len(sys.argv) > 1 and sys.argv[1] == "decrypt":
         main_decrypt()
     elif len(sys.argv) > 1 and sys.argv[1] == "encrypt":
         main_encrypt()
     else:
-        main(); main_decrypt(); main_encrypt()
+        main(); main_decrypt(); main_encrypt(); main_pack()

@@ -285,6 +285,58 @@ class Oracle:
         if self.L.ro_decrypt(self.h, _p(np.ascontiguousarray(ct, dtype=np.uint64)), pc, nl, _p(sk_powers), correction_factor, _p(o)): raise RuntimeError("ro_decrypt failed")
         return o
 
+    # ---- RLWE packing: Evaluator::pack_rlwe_ciphertexts_new, device branch, step by step (src/evaluator_lwes.cu:305-491, field trace :96-105)
+    def apply_galois(self, ct, g, nl, is_ntt, key):
+        """Evaluator::apply_galois: permute both polynomials, keyswitch c_1 with OverwriteExceptFirst (src/evaluator_keyswitching.cu:143-200)"""
+        ga = self.galois(ct, g, 2, nl, is_ntt)
+        return self.keyswitch(ga[nl * self.n:], nl, is_ntt, key, dest=ga, assign=ASSIGN_OVERWRITE_EXCEPT_FIRST)
+
+    def pack_rlwes(self, ciphers, input_ntt, nl, shift, input_interval, output_interval, keys, apply_field_trace=True):
+        """ciphers: list of [2][nl][N] arrays; keys: {galois element: key array}.  Output NTT form for CKKS / BGV, coefficient form for BFV."""
+        n = self.n
+        out_ntt = self.scheme != BFV
+        M = input_interval // output_interval
+        layers = M.bit_length() - 1
+        assert 1 <= len(ciphers) <= M
+        w = 2 * nl * n
+        rl = []
+        for i in range(M):
+            idx = int(format(i, "0%db" % layers)[::-1], 2) if layers else 0
+            if idx < len(ciphers):
+                c = np.ascontiguousarray(ciphers[idx], dtype=np.uint64).copy()
+                if input_ntt:
+                    c = self.ntt_inv(c, 2, nl)
+                c = self.ntt_multiply_inv_degree(c, 2, nl, scalar=n // input_interval)
+                if shift:
+                    c = self.negacyclic_shift(c, shift, 2, nl)
+                rl.append(c)
+            else:
+                rl.append(np.zeros(w, dtype=np.uint64))
+        for layer in range(layers):
+            gap = 1 << layer
+            sh = input_interval >> (layer + 1)
+            g = (n // input_interval) * (1 << (layer + 1)) + 1
+            for off in range(0, M, 2 * gap):
+                even, odd = rl[off], rl[off + gap]
+                temp = self.negacyclic_shift(odd, sh, 2, nl)
+                odd = self.sub(even, temp, 2, nl)
+                even = self.add(even, temp, 2, nl)
+                if out_ntt:
+                    odd = self.ntt_fwd(odd, 2, nl)
+                odd = self.apply_galois(odd, g, nl, out_ntt, keys[g])
+                if out_ntt:
+                    odd = self.ntt_inv(odd, 2, nl)
+                rl[off] = self.add(even, odd, 2, nl)
+        ret = rl[0]
+        if out_ntt:
+            ret = self.ntt_fwd(ret, 2, nl)
+        if output_interval != 1 and apply_field_trace:
+            deg = n
+            while deg > n // output_interval:
+                ret = self.add(ret, self.apply_galois(ret, deg + 1, nl, out_ntt, keys[deg + 1]), 2, nl)
+                deg >>= 1
+        return ret
+
     # ---- generator (state = np.uint64[4]: seed_lo, seed_hi, counter_lo, counter_hi; advanced in place), samplers, Encryptor
     @staticmethod
     def prng_state(seed_lo, seed_hi=0, counter=0):
@@ -392,6 +444,7 @@ def reflib():
         R.rs_prng.argtypes = [C.c_void_p, C.c_int, u64p, C.c_size_t, C.c_size_t, u64p]
         R.rs_public_key.argtypes = [C.c_void_p, u64p]
         R.rs_encrypt_seeded.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_int, C.c_int, C.c_size_t, C.c_uint64, C.c_uint64, u64p, u64p]
+        R.rs_pack_rlwes.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, u64p]
         R.rs_time_op.restype = C.c_double
         R.rs_time_op.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int]
         _ref = R
@@ -498,6 +551,11 @@ class Reference:
             plain = np.ascontiguousarray(plain, dtype=np.uint64)
             self._chk(self.R.rs_encrypt_seeded(self.h, _p(plain), plain.size, int(asymmetric), int(save_seed), nl, seed_lo, seed_hi, _p(o), C.byref(sd)))
         return o, int(sd.value)
+
+    def pack_rlwes(self, cts, nl, input_ntt, shift, input_interval, output_interval, apply_field_trace=True):
+        flat = np.ascontiguousarray(np.concatenate(cts), dtype=np.uint64)
+        o = np.zeros(2 * nl * self.n, dtype=np.uint64)
+        self._chk(self.R.rs_pack_rlwes(self.h, _p(flat), len(cts), nl, int(input_ntt), shift, input_interval, output_interval, int(apply_field_trace), _p(o))); return o
 
     def decrypt_raw(self, a, pc, nl, correction_factor=1):
         o = np.zeros((nl if self.scheme == 2 else 1) * self.n, dtype=np.uint64)

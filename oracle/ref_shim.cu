@@ -332,6 +332,22 @@ int rs_encrypt_seeded(void *hh, const uint64_t *plain, size_t plain_count, int a
     })
 }
 
+/* ---- Evaluator::pack_rlwe_ciphertexts_new (src/evaluator_lwes.cu:305-491) on raw ciphertexts [count][2][nl][N] with the Galois keys
+ * generated by rs_gen_galois; out [2][nl][N] ---- */
+int rs_pack_rlwes(void *hh, const uint64_t *cts, size_t count, size_t nl, int input_ntt_form, size_t shift, size_t input_interval, size_t output_interval,
+                  int apply_field_trace, uint64_t *out) {
+    RefShim *h = (RefShim *)hh;
+    RS_TRY({
+        std::vector<Ciphertext> v; v.reserve(count);
+        for (size_t i = 0; i < count; i++) v.push_back(make_ct(h, cts + i * 2 * nl * h->n, 2, nl, input_ntt_form != 0));
+        std::vector<const Ciphertext *> ptrs;
+        for (auto &c : v) ptrs.push_back(&c);
+        Ciphertext r = h->eval->pack_rlwe_ciphertexts_new(ptrs, h->glk, shift, input_interval, output_interval, MemoryPool::GlobalPool(), apply_field_trace != 0);
+        if (h->device) cudaDeviceSynchronize();
+        export_ct(r, out);
+    })
+}
+
 /* ---- timing helper: seconds per op, averaged over iters, data resident where the context is ----
  * op: 0 ntt_fwd(pc*nc limbs, componentwise key tables base 0) 1 ntt_inv 2 multiply 3 relinearize
  *     4 rotate(1) 5 rescale/modswitch_to_next 6 square 7 encrypt_zero_asymmetric (level nl) 8 decrypt (2 polynomials, level nl) */

@@ -171,6 +171,21 @@ def test_oracle_encryptor_reproduces_reference_golden(po):
             assert np.array_equal(dec[:m.size], m) and not dec[m.size:].any()
 
 
+def test_oracle_packing_reproduces_reference_golden(po):
+    """Evaluator::pack_rlwe_ciphertexts_new + field trace (src/evaluator_lwes.cu:96-105,305-491): golden vectors from the unmodified reference"""
+    g = np.load(os.path.join(GOLD, "ref_pack_n64.npz"))
+    n = int(g["n"])
+    for scheme, name in ((po.BFV, "bfv"), (po.CKKS, "ckks"), (po.BGV, "bgv")):
+        o = po.Oracle(6, g[name + "_moduli"], int(g[name + "_t"]) if scheme != po.CKKS else 0, scheme)
+        L = o.nm - 1
+        keys = {int(e): g["%s_key_%d" % (name, int(e))] for e in g[name + "_elts"]}
+        for ci, (count, shift, ii, oi, ft) in enumerate(g["cases"]):
+            cts = np.split(g["%s_c%d_in" % (name, ci)], int(count))
+            for inp_ntt in ((0, 1) if scheme != po.BFV else (0,)):
+                got = o.pack_rlwes(cts, bool(inp_ntt), L, int(shift), int(ii), int(oi), keys, bool(ft))
+                assert np.array_equal(got, g["%s_c%d_out%d" % (name, ci, inp_ntt)]), (name, ci, inp_ntt)
+
+
 # ---- (iii) live against the compiled reference --------------------------------------------------
 SURVEY_FPR = {2: ("3866d51961505bd9", "c59ae60bda39e030", "a0e0a04249a08cd3", "4a186e8776597c7e", "eb819b8149c577a2"),
               3: ("82ff3df13af52835", "2046b27467209ab9", "a967cf538de6dc20", "def3d7ec042efe31", "e11839bb23d6a573"),

@@ -98,6 +98,9 @@ _SIGS.update({
     "b2_bfv_scale_up": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, vp, C.c_int, vp, vp]),
     "b2_centralize": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, vp, vp]),
     "b2_encrypt": (C.c_int, [vp, vp, C.c_size_t, vp, C.c_int, C.c_size_t, vp, vp, vp, vp]),
+    "b2_pack_layer": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint64, vp, vp]),
+    "b2_pack_rlwes": (C.c_int, [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.c_size_t, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, u64p, C.POINTER(vp), C.c_size_t,
+                                C.c_int, C.c_int, C.POINTER(vp), vp]),
     "b2_secret_key_powers": (C.c_int, [vp, vp, C.c_size_t, vp, vp]),
     "b2_decrypt_phase": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, vp, vp]),
     "b2_decrypt_scale_and_round": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.c_size_t, C.c_size_t, vp]),
@@ -332,6 +335,25 @@ class Context:
         bsk = (C.c_uint64 * (self.K + 2))(); cnt = C.c_size_t(); g = C.c_uint64()
         _chk(self.L.b2_behz_bases(self.h, nl, bsk, C.byref(cnt), C.byref(g)))
         return [int(bsk[i]) for i in range(cnt.value)], int(g.value)
+
+    # ---- RLWE packing (src/evaluator_lwes.cu:305-491)
+    def pack_layer(self, inp, out, target, pairs, nl, shift, galois_element, key, stream=None):
+        _chk(self.L.b2_pack_layer(self.h, _dptr(inp), _dptr(out), _dptr(target), pairs, nl, shift, galois_element, key.h, self._stream(stream))); return out
+
+    def pack_rlwes(self, ciphers, input_ntt, nl, shift, input_interval, output_interval, keys, out, apply_field_trace=True, output_ntt=None, stream=None):
+        """one group: ciphers = list of device tensors, out = device tensor.  Several groups packed side by side: ciphers = list of lists,
+        out = list of tensors.  keys: {galois element: KSwitchKey}; output_ntt defaults to the reference's rule (CKKS / BGV: NTT form)"""
+        output_ntt = (self.scheme != BFV) if output_ntt is None else output_ntt
+        grouped = len(ciphers) > 0 and isinstance(ciphers[0], (list, tuple))
+        groups = ciphers if grouped else [ciphers]
+        outs = out if grouped else [out]
+        flat = [c for g in groups for c in g]
+        counts = (C.c_size_t * len(groups))(*[len(g) for g in groups])
+        elts = sorted(keys)
+        ea = (C.c_uint64 * len(elts))(*elts); ka = (vp * len(elts))(*[keys[e].h for e in elts])
+        _chk(self.L.b2_pack_rlwes(self.h, self._ptrs(flat), counts, len(groups), int(input_ntt), nl, shift, input_interval, output_interval, ea, ka, len(elts),
+                                  int(apply_field_trace), int(output_ntt), self._ptrs(outs), self._stream(stream)))
+        return out
 
     # ---- generator, samplers, Encryptor (src/utils/random_generator.cu, src/utils/rlwe.cu, src/encryptor.cu)
     def prng_fill(self, g, out, nbytes, stream=None):
