@@ -24,10 +24,10 @@ def _run(filt, adapter="1", timeout=900):
     m = re.search(r"\[  PASSED  \] (\d+) tests", out)
     stats = re.search(r"\[b2_adapter\] ntt (\d+) \(\+(\d+) batched\)\s+keyswitch (\d+) \(\+(\d+) batched\)\s+dyadic (\d+)\s+modswitch (\d+)\s+galois (\d+)\s+bfv_multiply (\d+) \| "
                       r"device calls left to the reference (\d+)", out)
-    extra = re.search(r"\[b2_adapter §8f\] samplers (\d+)\s+decrypt (\d+)", out)
+    extra = re.search(r"\[b2_adapter §8f\] samplers (\d+)\s+decrypt (\d+)\s+pack (\d+)", out)
     st = [int(x) for x in stats.groups()] if stats else None
     if st is not None:
-        st += [int(x) for x in extra.groups()] if extra else [0, 0]      # 9 samplers, 10 decrypt
+        st += [int(x) for x in extra.groups()] if extra else [0, 0, 0]      # 9 samplers, 10 decrypt, 11 pack
     return p.returncode, int(m.group(1)) if m else 0, st, out
 
 
@@ -45,14 +45,14 @@ def test_adapter_library_passes_host_tests_untouched():
 @needs_bin
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,filt,need", [
-    # (suite, gtest filter, indices of adapter counters that must be non-zero: 0 ntt 2 keyswitch 3 keyswitch_batched 4 dyadic 5 modswitch 6 galois 7 bfv_multiply 9 samplers 10 decrypt)
+    # (suite, gtest filter, indices of adapter counters that must be non-zero: 0 ntt 2 keyswitch 3 keyswitch_batched 4 dyadic 5 modswitch 6 galois 7 bfv_multiply 9 samplers 10 decrypt 11 pack)
     ("evaluator", "EvaluatorTest.Device*", [0, 2, 4, 5, 6, 7]),
     ("evaluator_batched", "EvaluatorBatchTest.Device*", [0, 1, 3, 4]),
     ("encryptor_decryptor_keygen", "EncryptorTest.Device*:EncryptorBatchTest.Device*:SpecialPrimeForEncryptionTest.Device*", [0, 9, 10]),
     # (RandomGeneratorTest.Device* samples modulo 12345 / 23456 / 56789 — not an NTT-friendly chain, so those calls stay with the reference by
     #  design; the samplers are exercised through the Encryptor / KeyGenerator suites, counter 9)
     ("lwe_packing", "LweTest.Device*", [0, 3, 6]),
-    ("bumblebee_matmul_cheetah_conv2d", "MatmulTest.Device*:Conv2dTest.Device*:BFVRing2kTest.Device*", [0, 4]),
+    ("bumblebee_matmul_cheetah_conv2d", "MatmulTest.Device*:Conv2dTest.Device*:BFVRing2kTest.Device*", [0, 4, 11]),
     ("encoders_serialisation_context", "BatchEncoderTest.Device*:BatchEncoderBatchTest.Device*:CKKSEncoderTest.Device*:SerializeTest.Device*:HeContextTest.Device*", []),
     ("multithread", "MultithreadTest.*", [0]),
     ("utils_device", "NTT.Device*:RNSToolTest.Device*:GaloisToolTest.Device*:RNSBase.Device*", []),
