@@ -29,7 +29,7 @@ def test_host_mirror_script(po, scheme, tmp_path):
     is_ntt = scheme != 1
     rng = np.random.default_rng(300 + scheme)
     steps = [1, -1, 4, 0]
-    gelts = [o.galois_element_from_step(s) for s in steps]
+    gelts = [o.galois_element_from_step(s) for s in steps] + [5]          # 3 (= step 1) and 5: the automorphisms of a two-layer packing
     relin = o.random_key(rng)
     gkeys = {g: o.random_key(rng) for g in gelts}
     a = o.random_poly(rng, 2, L); b = o.random_poly(rng, 2, L)
@@ -87,9 +87,10 @@ def test_host_mirror_script(po, scheme, tmp_path):
         want += [("add_plain", np.concatenate([o.bfv_scale_up(msg, L, c1[:w]), c1[w:]])), ("sub_plain", np.concatenate([o.bfv_scale_up(msg, L, c1[:w], True), c1[w:]]))]
     elif scheme == 2:
         want += [("add_plain", np.concatenate([o.add(c1[:w], msg, 1, L), c1[w:]])), ("sub_plain", np.concatenate([o.sub(c1[:w], msg, 1, L), c1[w:]]))]
+    want += [("pack_rlwe_ciphertexts_new", o.pack_rlwes([a, b, r], is_ntt, L, 0, n, n // 4, {3: gkeys[3], 5: gkeys[5]}, False))]
     pos = 0
     for name, exp in want:
         got = out[pos:pos + exp.size]; pos += exp.size
         assert np.array_equal(got, exp), f"{name} differs from the oracle (scheme {scheme})"
     probes = out[pos:]
-    assert probes.tolist() == [1, 0, 1, 1, 1, 1] + [1, 1, 1, 1], f"error behaviour probes: {probes.tolist()}"
+    assert probes.tolist() == [1, 0, 1, 1, 1, 1] + [1, 1, 1, 1, 1, 1], f"error behaviour probes: {probes.tolist()}"

@@ -474,6 +474,65 @@ static void transform_batched(const HeContextPointer &ctx, const std::vector<Cip
 void Evaluator::transform_to_ntt_inplace_batched(const std::vector<Ciphertext *> &es) const { transform_batched(context_, es, true); }
 void Evaluator::transform_from_ntt_inplace_batched(const std::vector<Ciphertext *> &es) const { transform_batched(context_, es, false); }
 
+// Evaluator::pack_rlwe_ciphertexts_batched / _new (src/evaluator_lwes.cu:305-700): argument checks of the reference, then ONE C-ABI call
+void Evaluator::pack_rlwe_ciphertexts_batched(const std::vector<std::vector<const Ciphertext *>> &groups, const GaloisKeys &akeys, size_t shift, size_t input_interval,
+                                              size_t output_interval, const std::vector<Ciphertext *> &outputs, bool apply_field_trace) const {
+    if (groups.size() != outputs.size()) throw std::invalid_argument("[Evaluator::pack_rlwe_ciphertexts_batched] Input groups and outputs should have same size.");
+    if (groups.empty()) return;
+    if (groups[0].empty() || !groups[0][0]) throw std::invalid_argument("[Evaluator::pack_rlwe_ciphertexts_batched] Input group 0 is empty.");
+    const Ciphertext &first = *groups[0][0];
+    check_ct("[Evaluator::pack_rlwe_ciphertexts_batched]", first);
+    const size_t n = context_->poly_modulus_degree(), nl = first.coeff_modulus_size();
+    auto pow2 = [](size_t v) { return v != 0 && (v & (v - 1)) == 0; };
+    if (input_interval > n) throw std::invalid_argument("[Evaluator::pack_rlwe_ciphertexts_batched] input_interval must be less than poly_modulus_degree.");
+    if (output_interval > input_interval) throw std::invalid_argument("[Evaluator::pack_rlwe_ciphertexts_batched] output_interval must be less than input_interval.");
+    if (!pow2(input_interval)) throw std::invalid_argument("[Evaluator::pack_rlwe_ciphertexts_batched] input_interval must be power of two.");
+    if (!pow2(output_interval)) throw std::invalid_argument("[Evaluator::pack_rlwe_ciphertexts_batched] output_interval must be power of two.");
+    const size_t M = input_interval / output_interval;
+    std::vector<const uint64_t *> ptrs;
+    std::vector<size_t> counts;
+    for (size_t g = 0; g < groups.size(); g++) {
+        if (groups[g].empty()) throw std::invalid_argument("[Evaluator::pack_rlwe_ciphertexts_batched] Input group " + std::to_string(g) + " is empty.");
+        if (groups[g].size() > M) throw std::invalid_argument("[Evaluator::pack_rlwe_ciphertexts_batched] Input group " + std::to_string(g) + " has more than input_interval / output_interval.");
+        for (const Ciphertext *c : groups[g]) {
+            if (!c || c->empty() || c->coeff_modulus_size() != nl) throw std::invalid_argument("[Evaluator::pack_rlwe_ciphertexts_batched] Input has different parms_id.");
+            if (c->is_ntt_form() != first.is_ntt_form()) throw std::invalid_argument("[Evaluator::pack_rlwe_ciphertexts_batched] Input has different ntt_form.");
+            if (c->polynomial_count() != 2) throw std::invalid_argument("[Evaluator::pack_rlwe_ciphertexts_batched] Input has different polynomial count.");
+            if (c->contains_seed()) throw std::invalid_argument("[Evaluator::pack_rlwe_ciphertexts_batched] Ciphertext contains a seed.");
+            ptrs.push_back(c->data());
+        }
+        counts.push_back(groups[g].size());
+    }
+    // the automorphism keys of the tree and of the trace
+    size_t layers = 0;
+    while (((size_t)1 << layers) < M) layers++;
+    std::vector<uint64_t> elts;
+    for (size_t l = 0; l < layers; l++) elts.push_back((n / input_interval) * ((uint64_t)1 << (l + 1)) + 1);
+    if (output_interval != 1 && apply_field_trace) for (size_t deg = n; deg > n / output_interval; deg >>= 1) elts.push_back(deg + 1);
+    std::vector<const b2_kswitch_key *> keys;
+    for (uint64_t e : elts) {
+        if (!akeys.has_key((size_t)e)) throw std::invalid_argument("[GaloisKeys::key] Galois key not present");
+        keys.push_back(akeys.key(GaloisKeys::get_index((size_t)e)));
+    }
+    const bool out_ntt = context_->scheme() != SchemeType::BFV;
+    std::vector<Ciphertext> res(groups.size());
+    std::vector<uint64_t *> op(groups.size());
+    for (size_t g = 0; g < groups.size(); g++) {
+        res[g] = Ciphertext::like(*groups[g][0], 2);
+        res[g].is_ntt_form() = out_ntt;
+        op[g] = res[g].data();
+    }
+    check(b2_pack_rlwes(context_->raw(), ptrs.data(), counts.data(), groups.size(), first.is_ntt_form() ? 1 : 0, nl, shift, input_interval, output_interval, elts.data(), keys.data(),
+                        elts.size(), apply_field_trace ? 1 : 0, out_ntt ? 1 : 0, op.data(), context_->stream), "[Evaluator::pack_rlwe_ciphertexts_batched]");
+    for (size_t g = 0; g < groups.size(); g++) *outputs[g] = std::move(res[g]);
+}
+Ciphertext Evaluator::pack_rlwe_ciphertexts_new(const std::vector<const Ciphertext *> &ciphers, const GaloisKeys &akeys, size_t shift, size_t input_interval, size_t output_interval,
+                                                bool apply_field_trace) const {
+    Ciphertext out;
+    pack_rlwe_ciphertexts_batched({ciphers}, akeys, shift, input_interval, output_interval, {&out}, apply_field_trace);
+    return out;
+}
+
 // Evaluator::translate_plain (src/evaluator_translate_plain.cu:95-170)
 void Evaluator::translate_plain(const Ciphertext &e, const Plaintext &p, Ciphertext &d, bool subtract) const {
     check_ct("[Evaluator::translate_plain]", e);

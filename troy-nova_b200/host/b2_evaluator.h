@@ -270,6 +270,13 @@ public:
     void transform_to_ntt_inplace_batched(const std::vector<Ciphertext *> &encrypted) const;
     void transform_from_ntt_inplace_batched(const std::vector<Ciphertext *> &encrypted) const;
 
+    // ---- RLWE packing (src/evaluator_lwes.cu:305-700): pack up to input_interval / output_interval ciphertexts into one (what the BumbleBee /
+    //      Cheetah output packing and pack_lwe_ciphertexts call), with the field trace; groups are packed side by side in one call
+    Ciphertext pack_rlwe_ciphertexts_new(const std::vector<const Ciphertext *> &ciphers, const GaloisKeys &automorphism_keys, size_t shift, size_t input_interval,
+                                         size_t output_interval, bool apply_field_trace = true) const;
+    void pack_rlwe_ciphertexts_batched(const std::vector<std::vector<const Ciphertext *>> &cipher_groups, const GaloisKeys &automorphism_keys, size_t shift,
+                                       size_t input_interval, size_t output_interval, const std::vector<Ciphertext *> &outputs, bool apply_field_trace = true) const;
+
     // ---- ct +/- pt (src/evaluator_translate_plain.cu:13-170): BFV with a mod-t plaintext (scale-up fused with the addition, one launch)
     //      or an RNS plaintext of the same form; CKKS with an NTT-form RNS plaintext of equal scale
     void add_plain(const Ciphertext &encrypted, const Plaintext &plain, Ciphertext &destination) const { translate_plain(encrypted, plain, destination, false); }

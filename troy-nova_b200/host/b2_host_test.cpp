@@ -134,6 +134,13 @@ int main(int argc, char **argv) {
                 ev.add_plain(c1, msg, ap); ev.sub_plain(c1, msg, sp);
                 emit(ap); emit(sp);
             }
+            {                                                                           // 34: RLWE packing of three ciphertexts (two layers, no trace): keys 3 and 5
+                Ciphertext packed = ev.pack_rlwe_ciphertexts_new({&a, &b, &r}, gk, 0, n, n / 4, false);
+                emit(packed);
+                GaloisKeys none(ctx);
+                cprobe([&] { ev.pack_rlwe_ciphertexts_new({&a, &b}, none, 0, n, n / 2, false); });          // key missing
+                cprobe([&] { ev.pack_rlwe_ciphertexts_new({&a, &b, &r}, gk, 0, n, n / 2, false); });        // more ciphertexts than slots
+            }
             cprobe([&] { Plaintext d; dec.decrypt(z, d); });                             // contains a seed
             cprobe([&] { Ciphertext t2 = c1.clone(); t2.is_ntt_form() = !t2.is_ntt_form(); Plaintext d; dec.decrypt(t2, d); });   // wrong form for the scheme
         }
