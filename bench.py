@@ -188,6 +188,16 @@ def gpu_reference_baseline():
     for op, name in ((3, "relinearize"), (4, "rotate"), (2, "multiply"), (5, "rescale"), (7, "encrypt_zero_asymmetric"), (8, "decrypt")):
         t = r.time_op(op, NCOMP - 1, 1, 2, 10)
         g[name + "_us"] = t * 1e6; g[name + "_ops_per_s"] = 1.0 / t
+    del r
+    try:      # C5 packing on the reference's device branch: 64 BFV ciphertexts at N = 8192 into one, with the field trace
+        n5 = 1 << 13
+        r5 = po.Reference(po.BFV, n5, [60, 40, 40, 60], t_bits=20, seed=0x123, device=True)
+        elts = sorted({(n5 >> k) + 1 for k in range(0, 13)} | {2 ** k + 1 for k in range(1, 14)})
+        r5.gen_galois([e for e in elts if e < 2 * n5])
+        t = r5.time_op(9, 3, 64, 1, 3)
+        g["c5_pack_64_to_1_us"] = t * 1e6
+    except Exception as ex:
+        g["c5_pack_error"] = str(ex)[:120]
     return g
 
 
@@ -249,6 +259,32 @@ def bench_c2(b2, torch, timed, local, world):
         ctx.galois(cts, gal, rot, 2 * B, L, False)          # coefficient-form automorphism of all 2 B polynomials
         ctx.keyswitch_batched([rot[b, 1] for b in range(B)], L, False, kh, [rot[b] for b in range(B)], b2.ASSIGN_OVERWRITE_EXCEPT_FIRST)
     t = timed(rotate_rows, 3); r["rotate_rows_ops_per_s"] = world * B / t; r["rotate_rows_us_per_op"] = t / B * 1e6
+    return r
+
+
+def bench_c5_pack(b2, torch, timed, local, world):
+    """BASELINE config 5 (BumbleBee output packing): BFV N=8192, q={60,40,40}+special 60: pack 64 ciphertexts into one with the
+    field trace (Evaluator::pack_rlwe_ciphertexts_new, input_interval N, output_interval N/64), and 16 such groups side by side in one call."""
+    log_n, n = 13, 1 << 13
+    moduli = b2.coeff_modulus_create(n, [60, 40, 40, 60]); K = len(moduli); L = K - 1
+    ctx = b2.Context(log_n, moduli, 1032193, b2.BFV, device=local)    # a 20-bit prime = 1 mod 2N
+    g = torch.Generator(device="cuda"); g.manual_seed(11)
+    elts = sorted({(n >> k) + 1 for k in range(0, log_n)} | {2 ** k + 1 for k in range(1, log_n + 1)})
+    elts = [e for e in elts if e < 2 * n]
+    keys = {}
+    for e in elts:
+        key = torch.empty((L, 2, K, n), dtype=torch.int64, device="cuda")
+        for i in range(K):
+            key[:, :, i, :] = torch.randint(0, moduli[i], (L, 2, n), dtype=torch.int64, device="cuda", generator=g)
+        keys[e] = ctx.kswitch_key(key)
+    G, M = 16, 64
+    cts = _rand_limbs(torch, moduli[:L], (G * M, 2), n, g)
+    outs = [torch.empty((2, L, n), dtype=torch.int64, device="cuda") for _ in range(G)]
+    r = {}
+    t = timed(lambda: ctx.pack_rlwes([cts[i] for i in range(M)], False, L, 0, n, n // M, keys, outs[0]), 5)
+    r["pack_64_to_1_us"] = t * 1e6; r["pack_64_to_1_ops_per_s"] = world / t
+    t = timed(lambda: ctx.pack_rlwes([[cts[gi * M + i] for i in range(M)] for gi in range(G)], False, L, 0, n, n // M, keys, outs), 3)
+    r["pack_16_groups_us_per_group"] = t / G * 1e6; r["pack_groups_per_s"] = world * G / t
     return r
 
 
@@ -525,6 +561,7 @@ def main():
         # the other named parameter sets (BASELINE.json configs 2 and 4), data resident, per GPU x world
         extra["c2_bfv_n16384_batch256"] = bench_c2(b2, torch, timed, local, world)
         extra["c4_bgv_n32768"] = bench_c4(b2, torch, timed, local, world)
+        extra["c5_bfv_n8192_packing"] = bench_c5_pack(b2, torch, timed, local, world)
         if world > 1:
             # ONE relinearize cut over all GPUs by RNS limb: all-gather of the coefficient-form target and
             # broadcast of the special limb over NCCL, everything else local to the modulus owner

@@ -350,7 +350,8 @@ int rs_pack_rlwes(void *hh, const uint64_t *cts, size_t count, size_t nl, int in
 
 /* ---- timing helper: seconds per op, averaged over iters, data resident where the context is ----
  * op: 0 ntt_fwd(pc*nc limbs, componentwise key tables base 0) 1 ntt_inv 2 multiply 3 relinearize
- *     4 rotate(1) 5 rescale/modswitch_to_next 6 square 7 encrypt_zero_asymmetric (level nl) 8 decrypt (2 polynomials, level nl) */
+ *     4 rotate(1) 5 rescale/modswitch_to_next 6 square 7 encrypt_zero_asymmetric (level nl) 8 decrypt (2 polynomials, level nl)
+ *     9 pack_rlwe_ciphertexts_new of pc ciphertexts, input_interval = N, output_interval = N / pc, with the field trace (needs the automorphism keys) */
 double rs_time_op(void *hh, int op, size_t nl, size_t pc, int warmup, int iters) {
     RefShim *h = (RefShim *)hh;
     try {
@@ -375,6 +376,10 @@ double rs_time_op(void *hh, int op, size_t nl, size_t pc, int warmup, int iters)
             case 6: { Ciphertext r = h->eval->square_new(c2); } break;
             case 7: { Ciphertext r = h->enc->encrypt_zero_asymmetric_new(level_with(h, nl)->parms_id()); } break;
             case 8: { Plaintext r = h->dec->decrypt_new(c2); } break;
+            case 9: {
+                std::vector<const Ciphertext *> ptrs(pc, &c2);
+                Ciphertext r = h->eval->pack_rlwe_ciphertexts_new(ptrs, h->glk, 0, h->n, h->n / pc);
+            } break;
             default: throw std::invalid_argument("bad op");
             }
             if (h->device) cudaDeviceSynchronize();

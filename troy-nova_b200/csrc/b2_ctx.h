@@ -40,6 +40,9 @@ struct b2_ctx {
     struct b2_behz *behz = nullptr;
     // Decryptor constants (gamma, base conversions q -> {t, gamma}), built lazily per level by b2_decrypt.cu
     struct b2_decrypt_state *dec = nullptr;
+    // stream-ordered arena of the multi-launch entry points (b2_pack_rlwes): a private pool with an unbounded release threshold, so that the
+    // memory stays mapped between calls (the device's default pool hands it back to the OS at every synchronisation)
+    cudaMemPool_t mempool = nullptr;
 };
 
 // Mutable state of one (stream, host thread).  `mu` is held by an entry point for the whole time it enqueues its launches,
@@ -83,6 +86,7 @@ void scratch_release_all(b2_ctx *ctx);
 int build_modulus_tables(uint64_t p, unsigned logn, Tw *T, Tw *IT, double *TD, double *ITD, ModInfo &M, uint64_t &psi_out);
 void behz_release(b2_ctx *ctx);
 void decrypt_release(b2_ctx *ctx);
+b2_status arena_pool(b2_ctx *ctx, cudaMemPool_t *out);
 b2_status mod_switch_locked(b2_ctx *ctx, b2_scratch *sc, const u64 *in, u64 *out, size_t count, size_t nl, int kind, size_t ws_off, cudaStream_t stream);
 #define B2_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return b2::cuda_fail(e__, #call); } while (0)
 #define B2_REQUIRE(cond, msg) do { if (!(cond)) { b2::set_error("%s: %s", __func__, msg); return B2_ERR_INVALID_ARG; } } while (0)

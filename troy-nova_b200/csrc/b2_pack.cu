@@ -74,6 +74,23 @@ __global__ void __launch_bounds__(256) pack_init_kernel(const u64 *const *__rest
         out[v] = (neg && val) ? p - val : val;
     }
 }
+b2_status arena_pool(b2_ctx *ctx, cudaMemPool_t *out) {
+    std::lock_guard<std::mutex> guard(ctx->mu);
+    if (!ctx->mempool) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = ctx->device;
+        cudaMemPool_t pool = nullptr;
+        B2_CUDA(cudaMemPoolCreate(&pool, &props));
+        unsigned long long keep = ~0ull;
+        cudaError_t e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        if (e != cudaSuccess) { cudaMemPoolDestroy(pool); return cuda_fail(e, "cudaMemPoolSetAttribute"); }
+        ctx->mempool = pool;
+    }
+    *out = ctx->mempool;
+    return B2_OK;
+}
 static inline unsigned pk_grid(u64 total) { return (unsigned)std::min<u64>((total + 255) / 256, 148u * 32u); }
 static u32 inv_mod_2n(u32 g, size_t n) { u32 inv = g; for (int it = 0; it < 5; it++) inv *= 2 - g * inv; return inv & (u32)(2 * n - 1); }
 static const b2_kswitch_key *find_key(const uint64_t *elts, const b2_kswitch_key *const *keys, size_t n_keys, uint64_t g) {
@@ -109,7 +126,10 @@ b2_status b2_pack_layer(b2_ctx *ctx, const uint64_t *in, uint64_t *out, uint64_t
     // BGV: the mod-down of its keyswitch is defined on NTT-form operands (the t-correction), so the key-switched pair is computed as the
     // reference does — NTT(target), keyswitch, INTT — and added: three more launches per layer
     uint64_t *ks = nullptr;
-    B2_CUDA(cudaMallocAsync((void **)&ks, pairs * 2 * nl * n * 8, stream));
+    cudaMemPool_t pool;
+    b2_status pst = arena_pool(ctx, &pool);
+    if (pst != B2_OK) return pst;
+    B2_CUDA(cudaMallocFromPoolAsync((void **)&ks, pairs * 2 * nl * n * 8, pool, stream));
     for (size_t b = 0; b < pairs; b++) d[b] = ks + b * 2 * nl * n;
     b2_status st = b2_ntt_forward(ctx, target, target, pairs, 1, nl, B2_TABLES_COMPONENTWISE, 0, 0, stream_);
     if (st == B2_OK) st = b2_keyswitch_batched(ctx, t.data(), d.data(), pairs, nl, 1, key, B2_ASSIGN_OVERWRITE, stream_);
@@ -160,7 +180,10 @@ b2_status b2_pack_rlwes(b2_ctx *ctx, const uint64_t *const *ciphers, const size_
     const size_t half = std::max<size_t>(slots / 2, groups), tab_bytes = ((count * 8 + slots * 4 + 15) / 16) * 16;
     const size_t words = slots * ctw + half * ctw + half * nl * n;
     void *arena = nullptr;
-    B2_CUDA(cudaMallocAsync(&arena, words * 8 + tab_bytes, stream));
+    cudaMemPool_t pool;
+    b2_status pst = arena_pool(ctx, &pool);
+    if (pst != B2_OK) return pst;
+    B2_CUDA(cudaMallocFromPoolAsync(&arena, words * 8 + tab_bytes, pool, stream));
     u64 *A = (u64 *)arena, *Bf = A + slots * ctw, *T = Bf + half * ctw;
     char *tab = (char *)(T + half * nl * n);
     b2_status st = B2_OK;
@@ -184,14 +207,14 @@ b2_status b2_pack_rlwes(b2_ctx *ctx, const uint64_t *const *ciphers, const size_
         scale[j].x = sc; scale[j].y = host::shoup_quotient(sc, q);
     }
     Tw *d_scale = nullptr;
-    if (cudaMallocAsync((void **)&d_scale, nl * sizeof(Tw), stream) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaMallocAsync(pack scale)"));
+    if (cudaMallocFromPoolAsync((void **)&d_scale, nl * sizeof(Tw), pool, stream) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaMallocAsync(pack scale)"));
     cudaMemcpyAsync(d_scale, scale.data(), nl * sizeof(Tw), cudaMemcpyHostToDevice, stream);
     const u64 *const *init_src = d_ciphers;
     u64 *staged = nullptr;
     std::vector<uint64_t> blob2;
     if (input_ntt_form) {
         // inverse transforms of the inputs into a staging area [count][ctw], one launch; the init kernel then reads from there
-        if (cudaMallocAsync((void **)&staged, count * ctw * 8 + count * 8, stream) != cudaSuccess) { cudaFreeAsync(d_scale, stream); return fail(cuda_fail(cudaGetLastError(), "cudaMallocAsync(pack staging)")); }
+        if (cudaMallocFromPoolAsync((void **)&staged, count * ctw * 8 + count * 8, pool, stream) != cudaSuccess) { cudaFreeAsync(d_scale, stream); return fail(cuda_fail(cudaGetLastError(), "cudaMallocAsync(pack staging)")); }
         std::vector<uint64_t *> souts(count);
         for (size_t i = 0; i < count; i++) souts[i] = (uint64_t *)(staged + i * ctw);
         st = b2_ntt_inverse_ptrs(ctx, ciphers, souts.data(), count, 2, nl, B2_TABLES_COMPONENTWISE, 0, 0, stream_);
