@@ -10,6 +10,8 @@ run() { # name, adapter(1/0), command...
   (time B2_ADAPTER=$ad B2_ADAPTER_STATS=1 timeout 900 "$@") > "$OUT/${name}_adapter$ad.log" 2>&1
   echo "---- $name adapter=$ad"; grep -vE "^\s*$" "$OUT/${name}_adapter$ad.log" | tail -${TAILN:-30}
 }
+# the first process on a freshly booted box is slow in BOTH arms (page cache, first large allocations): warm up before anything is compared
+B2_ADAPTER=0 timeout 300 $B/bench_matmul_b2 -D --bfv -m 128 -n 128 -r 128 -st 20 > /dev/null 2>&1
 Q3=60,40,40,40,40,40,40,40,40,40,40,40,40,40,40,40,40,40,40,40,60
 for ad in 1 0; do
   TAILN=45 run matmul128 $ad $B/bench_matmul_b2 -D --bfv -m 128 -n 128 -r 128 -st 20

@@ -187,7 +187,14 @@ b2_status b2_pack_rlwes(b2_ctx *ctx, const uint64_t *const *ciphers, const size_
     u64 *A = (u64 *)arena, *Bf = A + slots * ctw, *T = Bf + half * ctw;
     char *tab = (char *)(T + half * nl * n);
     b2_status st = B2_OK;
-    auto fail = [&](b2_status s) { cudaFreeAsync(arena, stream); return s; };
+    Tw *d_scale = nullptr;
+    u64 *staged = nullptr;
+    auto fail = [&](b2_status s) {      // every early exit returns the stream-ordered allocations
+        if (staged) cudaFreeAsync(staged, stream);
+        if (d_scale) cudaFreeAsync(d_scale, stream);
+        cudaFreeAsync(arena, stream);
+        return s;
+    };
     // slot (g, i) <- cipher[g][bitrev(i)] (evaluator_lwes.cu:347-358), or zero
     std::vector<uint64_t> blob((tab_bytes + 7) / 8);
     int *src = reinterpret_cast<int *>(blob.data() + count);
@@ -206,15 +213,13 @@ b2_status b2_pack_rlwes(b2_ctx *ctx, const uint64_t *const *ciphers, const size_
         const uint64_t q = ctx->q[j], sc = host::mulmod(host::invmod(n % q, q), mul % q, q);
         scale[j].x = sc; scale[j].y = host::shoup_quotient(sc, q);
     }
-    Tw *d_scale = nullptr;
-    if (cudaMallocFromPoolAsync((void **)&d_scale, nl * sizeof(Tw), pool, stream) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaMallocAsync(pack scale)"));
-    cudaMemcpyAsync(d_scale, scale.data(), nl * sizeof(Tw), cudaMemcpyHostToDevice, stream);
+    if (cudaMallocFromPoolAsync((void **)&d_scale, nl * sizeof(Tw), pool, stream) != cudaSuccess) { d_scale = nullptr; return fail(cuda_fail(cudaGetLastError(), "cudaMallocFromPoolAsync(pack scale)")); }
+    if (cudaMemcpyAsync(d_scale, scale.data(), nl * sizeof(Tw), cudaMemcpyHostToDevice, stream) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaMemcpyAsync(pack scale)"));
     const u64 *const *init_src = d_ciphers;
-    u64 *staged = nullptr;
     std::vector<uint64_t> blob2;
     if (input_ntt_form) {
         // inverse transforms of the inputs into a staging area [count][ctw], one launch; the init kernel then reads from there
-        if (cudaMallocFromPoolAsync((void **)&staged, count * ctw * 8 + count * 8, pool, stream) != cudaSuccess) { cudaFreeAsync(d_scale, stream); return fail(cuda_fail(cudaGetLastError(), "cudaMallocAsync(pack staging)")); }
+        if (cudaMallocFromPoolAsync((void **)&staged, count * ctw * 8 + count * 8, pool, stream) != cudaSuccess) { staged = nullptr; return fail(cuda_fail(cudaGetLastError(), "cudaMallocFromPoolAsync(pack staging)")); }
         std::vector<uint64_t *> souts(count);
         for (size_t i = 0; i < count; i++) souts[i] = (uint64_t *)(staged + i * ctw);
         st = b2_ntt_inverse_ptrs(ctx, ciphers, souts.data(), count, 2, nl, B2_TABLES_COMPONENTWISE, 0, 0, stream_);
@@ -256,10 +261,7 @@ b2_status b2_pack_rlwes(b2_ctx *ctx, const uint64_t *const *ciphers, const size_
     }
     for (size_t g = 0; g < groups && st == B2_OK; g++)
         if (cudaMemcpyAsync(outs[g], cur + g * ctw, ctw * 8, cudaMemcpyDeviceToDevice, stream) != cudaSuccess) st = cuda_fail(cudaGetLastError(), "cudaMemcpyAsync(pack result)");
-    if (staged) cudaFreeAsync(staged, stream);
-    cudaFreeAsync(d_scale, stream);
-    cudaFreeAsync(arena, stream);
-    return st;
+    return fail(st);      // releases the arena, the scale table and the staging area (stream-ordered: after the work enqueued above)
 }
 
 }  // extern "C"
