@@ -261,6 +261,16 @@ b2_status b2_pack_layer(b2_ctx *ctx, const uint64_t *in, uint64_t *out, uint64_t
 b2_status b2_pack_rlwes(b2_ctx *ctx, const uint64_t *const *ciphers, const size_t *counts, size_t groups, int input_ntt_form, size_t nl, size_t shift,
                         size_t input_interval, size_t output_interval, const uint64_t *galois_elements, const b2_kswitch_key *const *keys, size_t n_keys,
                         int apply_field_trace, int output_ntt_form, uint64_t *const *outs, void *stream);
+/* LWE ciphertexts (src/lwe_ciphertext.h): c0 = nl scalars, c1 = [nl][N].
+ * Evaluator::extract_lwe_new (src/evaluator_lwes.cu:51-94) on a coefficient-form ct [2][nl][N]: c1 = x^(2N - term) c_1, c0[j] = c_0[j][term]; one launch */
+b2_status b2_extract_lwe(b2_ctx *ctx, const uint64_t *ct, size_t term, size_t nl, uint64_t *c0, uint64_t *c1, void *stream);
+/* LWECiphertext::assemble_lwe[_batched] (src/lwe_ciphertext.cu:12-140): c0s / c1s / outs HOST arrays of `count` DEVICE pointers; outs[b] [2][nl][N], one launch */
+b2_status b2_assemble_lwes(b2_ctx *ctx, const uint64_t *const *c0s, const uint64_t *const *c1s, uint64_t *const *outs, size_t count, size_t nl, void *stream);
+/* Evaluator::pack_lwe_ciphertexts_new / _batched (src/evaluator_lwes.cu:201-303): counts[g] LWEs per group (c0s / c1s: all groups, one after the other)
+ * -> outs[g] [2][nl][N]; input_interval = N, output_interval = N / 2^ceil(log2 max count).  One assemble launch, then the tree of b2_pack_rlwes. */
+b2_status b2_pack_lwes(b2_ctx *ctx, const uint64_t *const *c0s, const uint64_t *const *c1s, const size_t *counts, size_t groups, size_t nl,
+                       const uint64_t *galois_elements, const b2_kswitch_key *const *keys, size_t n_keys, int apply_field_trace, int output_ntt_form,
+                       uint64_t *const *outs, void *stream);
 /* Evaluator::bfv_multiply / bfv_square device branch (src/evaluator.cu:29-116,199-282) = BEHZ RNS multiplication:
  * RNSTool::fast_b_conv_m_tilde_sm_mrq + NTT + dyadic convolution + INTT + RNSTool::fast_floor_fast_b_conv_sk
  * (src/fgk/rns_tool.cu:7-343).  a, b [batch][2][nl][N] coefficient form -> out [batch][3][nl][N] coefficient form.

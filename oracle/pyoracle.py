@@ -337,6 +337,28 @@ class Oracle:
                 deg >>= 1
         return ret
 
+    # ---- LWE (src/evaluator_lwes.cu:51-94, src/lwe_ciphertext.cu:12-140, pack_lwe_ciphertexts_new :201-229)
+    def extract_lwe(self, ct, term, nl):
+        """coefficient-form ct [2][nl][N] -> (c0 [nl], c1 [nl][N])"""
+        n = self.n
+        ct = np.ascontiguousarray(ct, dtype=np.uint64)
+        c1 = self.negacyclic_shift(ct[nl * n:], 0 if term == 0 else 2 * n - term, 1, nl)
+        return ct[:nl * n].reshape(nl, n)[:, term].copy(), c1
+
+    def assemble_lwe(self, c0, c1, nl):
+        n = self.n
+        out = np.zeros(2 * nl * n, dtype=np.uint64)
+        out[:nl * n].reshape(nl, n)[:, 0] = c0
+        out[nl * n:] = c1
+        return out
+
+    def pack_lwes(self, lwes, nl, keys, apply_field_trace=True):
+        l = 0
+        while (1 << l) < len(lwes):
+            l += 1
+        rl = [self.assemble_lwe(c0, c1, nl) for c0, c1 in lwes]
+        return self.pack_rlwes(rl, False, nl, 0, self.n, self.n >> l, keys, apply_field_trace)
+
     # ---- generator (state = np.uint64[4]: seed_lo, seed_hi, counter_lo, counter_hi; advanced in place), samplers, Encryptor
     @staticmethod
     def prng_state(seed_lo, seed_hi=0, counter=0):
@@ -445,6 +467,8 @@ def reflib():
         R.rs_public_key.argtypes = [C.c_void_p, u64p]
         R.rs_encrypt_seeded.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_int, C.c_int, C.c_size_t, C.c_uint64, C.c_uint64, u64p, u64p]
         R.rs_pack_rlwes.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, u64p]
+        R.rs_extract_lwe.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_size_t, C.c_int, u64p, u64p]
+        R.rs_pack_lwes.argtypes = [C.c_void_p, u64p, u64p, C.c_size_t, C.c_size_t, C.c_int, u64p]
         R.rs_time_op.restype = C.c_double
         R.rs_time_op.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int]
         _ref = R
@@ -556,6 +580,15 @@ class Reference:
         flat = np.ascontiguousarray(np.concatenate(cts), dtype=np.uint64)
         o = np.zeros(2 * nl * self.n, dtype=np.uint64)
         self._chk(self.R.rs_pack_rlwes(self.h, _p(flat), len(cts), nl, int(input_ntt), shift, input_interval, output_interval, int(apply_field_trace), _p(o))); return o
+
+    def extract_lwe(self, ct, term, nl, ntt_form):
+        c0 = np.zeros(nl, dtype=np.uint64); c1 = np.zeros(nl * self.n, dtype=np.uint64)
+        self._chk(self.R.rs_extract_lwe(self.h, _p(np.ascontiguousarray(ct, dtype=np.uint64)), term, nl, int(ntt_form), _p(c0), _p(c1))); return c0, c1
+
+    def pack_lwes(self, lwes, nl, apply_field_trace=True):
+        c0 = np.ascontiguousarray(np.concatenate([l[0] for l in lwes]), dtype=np.uint64); c1 = np.ascontiguousarray(np.concatenate([l[1] for l in lwes]), dtype=np.uint64)
+        o = np.zeros(2 * nl * self.n, dtype=np.uint64)
+        self._chk(self.R.rs_pack_lwes(self.h, _p(c0), _p(c1), len(lwes), nl, int(apply_field_trace), _p(o))); return o
 
     def decrypt_raw(self, a, pc, nl, correction_factor=1):
         o = np.zeros((nl if self.scheme == 2 else 1) * self.n, dtype=np.uint64)

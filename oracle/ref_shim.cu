@@ -348,6 +348,38 @@ int rs_pack_rlwes(void *hh, const uint64_t *cts, size_t count, size_t nl, int in
     })
 }
 
+/* ---- Evaluator::extract_lwe_new (src/evaluator_lwes.cu:51-94) and pack_lwe_ciphertexts_new (:201-229) on raw data ---- */
+int rs_extract_lwe(void *hh, const uint64_t *ct, size_t term, size_t nl, int ntt_form, uint64_t *c0, uint64_t *c1) {
+    RefShim *h = (RefShim *)hh;
+    RS_TRY({
+        Ciphertext c = make_ct(h, ct, 2, nl, ntt_form != 0);
+        LWECiphertext l = h->eval->extract_lwe_new(c, term);
+        if (l.on_device()) l.to_host_inplace();
+        std::memcpy(c0, l.const_c0().raw_pointer(), nl * 8);
+        std::memcpy(c1, l.const_c1().raw_pointer(), nl * h->n * 8);
+    })
+}
+int rs_pack_lwes(void *hh, const uint64_t *c0s, const uint64_t *c1s, size_t count, size_t nl, int apply_field_trace, uint64_t *out) {
+    RefShim *h = (RefShim *)hh;
+    RS_TRY({
+        /* LWEs are built by extracting term 0 of RLWEs assembled from the raw (c0, c1): assemble o extract is the identity on them */
+        std::vector<LWECiphertext> lwes; lwes.reserve(count);
+        std::vector<uint64_t> raw(2 * nl * h->n);
+        for (size_t i = 0; i < count; i++) {
+            std::fill(raw.begin(), raw.end(), 0);
+            for (size_t j = 0; j < nl; j++) raw[j * h->n] = c0s[i * nl + j];
+            std::memcpy(raw.data() + nl * h->n, c1s + i * nl * h->n, nl * h->n * 8);
+            Ciphertext c = make_ct(h, raw.data(), 2, nl, false);
+            lwes.push_back(h->eval->extract_lwe_new(c, 0));
+        }
+        std::vector<const LWECiphertext *> ptrs;
+        for (auto &l : lwes) ptrs.push_back(&l);
+        Ciphertext r = h->eval->pack_lwe_ciphertexts_new(ptrs, h->glk, MemoryPool::GlobalPool(), apply_field_trace != 0);
+        if (h->device) cudaDeviceSynchronize();
+        export_ct(r, out);
+    })
+}
+
 /* ---- timing helper: seconds per op, averaged over iters, data resident where the context is ----
  * op: 0 ntt_fwd(pc*nc limbs, componentwise key tables base 0) 1 ntt_inv 2 multiply 3 relinearize
  *     4 rotate(1) 5 rescale/modswitch_to_next 6 square 7 encrypt_zero_asymmetric (level nl) 8 decrypt (2 polynomials, level nl)

@@ -88,6 +88,10 @@ def test_host_mirror_script(po, scheme, tmp_path):
     elif scheme == 2:
         want += [("add_plain", np.concatenate([o.add(c1[:w], msg, 1, L), c1[w:]])), ("sub_plain", np.concatenate([o.sub(c1[:w], msg, 1, L), c1[w:]]))]
     want += [("pack_rlwe_ciphertexts_new", o.pack_rlwes([a, b, r], is_ntt, L, 0, n, n // 4, {3: gkeys[3], 5: gkeys[5]}, False))]
+    coeff = (lambda c: c) if not is_ntt else (lambda c: o.ntt_inv(c.copy(), 2, L))
+    l0, l7, l9 = o.extract_lwe(coeff(a), 0, L), o.extract_lwe(coeff(b), 7, L), o.extract_lwe(coeff(r), 9, L)
+    want += [("extract_lwe c0", l7[0]), ("extract_lwe c1", l7[1]), ("assemble_lwe", o.assemble_lwe(l9[0], l9[1], L)),
+             ("pack_lwe_ciphertexts_new", o.pack_lwes([l0, l7, l9], L, {3: gkeys[3], 5: gkeys[5]}, False))]
     pos = 0
     for name, exp in want:
         got = out[pos:pos + exp.size]; pos += exp.size

@@ -266,6 +266,34 @@ def test_live_reference_encryptor(po, scheme, bits, t_bits):
             assert np.array_equal(r.encrypt_seeded(plain, asym, L, 4242)[0], o.encrypt(plain, pk if asym else sk, asym, L, o.prng_state(4242))), ("enc", asym)
 
 
+@pytest.mark.parametrize("scheme,bits", [(1, [40, 40, 50]), (2, [40, 40, 50]), (3, [40, 45, 55])])
+def test_live_reference_packing_and_lwe(po, scheme, bits):
+    """oracle pack_rlwes / extract_lwe / pack_lwes == the unmodified reference's Evaluator::pack_rlwe_ciphertexts_new, extract_lwe_new and
+    pack_lwe_ciphertexts_new with the reference's automorphism keys (src/evaluator_lwes.cu:51-94,201-229,305-491)"""
+    if not po.ref_available():
+        pytest.skip("oracle/_ref not built")
+    n, logn = 64, 6
+    r = po.Reference(scheme, n, bits, t_bits=20)
+    o = po.Oracle(logn, r.moduli, r.t if scheme != po.CKKS else 0, scheme)
+    L = r.nm - 1
+    elts = [e for e in sorted({(n >> k) + 1 for k in range(0, logn)} | {2 ** k + 1 for k in range(1, logn + 1)}) if e < 2 * n]
+    r.gen_galois(elts)
+    keys = {e: r.galois_key(e) for e in elts}
+    rng = np.random.default_rng(scheme)
+    for (count, shift, ii, oi, ft) in ((4, 0, n, n // 4, True), (8, 5, n, n // 8, False), (5, 2 * n - 3, n, n // 8, True), (1, 0, n, n, True)):
+        cts = [o.random_poly(rng, 2, L) for _ in range(count)]
+        for inp_ntt in ((False, True) if scheme != po.BFV else (False,)):
+            assert np.array_equal(r.pack_rlwes(cts, L, inp_ntt, shift, ii, oi, ft), o.pack_rlwes(cts, inp_ntt, L, shift, ii, oi, keys, ft)), (count, shift, ii, oi, ft, inp_ntt)
+    ct = o.random_poly(rng, 2, L)
+    for term in (0, 1, 17, n - 1):
+        w0, w1 = r.extract_lwe(ct, term, L, False)
+        g0, g1 = o.extract_lwe(ct, term, L)
+        assert np.array_equal(w0, g0) and np.array_equal(w1, g1), term
+    for count in (1, 3, 7):
+        lwes = [(o.random_poly(rng, 1, L).reshape(L, n)[:, 0].copy(), o.random_poly(rng, 1, L)) for _ in range(count)]
+        assert np.array_equal(r.pack_lwes(lwes, L, True), o.pack_lwes(lwes, L, keys, True)), count
+
+
 @pytest.mark.parametrize("log_n,bits,t_bits", [(6, [40, 40, 40], 20), (10, [60, 40, 40, 60], 20), (9, [50, 36, 45, 60, 55], 30), (7, [60] * 6, 59)])
 def test_live_reference_behz_multiply(po, log_n, bits, t_bits):
     """BEHZ multiply at every level of several modulus chains, incl. a 60-bit plain modulus (|B| = |q| + 1 branch,

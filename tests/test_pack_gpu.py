@@ -74,6 +74,42 @@ def test_pack_rlwes_groups_side_by_side(b2, po, scheme):
     assert launches <= (b2.launch_count() - before) + 8, "groups must share the launches of one group (plus the per-group result copies)"
 
 
+@pytest.mark.parametrize("scheme", [1, 2, 3])
+def test_lwe_extract_assemble_pack(b2, po, scheme):
+    """Evaluator::extract_lwe_new, LWECiphertext::assemble_lwe_batched and pack_lwe_ciphertexts_new / _batched (src/evaluator_lwes.cu:51-94,201-303,
+    src/lwe_ciphertext.cu:12-140) against the oracle compositions pinned to the reference (tests/test_oracle_pinning.py)"""
+    o = make_oracle(po, scheme=scheme, log_n=10, bits=[50, 40, 40, 55], t_bits=20 if scheme != 2 else 0)
+    ctx = b2.Context(o.log_n, o.moduli, o.t, o.scheme)
+    n, L = o.n, o.nm - 1
+    rng = np.random.default_rng(5)
+    hkeys, dkeys = _keys(o, ctx, rng)
+    ct = o.random_poly(rng, 2, L)
+    d_ct = to_dev(ct)
+    lwes = []
+    for term in (0, 1, 333, n - 1):
+        c0, c1 = _zeros(L + (L & 1)), _zeros(L * n)
+        before = b2.launch_count()
+        ctx.extract_lwe(d_ct, term, L, c0, c1)
+        assert b2.launch_count() - before == 1
+        w0, w1 = o.extract_lwe(ct, term, L)
+        assert np.array_equal(to_np(c0)[:L], w0) and np.array_equal(to_np(c1), w1), term
+        lwes.append((c0, c1, w0, w1))
+    outs = [_zeros(2 * L * n) for _ in lwes]
+    before = b2.launch_count()
+    ctx.assemble_lwes([l[0] for l in lwes], [l[1] for l in lwes], outs, L)
+    assert b2.launch_count() - before == 1
+    for (c0, c1, w0, w1), out in zip(lwes, outs):
+        assert np.array_equal(to_np(out), o.assemble_lwe(w0, w1, L))
+    # two groups of LWEs packed side by side (sizes 4 and 3 -> both into N / 4 slots), with the trace
+    more = [(o.random_poly(rng, 1, L).reshape(L, n)[:, 0].copy(), o.random_poly(rng, 1, L)) for _ in range(3)]
+    g0 = [(l[2], l[3]) for l in lwes]
+    d_groups = [[(l[0], l[1]) for l in lwes], [(to_dev(np.concatenate([c0, np.zeros(L & 1, dtype=np.uint64)])), to_dev(c1)) for c0, c1 in more]]
+    pouts = [_zeros(2 * L * n), _zeros(2 * L * n)]
+    ctx.pack_lwes(d_groups, L, dkeys, pouts)
+    assert np.array_equal(to_np(pouts[0]), o.pack_lwes(g0, L, hkeys, True)), "group 0"
+    assert np.array_equal(to_np(pouts[1]), o.pack_lwes(more + [(np.zeros(L, dtype=np.uint64), np.zeros(L * n, dtype=np.uint64))][:0], L, hkeys, True)), "group 1"
+
+
 def test_pack_layer_and_errors(b2, po):
     o = make_oracle(po, scheme=1, log_n=11, bits=[60, 40, 60], t_bits=20)
     ctx = b2.Context(o.log_n, o.moduli, o.t, o.scheme)

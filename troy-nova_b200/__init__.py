@@ -101,6 +101,9 @@ _SIGS.update({
     "b2_pack_layer": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint64, vp, vp]),
     "b2_pack_rlwes": (C.c_int, [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.c_size_t, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, u64p, C.POINTER(vp), C.c_size_t,
                                 C.c_int, C.c_int, C.POINTER(vp), vp]),
+    "b2_extract_lwe": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, vp, vp, vp]),
+    "b2_assemble_lwes": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.c_size_t, C.c_size_t, vp]),
+    "b2_pack_lwes": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t), C.c_size_t, C.c_size_t, u64p, C.POINTER(vp), C.c_size_t, C.c_int, C.c_int, C.POINTER(vp), vp]),
     "b2_secret_key_powers": (C.c_int, [vp, vp, C.c_size_t, vp, vp]),
     "b2_decrypt_phase": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, vp, vp]),
     "b2_decrypt_scale_and_round": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.c_size_t, C.c_size_t, vp]),
@@ -354,6 +357,23 @@ class Context:
         _chk(self.L.b2_pack_rlwes(self.h, self._ptrs(flat), counts, len(groups), int(input_ntt), nl, shift, input_interval, output_interval, ea, ka, len(elts),
                                   int(apply_field_trace), int(output_ntt), self._ptrs(outs), self._stream(stream)))
         return out
+
+    def extract_lwe(self, ct, term, nl, c0, c1, stream=None):
+        _chk(self.L.b2_extract_lwe(self.h, _dptr(ct), term, nl, _dptr(c0), _dptr(c1), self._stream(stream))); return c0, c1
+
+    def assemble_lwes(self, c0s, c1s, outs, nl, stream=None):
+        _chk(self.L.b2_assemble_lwes(self.h, self._ptrs(c0s), self._ptrs(c1s), self._ptrs(outs), len(c0s), nl, self._stream(stream))); return outs
+
+    def pack_lwes(self, groups, nl, keys, outs, apply_field_trace=True, output_ntt=None, stream=None):
+        """groups: list of groups, each a list of (c0, c1) device tensors; outs: one device tensor per group"""
+        output_ntt = (self.scheme != BFV) if output_ntt is None else output_ntt
+        c0s = [l[0] for g in groups for l in g]; c1s = [l[1] for g in groups for l in g]
+        counts = (C.c_size_t * len(groups))(*[len(g) for g in groups])
+        elts = sorted(keys)
+        ea = (C.c_uint64 * len(elts))(*elts); ka = (vp * len(elts))(*[keys[e].h for e in elts])
+        _chk(self.L.b2_pack_lwes(self.h, self._ptrs(c0s), self._ptrs(c1s), counts, len(groups), nl, ea, ka, len(elts), int(apply_field_trace), int(output_ntt),
+                                 self._ptrs(outs), self._stream(stream)))
+        return outs
 
     # ---- generator, samplers, Encryptor (src/utils/random_generator.cu, src/utils/rlwe.cu, src/encryptor.cu)
     def prng_fill(self, g, out, nbytes, stream=None):

@@ -139,40 +139,16 @@ b2_status b2_pack_layer(b2_ctx *ctx, const uint64_t *in, uint64_t *out, uint64_t
     return st;
 }
 
-// Evaluator::pack_rlwe_ciphertexts_new / pack_rlwe_ciphertexts_batched for `groups` groups packed side by side (every layer is one fused
-// launch + one batched keyswitch over ALL groups).  ciphers: HOST array of sum(counts) DEVICE pointers (group after group), each
-// [2][nl][N] in the form given by input_ntt_form; counts: HOST [groups]; galois_elements / keys: the automorphism keys (GaloisKeys) as
-// parallel HOST arrays; outs: HOST array of `groups` DEVICE pointers, each [2][nl][N], NTT form iff output_ntt_form (the reference: CKKS /
-// BGV).  Everything is enqueued on `stream`; the arena is stream-ordered memory.
-b2_status b2_pack_rlwes(b2_ctx *ctx, const uint64_t *const *ciphers, const size_t *counts, size_t groups, int input_ntt_form, size_t nl, size_t shift,
-                        size_t input_interval, size_t output_interval, const uint64_t *galois_elements, const b2_kswitch_key *const *keys, size_t n_keys,
-                        int apply_field_trace, int output_ntt_form, uint64_t *const *outs, void *stream_) {
-    B2_REQUIRE(ctx && ciphers && counts && outs && (n_keys == 0 || (galois_elements && keys)), "null argument");
-    if (groups == 0) return B2_OK;
-    const size_t n = ctx->n;
-    B2_REQUIRE(nl >= 1 && nl + 1 <= ctx->K, "bad level (packing needs a special prime)");
-    B2_REQUIRE(input_interval <= n, "input_interval must be less than poly_modulus_degree.");                    // evaluator_lwes.cu:324-335
-    B2_REQUIRE(output_interval <= input_interval && output_interval >= 1, "output_interval must be less than input_interval.");
-    B2_REQUIRE((input_interval & (input_interval - 1)) == 0, "input_interval must be power of two.");
-    B2_REQUIRE((output_interval & (output_interval - 1)) == 0, "output_interval must be power of two.");
-    const size_t M = input_interval / output_interval;
-    size_t count = 0;
-    for (size_t g = 0; g < groups; g++) {
-        B2_REQUIRE(counts[g] >= 1 && counts[g] <= M, "ciphers count must be less than input_interval / output_interval.");
-        B2_REQUIRE(outs[g] && (((uintptr_t)outs[g]) & 15) == 0, "null or misaligned output");
-        count += counts[g];
-    }
-    B2_REQUIRE(shift < 2 * n, "shift must be below 2N");
-    B2_REQUIRE(ctx->scheme != B2_SCHEME_BGV || ctx->t > 1, "BGV needs a plain modulus");
+}  // extern "C"
+
+namespace b2 {
+// the packing tree over coefficient-form inputs (arguments validated by the callers)
+static b2_status pack_run(b2_ctx *ctx, const uint64_t *const *ciphers, const size_t *counts, size_t groups, size_t count, size_t nl, size_t shift, size_t input_interval,
+                          size_t output_interval, const uint64_t *galois_elements, const b2_kswitch_key *const *keys, size_t n_keys, bool trace, int output_ntt_form,
+                          uint64_t *const *outs, void *stream_) {
+    const size_t n = ctx->n, M = input_interval / output_interval;
     size_t layers = 0;
     while (((size_t)1 << layers) < M) layers++;
-    for (size_t i = 0; i < count; i++) B2_REQUIRE(ciphers[i] && (((uintptr_t)ciphers[i]) & 15) == 0, "null or misaligned ciphertext");
-    // every key the tree and the trace will use must be present before anything is enqueued
-    for (size_t l = 0; l < layers; l++)
-        B2_REQUIRE(find_key(galois_elements, keys, n_keys, (n / input_interval) * ((uint64_t)1 << (l + 1)) + 1), "Galois key not present");
-    const bool trace = output_interval != 1 && apply_field_trace;
-    if (trace)
-        for (size_t deg = n; deg > n / output_interval; deg >>= 1) B2_REQUIRE(find_key(galois_elements, keys, n_keys, deg + 1), "Galois key not present");
     B2_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t stream = (cudaStream_t)stream_;
     const size_t ctw = 2 * nl * n, slots = groups * M;
@@ -188,9 +164,7 @@ b2_status b2_pack_rlwes(b2_ctx *ctx, const uint64_t *const *ciphers, const size_
     char *tab = (char *)(T + half * nl * n);
     b2_status st = B2_OK;
     Tw *d_scale = nullptr;
-    u64 *staged = nullptr;
     auto fail = [&](b2_status s) {      // every early exit returns the stream-ordered allocations
-        if (staged) cudaFreeAsync(staged, stream);
         if (d_scale) cudaFreeAsync(d_scale, stream);
         cudaFreeAsync(arena, stream);
         return s;
@@ -216,21 +190,6 @@ b2_status b2_pack_rlwes(b2_ctx *ctx, const uint64_t *const *ciphers, const size_
     if (cudaMallocFromPoolAsync((void **)&d_scale, nl * sizeof(Tw), pool, stream) != cudaSuccess) { d_scale = nullptr; return fail(cuda_fail(cudaGetLastError(), "cudaMallocFromPoolAsync(pack scale)")); }
     if (cudaMemcpyAsync(d_scale, scale.data(), nl * sizeof(Tw), cudaMemcpyHostToDevice, stream) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaMemcpyAsync(pack scale)"));
     const u64 *const *init_src = d_ciphers;
-    std::vector<uint64_t> blob2;
-    if (input_ntt_form) {
-        // inverse transforms of the inputs into a staging area [count][ctw], one launch; the init kernel then reads from there
-        if (cudaMallocFromPoolAsync((void **)&staged, count * ctw * 8 + count * 8, pool, stream) != cudaSuccess) { staged = nullptr; return fail(cuda_fail(cudaGetLastError(), "cudaMallocFromPoolAsync(pack staging)")); }
-        std::vector<uint64_t *> souts(count);
-        for (size_t i = 0; i < count; i++) souts[i] = (uint64_t *)(staged + i * ctw);
-        st = b2_ntt_inverse_ptrs(ctx, ciphers, souts.data(), count, 2, nl, B2_TABLES_COMPONENTWISE, 0, 0, stream_);
-        if (st == B2_OK) {
-            blob2.resize(count);
-            for (size_t i = 0; i < count; i++) blob2[i] = (uint64_t)(uintptr_t)souts[i];
-            u64 *ptab = staged + count * ctw;
-            if (cudaMemcpyAsync(ptab, blob2.data(), count * 8, cudaMemcpyHostToDevice, stream) != cudaSuccess) st = cuda_fail(cudaGetLastError(), "cudaMemcpyAsync(pack staging table)");
-            init_src = (const u64 *const *)ptab;
-        }
-    }
     if (st == B2_OK) {
         const u64 total = (u64)slots * ctw;
         pack_init_kernel<<<pk_grid(total), 256, 0, stream>>>(init_src, d_src, A, ctx->d_mods, d_scale, (u32)nl, ctx->logn, (u32)shift, total);
@@ -261,7 +220,165 @@ b2_status b2_pack_rlwes(b2_ctx *ctx, const uint64_t *const *ciphers, const size_
     }
     for (size_t g = 0; g < groups && st == B2_OK; g++)
         if (cudaMemcpyAsync(outs[g], cur + g * ctw, ctw * 8, cudaMemcpyDeviceToDevice, stream) != cudaSuccess) st = cuda_fail(cudaGetLastError(), "cudaMemcpyAsync(pack result)");
-    return fail(st);      // releases the arena, the scale table and the staging area (stream-ordered: after the work enqueued above)
+    return fail(st);      // releases the arena and the scale table (stream-ordered: after the work enqueued above)
+}
+
+// argument checks shared by the two packing entry points (evaluator_lwes.cu:324-339 and the key look-ups of GaloisKeys::key)
+static b2_status pack_check(b2_ctx *ctx, const size_t *counts, size_t groups, size_t nl, size_t shift, size_t input_interval, size_t output_interval,
+                            const uint64_t *galois_elements, const b2_kswitch_key *const *keys, size_t n_keys, bool trace, uint64_t *const *outs, size_t *count_out) {
+    const size_t n = ctx->n;
+    B2_REQUIRE(nl >= 1 && nl + 1 <= ctx->K, "bad level (packing needs a special prime)");
+    B2_REQUIRE(input_interval >= 1 && input_interval <= n, "input_interval must be less than poly_modulus_degree.");
+    B2_REQUIRE(output_interval <= input_interval && output_interval >= 1, "output_interval must be less than input_interval.");
+    B2_REQUIRE((input_interval & (input_interval - 1)) == 0, "input_interval must be power of two.");
+    B2_REQUIRE((output_interval & (output_interval - 1)) == 0, "output_interval must be power of two.");
+    const size_t M = input_interval / output_interval;
+    size_t count = 0;
+    for (size_t g = 0; g < groups; g++) {
+        B2_REQUIRE(counts[g] >= 1 && counts[g] <= M, "ciphers count must be less than input_interval / output_interval.");
+        B2_REQUIRE(outs[g] && (((uintptr_t)outs[g]) & 15) == 0, "null or misaligned output");
+        count += counts[g];
+    }
+    B2_REQUIRE(shift < 2 * n, "shift must be below 2N");
+    B2_REQUIRE(ctx->scheme != B2_SCHEME_BGV || ctx->t > 1, "BGV needs a plain modulus");
+    size_t layers = 0;
+    while (((size_t)1 << layers) < M) layers++;
+    // every key the tree and the trace will use must be present before anything is enqueued
+    for (size_t l = 0; l < layers; l++)
+        B2_REQUIRE(find_key(galois_elements, keys, n_keys, (n / input_interval) * ((uint64_t)1 << (l + 1)) + 1), "Galois key not present");
+    if (trace)
+        for (size_t deg = n; deg > n / output_interval; deg >>= 1) B2_REQUIRE(find_key(galois_elements, keys, n_keys, deg + 1), "Galois key not present");
+    *count_out = count;
+    return B2_OK;
+}
+
+// LWE (c0 [nl] scalars, c1 [nl][N]) -> RLWE [2][nl][N]: c_0 = the constant polynomial c0, c_1 = c1   (src/lwe_ciphertext.cu:12-22)
+__global__ void __launch_bounds__(256) lwe_assemble_kernel(const u64 *const *__restrict__ c0s, const u64 *const *__restrict__ c1s, u64 *const *__restrict__ outs,
+                                                           u32 nl, u32 n, u64 total) {
+    for (u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (u64)gridDim.x * blockDim.x) {
+        const u64 per = (u64)nl * n, b = v / per, r = v % per;
+        const u32 x = (u32)(r % n), j = (u32)(r / n);
+        u64 *o = outs[b];
+        o[r] = x == 0 ? c0s[b][j] : 0;
+        o[per + r] = c1s[b][r];
+    }
+}
+// RLWE (coefficient form) -> LWE of coefficient `term`: c1 = x^(2N - term) c_1 (term > 0), c0[j] = c_0[j][term]   (src/evaluator_lwes.cu:51-94)
+__global__ void __launch_bounds__(256) lwe_extract_kernel(const u64 *__restrict__ ct, u64 *__restrict__ c0, u64 *__restrict__ c1, const ModInfo *__restrict__ mods,
+                                                          u32 nl, u32 n, u32 term, u32 shift, u64 total) {
+    for (u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (u64)gridDim.x * blockDim.x) {
+        const u32 x = (u32)(v % n), j = (u32)(v / n);
+        const u64 p = mods[j].p;
+        const u32 src = (x - shift) & (n - 1);
+        const bool neg = ((src + shift) & n) != 0;
+        const u64 val = ct[((u64)nl + j) * n + src];
+        c1[v] = (neg && val) ? p - val : val;
+        if (x == 0) c0[j] = ct[(u64)j * n + term];
+    }
+}
+}  // namespace b2
+
+extern "C" {
+
+// Evaluator::pack_rlwe_ciphertexts_new / pack_rlwe_ciphertexts_batched for `groups` groups packed side by side (every layer is one fused
+// launch + one batched keyswitch over ALL groups).  ciphers: HOST array of sum(counts) DEVICE pointers (group after group), each
+// [2][nl][N] in the form given by input_ntt_form; counts: HOST [groups]; galois_elements / keys: the automorphism keys (GaloisKeys) as
+// parallel HOST arrays; outs: HOST array of `groups` DEVICE pointers, each [2][nl][N], NTT form iff output_ntt_form (the reference: CKKS /
+// BGV).  Everything is enqueued on `stream`; the arena is stream-ordered memory.
+b2_status b2_pack_rlwes(b2_ctx *ctx, const uint64_t *const *ciphers, const size_t *counts, size_t groups, int input_ntt_form, size_t nl, size_t shift,
+                        size_t input_interval, size_t output_interval, const uint64_t *galois_elements, const b2_kswitch_key *const *keys, size_t n_keys,
+                        int apply_field_trace, int output_ntt_form, uint64_t *const *outs, void *stream_) {
+    B2_REQUIRE(ctx && ciphers && counts && outs && (n_keys == 0 || (galois_elements && keys)), "null argument");
+    if (groups == 0) return B2_OK;
+    const bool trace = output_interval != 1 && apply_field_trace;
+    size_t count = 0;
+    b2_status st = pack_check(ctx, counts, groups, nl, shift, input_interval, output_interval, galois_elements, keys, n_keys, trace, outs, &count);
+    if (st != B2_OK) return st;
+    for (size_t i = 0; i < count; i++) B2_REQUIRE(ciphers[i] && (((uintptr_t)ciphers[i]) & 15) == 0, "null or misaligned ciphertext");
+    B2_CUDA(cudaSetDevice(ctx->device));
+    if (!input_ntt_form) return pack_run(ctx, ciphers, counts, groups, count, nl, shift, input_interval, output_interval, galois_elements, keys, n_keys, trace, output_ntt_form, outs, stream_);
+    // NTT-form inputs: one batched inverse transform into a staging area, which the tree then reads
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t ctw = 2 * nl * ctx->n;
+    cudaMemPool_t pool;
+    st = arena_pool(ctx, &pool);
+    if (st != B2_OK) return st;
+    uint64_t *staged = nullptr;
+    B2_CUDA(cudaMallocFromPoolAsync((void **)&staged, count * ctw * 8, pool, stream));
+    std::vector<uint64_t *> souts(count);
+    for (size_t i = 0; i < count; i++) souts[i] = staged + i * ctw;
+    st = b2_ntt_inverse_ptrs(ctx, ciphers, souts.data(), count, 2, nl, B2_TABLES_COMPONENTWISE, 0, 0, stream_);
+    if (st == B2_OK) st = pack_run(ctx, souts.data(), counts, groups, count, nl, shift, input_interval, output_interval, galois_elements, keys, n_keys, trace, output_ntt_form, outs, stream_);
+    cudaFreeAsync(staged, stream);
+    return st;
+}
+
+// LWECiphertext::assemble_lwe_batched (src/lwe_ciphertext.cu:74-140): c0s[b] DEVICE [nl], c1s[b] DEVICE [nl][N] -> outs[b] DEVICE [2][nl][N] (coefficient form), one launch
+b2_status b2_assemble_lwes(b2_ctx *ctx, const uint64_t *const *c0s, const uint64_t *const *c1s, uint64_t *const *outs, size_t count, size_t nl, void *stream_) {
+    B2_REQUIRE(ctx && (count == 0 || (c0s && c1s && outs)) && nl >= 1 && nl <= ctx->K, "bad arguments");
+    if (count == 0) return B2_OK;
+    for (size_t i = 0; i < count; i++) B2_REQUIRE(c0s[i] && c1s[i] && outs[i], "null operand in batch");
+    B2_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    Scratch sc(ctx, stream);
+    b2_status st = ensure_ptrtab(sc.s, stream, 3 * count * 8);
+    if (st != B2_OK) return st;
+    std::vector<uint64_t> blob(3 * count);
+    for (size_t i = 0; i < count; i++) { blob[i] = (uint64_t)(uintptr_t)c0s[i]; blob[count + i] = (uint64_t)(uintptr_t)c1s[i]; blob[2 * count + i] = (uint64_t)(uintptr_t)outs[i]; }
+    B2_CUDA(cudaMemcpyAsync(sc->ptrtab, blob.data(), blob.size() * 8, cudaMemcpyHostToDevice, stream));
+    const u64 *const *t = (const u64 *const *)sc->ptrtab;
+    const u64 total = (u64)count * nl * ctx->n;
+    lwe_assemble_kernel<<<pk_grid(total), 256, 0, stream>>>(t, t + count, (u64 *const *)(t + 2 * count), (u32)nl, (u32)ctx->n, total);
+    count_launches(1);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
+// Evaluator::extract_lwe_new (src/evaluator_lwes.cu:51-94) on a coefficient-form ciphertext ct [2][nl][N]: c0 DEVICE [nl], c1 DEVICE [nl][N], one launch
+b2_status b2_extract_lwe(b2_ctx *ctx, const uint64_t *ct, size_t term, size_t nl, uint64_t *c0, uint64_t *c1, void *stream_) {
+    B2_REQUIRE(ctx && ct && c0 && c1 && nl >= 1 && nl <= ctx->K && term < ctx->n, "bad arguments (term must be below N)");
+    B2_REQUIRE(ct != c1, "out of place only");
+    B2_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t n = ctx->n;
+    const u64 total = (u64)nl * n;
+    lwe_extract_kernel<<<pk_grid(total), 256, 0, stream>>>((const u64 *)ct, (u64 *)c0, (u64 *)c1, ctx->d_mods, (u32)nl, (u32)n, (u32)term, (u32)(term == 0 ? 0 : 2 * n - term), total);
+    count_launches(1);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
+// Evaluator::pack_lwe_ciphertexts_new / _batched (src/evaluator_lwes.cu:201-303): assemble every LWE into an RLWE (one launch for all groups) and pack each
+// group of counts[g] LWEs into one ciphertext: input_interval = N, output_interval = N / 2^ceil(log2 counts[g]) — all groups must share it (the reference's
+// batched form requires equal group sizes up to the power of two as well).
+b2_status b2_pack_lwes(b2_ctx *ctx, const uint64_t *const *c0s, const uint64_t *const *c1s, const size_t *counts, size_t groups, size_t nl, const uint64_t *galois_elements,
+                       const b2_kswitch_key *const *keys, size_t n_keys, int apply_field_trace, int output_ntt_form, uint64_t *const *outs, void *stream_) {
+    B2_REQUIRE(ctx && c0s && c1s && counts && outs && (n_keys == 0 || (galois_elements && keys)), "null argument");
+    if (groups == 0) return B2_OK;
+    const size_t n = ctx->n;
+    size_t l = 0, maxc = 0;
+    for (size_t g = 0; g < groups; g++) { B2_REQUIRE(counts[g] >= 1, "LWE ciphertexts must not be empty."); maxc = std::max(maxc, counts[g]); }
+    B2_REQUIRE(maxc <= n, "LWE ciphertexts count must be less than poly_modulus_degree.");
+    while (((size_t)1 << l) < maxc) l++;
+    const size_t output_interval = n >> l;
+    const bool trace = output_interval != 1 && apply_field_trace;
+    size_t count = 0;
+    b2_status st = pack_check(ctx, counts, groups, nl, 0, n, output_interval, galois_elements, keys, n_keys, trace, outs, &count);
+    if (st != B2_OK) return st;
+    B2_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t ctw = 2 * nl * n;
+    cudaMemPool_t pool;
+    st = arena_pool(ctx, &pool);
+    if (st != B2_OK) return st;
+    uint64_t *staged = nullptr;
+    B2_CUDA(cudaMallocFromPoolAsync((void **)&staged, count * ctw * 8, pool, stream));
+    std::vector<uint64_t *> souts(count);
+    for (size_t i = 0; i < count; i++) souts[i] = staged + i * ctw;
+    st = b2_assemble_lwes(ctx, c0s, c1s, souts.data(), count, nl, stream_);
+    if (st == B2_OK) st = pack_run(ctx, souts.data(), counts, groups, count, nl, 0, n, output_interval, galois_elements, keys, n_keys, trace, output_ntt_form, outs, stream_);
+    cudaFreeAsync(staged, stream);
+    return st;
 }
 
 }  // extern "C"

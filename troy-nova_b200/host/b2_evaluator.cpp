@@ -533,6 +533,83 @@ Ciphertext Evaluator::pack_rlwe_ciphertexts_new(const std::vector<const Cipherte
     return out;
 }
 
+// ---- LWE (src/lwe_ciphertext.cu, src/evaluator_lwes.cu:51-94, 201-303) ------------------------------------------------------------------
+LWECiphertext::LWECiphertext(const HeContextPointer &ctx, size_t coeff_modulus_size)
+    : ctx_(ctx), limbs_(coeff_modulus_size), c0_(ctx, (coeff_modulus_size + 1) & ~(size_t)1), c1_(ctx, coeff_modulus_size * ctx->poly_modulus_degree()) {}
+std::vector<uint64_t> LWECiphertext::c0_to_host() const { std::vector<uint64_t> v(limbs_); if (limbs_) c0_.download(v.data(), limbs_); return v; }
+std::vector<uint64_t> LWECiphertext::c1_to_host() const { std::vector<uint64_t> v(c1_.size()); if (!v.empty()) c1_.download(v.data(), v.size()); return v; }
+Ciphertext LWECiphertext::assemble_lwe() const {
+    if (empty()) throw std::invalid_argument("[LWECiphertext::assemble_lwe] LWE ciphertext is empty.");
+    Ciphertext r(ctx_, 2, limbs_, false);
+    r.scale() = scale_; r.correction_factor() = cf_;
+    const uint64_t *p0 = c0_.data(), *p1 = c1_.data();
+    uint64_t *o = r.data();
+    check(b2_assemble_lwes(ctx_->raw(), &p0, &p1, &o, 1, limbs_, ctx_->stream), "[LWECiphertext::assemble_lwe]");
+    return r;
+}
+LWECiphertext Evaluator::extract_lwe_new(const Ciphertext &e, size_t term) const {
+    check_ct("[Evaluator::extract_lwe_new]", e);
+    if (e.contains_seed()) throw std::invalid_argument("[Evaluator::extract_lwe_new] Ciphertext contains a seed.");
+    if (e.polynomial_count() != 2) throw std::invalid_argument("[Evaluator::extract_lwe_new] Ciphertext size must be 2.");
+    if (e.is_ntt_form()) {          // evaluator_lwes.cu:56-60
+        Ciphertext t;
+        transform_from_ntt(e, t);
+        return extract_lwe_new(t, term);
+    }
+    if (term >= context_->poly_modulus_degree()) throw std::invalid_argument("[Evaluator::extract_lwe_new] term out of range.");
+    LWECiphertext r(context_, e.coeff_modulus_size());
+    r.scale() = e.scale(); r.correction_factor() = e.correction_factor();
+    check(b2_extract_lwe(context_->raw(), e.data(), term, e.coeff_modulus_size(), r.c0(), r.c1(), context_->stream), "[Evaluator::extract_lwe_new]");
+    return r;
+}
+void Evaluator::pack_lwe_ciphertexts_batched(const std::vector<std::vector<const LWECiphertext *>> &groups, const GaloisKeys &akeys, const std::vector<Ciphertext *> &outputs,
+                                             bool apply_field_trace) const {
+    if (groups.size() != outputs.size()) throw std::invalid_argument("[Evaluator::pack_lwe_ciphertexts_batched] Input groups and outputs should have same size.");
+    if (groups.empty()) return;
+    const size_t n = context_->poly_modulus_degree();
+    std::vector<const uint64_t *> c0s, c1s;
+    std::vector<size_t> counts;
+    size_t nl = 0, maxc = 0;
+    for (const auto &g : groups) {
+        if (g.empty()) throw std::invalid_argument("[Evaluator::pack_lwe_ciphertexts_new] LWE ciphertexts must not be empty.");
+        if (g.size() > n) throw std::invalid_argument("[Evaluator::pack_lwe_ciphertexts_new] LWE ciphertexts count must be less than poly_modulus_degree.");
+        for (const LWECiphertext *l : g) {
+            if (!l || l->empty()) throw std::invalid_argument("[Evaluator::pack_lwe_ciphertexts_new] LWE ciphertexts must not be empty.");
+            if (nl == 0) nl = l->coeff_modulus_size();
+            if (l->coeff_modulus_size() != nl || l->context().get() != context_.get()) throw std::invalid_argument("[Evaluator::pack_lwe_ciphertexts_new] LWE ciphertexts must have same parms id.");
+            c0s.push_back(l->c0()); c1s.push_back(l->c1());
+        }
+        counts.push_back(g.size()); maxc = std::max(maxc, g.size());
+    }
+    size_t l2 = 0;
+    while (((size_t)1 << l2) < maxc) l2++;
+    const size_t output_interval = n >> l2;
+    std::vector<uint64_t> elts;
+    for (size_t l = 0; l < l2; l++) elts.push_back(((uint64_t)1 << (l + 1)) + 1);
+    if (output_interval != 1 && apply_field_trace) for (size_t deg = n; deg > n / output_interval; deg >>= 1) elts.push_back(deg + 1);
+    std::vector<const b2_kswitch_key *> keys;
+    for (uint64_t e : elts) {
+        if (!akeys.has_key((size_t)e)) throw std::invalid_argument("[GaloisKeys::key] Galois key not present");
+        keys.push_back(akeys.key(GaloisKeys::get_index((size_t)e)));
+    }
+    const bool out_ntt = context_->scheme() != SchemeType::BFV;
+    std::vector<Ciphertext> res(groups.size());
+    std::vector<uint64_t *> op(groups.size());
+    for (size_t g = 0; g < groups.size(); g++) {
+        res[g] = Ciphertext(context_, 2, nl, out_ntt);
+        res[g].scale() = groups[g][0]->scale(); res[g].correction_factor() = groups[g][0]->correction_factor();
+        op[g] = res[g].data();
+    }
+    check(b2_pack_lwes(context_->raw(), c0s.data(), c1s.data(), counts.data(), groups.size(), nl, elts.data(), keys.data(), elts.size(), apply_field_trace ? 1 : 0, out_ntt ? 1 : 0,
+                       op.data(), context_->stream), "[Evaluator::pack_lwe_ciphertexts_batched]");
+    for (size_t g = 0; g < groups.size(); g++) *outputs[g] = std::move(res[g]);
+}
+Ciphertext Evaluator::pack_lwe_ciphertexts_new(const std::vector<const LWECiphertext *> &lwes, const GaloisKeys &akeys, bool apply_field_trace) const {
+    Ciphertext out;
+    pack_lwe_ciphertexts_batched({lwes}, akeys, {&out}, apply_field_trace);
+    return out;
+}
+
 // Evaluator::translate_plain (src/evaluator_translate_plain.cu:95-170)
 void Evaluator::translate_plain(const Ciphertext &e, const Plaintext &p, Ciphertext &d, bool subtract) const {
     check_ct("[Evaluator::translate_plain]", e);

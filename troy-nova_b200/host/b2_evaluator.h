@@ -155,6 +155,35 @@ private:
     DeviceArray buf_;
 };
 
+// src/lwe_ciphertext.h: c0 = coeff_modulus_size scalars, c1 = [coeff_modulus_size][N]; produced by Evaluator::extract_lwe_new, consumed by
+// assemble_lwe / Evaluator::pack_lwe_ciphertexts_new
+class LWECiphertext {
+public:
+    LWECiphertext() = default;
+    LWECiphertext(const HeContextPointer &ctx, size_t coeff_modulus_size);
+    Ciphertext assemble_lwe() const;                                     // RLWE with c_0 = the constant polynomial c0, c_1 = c1, coefficient form
+    const HeContextPointer &context() const { return ctx_; }
+    size_t coeff_modulus_size() const { return limbs_; }
+    double scale() const { return scale_; }
+    double &scale() { return scale_; }
+    uint64_t correction_factor() const { return cf_; }
+    uint64_t &correction_factor() { return cf_; }
+    const uint64_t *c0() const { return c0_.data(); }
+    uint64_t *c0() { return c0_.data(); }
+    const uint64_t *c1() const { return c1_.data(); }
+    uint64_t *c1() { return c1_.data(); }
+    std::vector<uint64_t> c0_to_host() const;
+    std::vector<uint64_t> c1_to_host() const;
+    bool empty() const { return c1_.size() == 0; }
+
+private:
+    HeContextPointer ctx_;
+    size_t limbs_ = 0;
+    double scale_ = 1.0;
+    uint64_t cf_ = 1;
+    DeviceArray c0_, c1_;
+};
+
 // src/kswitch_keys.h: keys()[index] = vector of `digits` public keys, each a 2-polynomial key-level NTT-form ciphertext.
 class KSwitchKeys {
 public:
@@ -276,6 +305,12 @@ public:
                                          size_t output_interval, bool apply_field_trace = true) const;
     void pack_rlwe_ciphertexts_batched(const std::vector<std::vector<const Ciphertext *>> &cipher_groups, const GaloisKeys &automorphism_keys, size_t shift,
                                        size_t input_interval, size_t output_interval, const std::vector<Ciphertext *> &outputs, bool apply_field_trace = true) const;
+
+    // ---- LWE extraction and packing (src/evaluator_lwes.cu:51-94, 201-303)
+    LWECiphertext extract_lwe_new(const Ciphertext &encrypted, size_t term) const;
+    Ciphertext pack_lwe_ciphertexts_new(const std::vector<const LWECiphertext *> &lwes, const GaloisKeys &automorphism_keys, bool apply_field_trace = true) const;
+    void pack_lwe_ciphertexts_batched(const std::vector<std::vector<const LWECiphertext *>> &lwes_groups, const GaloisKeys &automorphism_keys,
+                                      const std::vector<Ciphertext *> &outputs, bool apply_field_trace = true) const;
 
     // ---- ct +/- pt (src/evaluator_translate_plain.cu:13-170): BFV with a mod-t plaintext (scale-up fused with the addition, one launch)
     //      or an RNS plaintext of the same form; CKKS with an NTT-form RNS plaintext of equal scale

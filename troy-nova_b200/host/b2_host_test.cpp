@@ -137,6 +137,10 @@ int main(int argc, char **argv) {
             {                                                                           // 34: RLWE packing of three ciphertexts (two layers, no trace): keys 3 and 5
                 Ciphertext packed = ev.pack_rlwe_ciphertexts_new({&a, &b, &r}, gk, 0, n, n / 4, false);
                 emit(packed);
+                LWECiphertext l0 = ev.extract_lwe_new(a, 0), l7 = ev.extract_lwe_new(b, 7), l9 = ev.extract_lwe_new(r, 9);       // 35-37: NTT-form inputs are transformed first
+                { const std::vector<uint64_t> v0 = l7.c0_to_host(), v1 = l7.c1_to_host(); out.insert(out.end(), v0.begin(), v0.end()); out.insert(out.end(), v1.begin(), v1.end()); }
+                emit(l9.assemble_lwe());
+                emit(ev.pack_lwe_ciphertexts_new({&l0, &l7, &l9}, gk, false));                                                       //        three LWEs -> N / 4 slots, keys 3 and 5
                 GaloisKeys none(ctx);
                 cprobe([&] { ev.pack_rlwe_ciphertexts_new({&a, &b}, none, 0, n, n / 2, false); });          // key missing
                 cprobe([&] { ev.pack_rlwe_ciphertexts_new({&a, &b, &r}, gk, 0, n, n / 2, false); });        // more ciphertexts than slots
