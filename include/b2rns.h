@@ -232,6 +232,13 @@ b2_status b2_encrypt_zero_asymmetric(b2_ctx *ctx, const uint64_t *pk, size_t nl,
  * receives the seed of a's generator, which the reference stores in the ciphertext when save_seed != 0. */
 b2_status b2_encrypt_zero_symmetric(b2_ctx *ctx, const uint64_t *sk, size_t nl, int is_ntt_form, int save_seed, b2_prng *c1_prng, b2_prng *e_prng, uint64_t *ct,
                                     uint64_t *seed_out, void *stream);
+/* KeyGenerator (src/key_generator.cu): with the generator in the state of the reference's context generator the keys equal the reference's.
+ *   secret key (:31-58)                sk [K][N] = NTT(ternary sample)
+ *   public key (:60-78)                = b2_encrypt_zero_symmetric(sk, K, ntt = 1, save_seed = 0) at the key level
+ *   key-switching key (:136-157)       out [K-1][2][K][N]: digit i = symmetric encryption of zero at the key level + (P mod q_i) new_key in limb i of c_0;
+ *                                      new_key [K][N] NTT form = s^2 (relinearisation; b2_secret_key_powers) or the Galois image of s (rotations; b2_galois) */
+b2_status b2_generate_secret_key(b2_ctx *ctx, b2_prng *g, uint64_t *sk, void *stream);
+b2_status b2_generate_kswitch_key(b2_ctx *ctx, const uint64_t *sk, const uint64_t *new_key, b2_prng *g, uint64_t *out, void *stream);
 /* scaling_variant::scale_up = multiply_translate_plain (src/fgk/translate_plain.cu:6-70): BFV, plain = plain_count words modulo t;
  * dest[j][x] = from[j][x] +/- round(q/t m_x) mod q_j for x < plain_count (from == NULL: zero; from == dest allowed), [nl][N].
  * This is the c_0 update of Encryptor::encrypt and of Evaluator::add_plain / sub_plain. */

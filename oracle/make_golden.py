@@ -121,6 +121,20 @@ def main_encrypt():
     print("wrote encrypt", len(g), "arrays")
 
 
+def main_keygen():
+    """tests/golden/ref_keygen_n256.npz: the reference's KeyGenerator from a context seed (src/key_generator.cu): secret key, public key, relinearisation key and
+    two Galois keys, in the order they were drawn from the context's generator."""
+    g = {"n": N, "bits": np.array(BITS), "seed": np.uint64(0xabcdef12345)}
+    for scheme, name in ((po.BFV, "bfv"), (po.CKKS, "ckks"), (po.BGV, "bgv")):
+        r = po.Reference(scheme, N, BITS, t_bits=20, seed=0xabcdef12345)
+        r.gen_relin(); r.gen_galois([3, 2 * N - 1])
+        g[name + "_moduli"] = r.moduli; g[name + "_t"] = np.uint64(r.t)
+        g[name + "_sk"] = r.secret_key(); g[name + "_pk"] = r.public_key(); g[name + "_relin"] = r.relin_key()
+        g[name + "_galois_3"] = r.galois_key(3); g[name + "_galois_conj"] = r.galois_key(2 * N - 1)
+    np.savez_compressed(os.path.join(OUT, "ref_keygen_n256.npz"), **g)
+    print("wrote keygen", len(g), "arrays")
+
+
 PACK_CASES = ((4, 0, 64, 16, 1), (3, 0, 64, 16, 1), (8, 5, 64, 8, 0), (2, 0, 32, 16, 1), (1, 0, 64, 64, 1), (5, 3, 64, 8, 1))
 
 
@@ -156,9 +170,11 @@ def main_pack():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "pack":
         main_pack()
+    elif len(sys.argv) > 1 and sys.argv[1] == "keygen":
+        main_keygen()
     elif len(sys.argv) > 1 and sys.argv[1] == "decrypt":
         main_decrypt()
     elif len(sys.argv) > 1 and sys.argv[1] == "encrypt":
         main_encrypt()
     else:
-        main(); main_decrypt(); main_encrypt(); main_pack()
+        main(); main_decrypt(); main_encrypt(); main_pack(); main_keygen()

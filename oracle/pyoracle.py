@@ -115,6 +115,8 @@ def lib():
         L.ro_bfv_scale_up.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_size_t, u64p, C.c_int, u64p]
         L.ro_centralize.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_size_t, u64p]
         L.ro_encrypt.argtypes = [C.c_void_p, u64p, C.c_size_t, u64p, C.c_int, C.c_size_t, u64p, u64p, u64p]
+        L.ro_keygen_secret_prng.argtypes = [C.c_void_p, u64p, u64p]
+        L.ro_keygen_kswitch_prng.argtypes = [C.c_void_p, u64p, u64p, u64p, u64p]
         L.ro_fnv1a64.restype = C.c_uint64
         L.ro_fnv1a64.argtypes = [u64p, C.c_size_t]
         _lib = L
@@ -383,6 +385,14 @@ class Oracle:
         e_st = c1_st if e_st is None else e_st
         seed = self.L.ro_encrypt_zero_symmetric(self.h, _p(sk), nl, int(is_ntt), int(save_seed), _p(c1_st), _p(e_st), _p(ct))
         return ct, int(seed)
+
+    def keygen_secret_prng(self, st):
+        sk = np.zeros(self.nm * self.n, dtype=np.uint64)
+        self.L.ro_keygen_secret_prng(self.h, _p(st), _p(sk)); return sk
+
+    def keygen_kswitch_prng(self, sk, new_key, st):
+        out = np.zeros(max(self.nm - 1, 1) * 2 * self.nm * self.n, dtype=np.uint64)
+        self.L.ro_keygen_kswitch_prng(self.h, _p(np.ascontiguousarray(sk, dtype=np.uint64)), _p(np.ascontiguousarray(new_key, dtype=np.uint64)), _p(st), _p(out)); return out
 
     def bfv_scale_up(self, plain, nl, frm=None, subtract=False):
         plain = np.ascontiguousarray(plain, dtype=np.uint64)

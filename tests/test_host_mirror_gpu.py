@@ -92,6 +92,15 @@ def test_host_mirror_script(po, scheme, tmp_path):
     l0, l7, l9 = o.extract_lwe(coeff(a), 0, L), o.extract_lwe(coeff(b), 7, L), o.extract_lwe(coeff(r), 9, L)
     want += [("extract_lwe c0", l7[0]), ("extract_lwe c1", l7[1]), ("assemble_lwe", o.assemble_lwe(l9[0], l9[1], L)),
              ("pack_lwe_ciphertexts_new", o.pack_lwes([l0, l7, l9], L, {3: gkeys[3], 5: gkeys[5]}, False))]
+    kst = o.prng_state(0x5eed)
+    ksk = o.keygen_secret_prng(kst)
+    kpk, _ = o.encrypt_zero_symmetric(ksk, K, True, False, kst)
+    krk = o.keygen_kswitch_prng(ksk, o.secret_key_powers(ksk, 2)[K * n:], kst)
+    kgk = o.keygen_kswitch_prng(ksk, o.galois(ksk, 3, 1, K, True), kst)
+    kpk2, _ = o.encrypt_zero_symmetric(ksk, K, True, False, kst)                 # the second create_public_key call of the script
+    kct = o.encrypt(msg, kpk2, True, L, o.prng_state(99))
+    want += [("KeyGenerator secret key", ksk), ("public key", kpk), ("relinearisation key", krk), ("Galois key", kgk),
+             ("decrypt(encrypt(m)) under generated keys", o.decrypt(kct, 2, L, o.secret_key_powers(ksk, 1)))]
     pos = 0
     for name, exp in want:
         got = out[pos:pos + exp.size]; pos += exp.size

@@ -186,6 +186,28 @@ def test_oracle_packing_reproduces_reference_golden(po):
                 assert np.array_equal(got, g["%s_c%d_out%d" % (name, ci, inp_ntt)]), (name, ci, inp_ntt)
 
 
+def _replay_keygen(po, o, seed, n):
+    K = o.nm
+    st = o.prng_state(seed)
+    sk = o.keygen_secret_prng(st)
+    pk, _ = o.encrypt_zero_symmetric(sk, K, True, False, st)
+    relin = o.keygen_kswitch_prng(sk, o.secret_key_powers(sk, 2)[K * n:], st)
+    g3 = o.keygen_kswitch_prng(sk, o.galois(sk, 3, 1, K, True), st)
+    gc = o.keygen_kswitch_prng(sk, o.galois(sk, 2 * n - 1, 1, K, True), st)
+    return sk, pk, relin, g3, gc
+
+
+def test_oracle_keygen_reproduces_reference_golden(po):
+    """KeyGenerator from a context seed (src/key_generator.cu:31-78,136-256): every key the unmodified reference generated, in its drawing order"""
+    g = np.load(os.path.join(GOLD, "ref_keygen_n256.npz"))
+    n = int(g["n"])
+    for scheme, name in ((po.BFV, "bfv"), (po.CKKS, "ckks"), (po.BGV, "bgv")):
+        o = po.Oracle(8, g[name + "_moduli"], int(g[name + "_t"]) if scheme != po.CKKS else 0, scheme)
+        sk, pk, relin, g3, gc = _replay_keygen(po, o, int(g["seed"]), n)
+        for got, key in ((sk, "_sk"), (pk, "_pk"), (relin, "_relin"), (g3, "_galois_3"), (gc, "_galois_conj")):
+            assert np.array_equal(got, g[name + key]), (name, key)
+
+
 # ---- (iii) live against the compiled reference --------------------------------------------------
 SURVEY_FPR = {2: ("3866d51961505bd9", "c59ae60bda39e030", "a0e0a04249a08cd3", "4a186e8776597c7e", "eb819b8149c577a2"),
               3: ("82ff3df13af52835", "2046b27467209ab9", "a967cf538de6dc20", "def3d7ec042efe31", "e11839bb23d6a573"),
@@ -264,6 +286,19 @@ def test_live_reference_encryptor(po, scheme, bits, t_bits):
     for plain in plains:
         for asym in (True, False):
             assert np.array_equal(r.encrypt_seeded(plain, asym, L, 4242)[0], o.encrypt(plain, pk if asym else sk, asym, L, o.prng_state(4242))), ("enc", asym)
+
+
+@pytest.mark.parametrize("scheme,bits", [(1, [40, 40, 50, 55]), (2, [50, 40, 40, 55]), (3, [60, 60, 60])])
+def test_live_reference_keygen(po, scheme, bits):
+    if not po.ref_available():
+        pytest.skip("oracle/_ref not built")
+    n, S = 1024, 0x77aa55
+    r = po.Reference(scheme, n, bits, t_bits=20, seed=S)
+    r.gen_relin(); r.gen_galois([3, 2 * n - 1])
+    o = po.Oracle(10, r.moduli, r.t if scheme != po.CKKS else 0, scheme)
+    sk, pk, relin, g3, gc = _replay_keygen(po, o, S, n)
+    assert np.array_equal(sk, r.secret_key()) and np.array_equal(pk, r.public_key())
+    assert np.array_equal(relin, r.relin_key()) and np.array_equal(g3, r.galois_key(3)) and np.array_equal(gc, r.galois_key(2 * n - 1))
 
 
 @pytest.mark.parametrize("scheme,bits", [(1, [40, 40, 50]), (2, [40, 40, 50]), (3, [40, 45, 55])])

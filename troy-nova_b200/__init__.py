@@ -104,6 +104,8 @@ _SIGS.update({
     "b2_extract_lwe": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, vp, vp, vp]),
     "b2_assemble_lwes": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.c_size_t, C.c_size_t, vp]),
     "b2_pack_lwes": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t), C.c_size_t, C.c_size_t, u64p, C.POINTER(vp), C.c_size_t, C.c_int, C.c_int, C.POINTER(vp), vp]),
+    "b2_generate_secret_key": (C.c_int, [vp, vp, vp, vp]),
+    "b2_generate_kswitch_key": (C.c_int, [vp, vp, vp, vp, vp, vp]),
     "b2_secret_key_powers": (C.c_int, [vp, vp, C.c_size_t, vp, vp]),
     "b2_decrypt_phase": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, vp, vp]),
     "b2_decrypt_scale_and_round": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.c_size_t, C.c_size_t, vp]),
@@ -394,6 +396,13 @@ class Context:
         seed = C.c_uint64(0)
         _chk(self.L.b2_encrypt_zero_symmetric(self.h, _dptr(sk), nl, int(is_ntt), int(save_seed), C.byref(c1_prng), C.byref(e_prng), _dptr(ct), C.byref(seed), self._stream(stream)))
         return int(seed.value)
+
+    def generate_secret_key(self, g, sk, stream=None):
+        _chk(self.L.b2_generate_secret_key(self.h, C.byref(g), _dptr(sk), self._stream(stream))); return sk
+
+    def generate_kswitch_key(self, sk, new_key, g, out, stream=None):
+        """out [K-1][2][K][N]: KeyGenerator::generate_one_kswitch_key for new_key (s^2, or the Galois image of s)"""
+        _chk(self.L.b2_generate_kswitch_key(self.h, _dptr(sk), _dptr(new_key), C.byref(g), _dptr(out), self._stream(stream))); return out
 
     def bfv_scale_up(self, plain, plain_count, nl, dest, frm=None, subtract=False, stream=None):
         _chk(self.L.b2_bfv_scale_up(self.h, _dptr(plain), plain_count, nl, None if frm is None else _dptr(frm), int(subtract), _dptr(dest), self._stream(stream))); return dest

@@ -250,6 +250,12 @@ __global__ void __launch_bounds__(256) centralize_kernel(const u64 *__restrict__
     out[idx] = m >= ((t + 1) >> 1) ? submod(mq, barrett64(t, Q.p, Q.ratio), Q.p) : mq;
 }
 
+// key-switching key, digit i: c_0 limb i += (P mod q_i) * new_key limb i     (key_generator.cu:150-155)
+__global__ void __launch_bounds__(256) kskey_add_kernel(u64 *__restrict__ c0_limb, const u64 *__restrict__ new_key_limb, Tw factor, u64 p, u32 n) {
+    const u32 x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x < n) c0_limb[x] = addmod(c0_limb[x], shoup(new_key_limb[x], factor, p), p);
+}
+
 static uint64_t q_div_t_mod(const std::vector<uint64_t> &q, size_t nl, uint64_t t, uint64_t m) {     // floor(prod q / t) mod m
     std::vector<uint64_t> limbs{1};
     for (size_t i = 0; i < nl; i++) {
@@ -420,6 +426,38 @@ b2_status b2_encrypt_zero_symmetric(b2_ctx *ctx, const uint64_t *sk, size_t nl, 
     // ONE inverse transform over 2 nl limbs of the sample A: groups [0, nl) = sk o A -> c0 = -(. + scale e), groups [nl, 2 nl) = A -> c1
     for (size_t j = 0; j < nl; j++) g.push_back(LimbGroup{(u32)j, 1u, (u64)((nl + j) * n), 0});
     return run_ntt_dir<false>(ctx, sc.s, g, mid, SkMulLoad{A, (const u64 *)sk, ctx->d_mods, (u32)nl, (u32)n}, SymCoeffStore{c0, E, ctx->d_mods, (u32)nl, (u32)n, escale}, stream);
+}
+
+// KeyGenerator::KeyGenerator (src/key_generator.cu:31-58): sk [K][N] = NTT(ternary sample), two launches
+b2_status b2_generate_secret_key(b2_ctx *ctx, b2_prng *g, uint64_t *sk, void *stream_) {
+    B2_REQUIRE(ctx && g && sk && ((((uintptr_t)sk) & 15) == 0), "null or misaligned argument");
+    B2_CUDA(cudaSetDevice(ctx->device));
+    b2_status st = sample_locked(ctx, B2_SAMPLE_TERNARY, g, (u64 *)sk, 1, ctx->K, (cudaStream_t)stream_);
+    if (st != B2_OK) return st;
+    return b2_ntt_forward(ctx, sk, sk, 1, 1, ctx->K, B2_TABLES_COMPONENTWISE, 0, 0, stream_);
+}
+
+// KeyGenerator::generate_one_kswitch_key (src/key_generator.cu:136-157): out [K-1][2][K][N]; digit i is a symmetric encryption of zero at the key level
+// (NTT form, generator g for a's seed and for the noise, as rlwe::symmetric does) with (P mod q_i) new_key added into limb i of c_0.
+// new_key [K][N] NTT form: s^2 for relinearisation keys (b2_secret_key_powers), the Galois image of s for rotation keys (b2_galois, NTT form).
+b2_status b2_generate_kswitch_key(b2_ctx *ctx, const uint64_t *sk, const uint64_t *new_key, b2_prng *g, uint64_t *out, void *stream_) {
+    B2_REQUIRE(ctx && sk && new_key && g && out, "null argument");
+    B2_REQUIRE(ctx->K >= 2, "key switching needs a special prime");
+    B2_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t n = ctx->n, K = ctx->K, per = 2 * K * n;
+    const uint64_t P = ctx->q[K - 1];
+    for (size_t i = 0; i + 1 < K; i++) {
+        uint64_t *d = out + i * per;
+        b2_status st = b2_encrypt_zero_symmetric(ctx, sk, K, 1, 0, g, g, d, nullptr, stream_);
+        if (st != B2_OK) return st;
+        const uint64_t qi = ctx->q[i], f = P % qi;
+        Tw fw; fw.x = f; fw.y = host::shoup_quotient(f, qi);
+        kskey_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((u64 *)d + i * n, (const u64 *)new_key + i * n, fw, qi, (u32)n);
+        count_launches(1);
+        B2_CUDA(cudaGetLastError());
+    }
+    return B2_OK;
 }
 
 // scaling_variant::scale_up (BFV; Encryptor: multiply_add_plain_inplace on c_0; Evaluator::add_plain / sub_plain): plain = plain_count words

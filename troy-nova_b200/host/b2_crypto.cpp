@@ -9,6 +9,17 @@ SecretKey SecretKey::from_host(const HeContextPointer &ctx, const uint64_t *word
     k.buf_.upload(words, k.buf_.size());
     return k;
 }
+SecretKey SecretKey::uninitialised(const HeContextPointer &ctx) {
+    SecretKey k; k.ctx_ = ctx;
+    k.buf_ = DeviceArray(ctx, ctx->key_modulus_size() * ctx->poly_modulus_degree());
+    return k;
+}
+SecretKey SecretKey::clone() const { SecretKey k; k.ctx_ = ctx_; k.buf_ = buf_.clone(); return k; }
+std::vector<uint64_t> SecretKey::to_host() const {
+    std::vector<uint64_t> v(buf_.size());
+    if (!v.empty()) buf_.download(v.data(), v.size());
+    return v;
+}
 PublicKey PublicKey::from_host(const HeContextPointer &ctx, const uint64_t *words) {
     PublicKey k; k.ctx_ = ctx;
     k.buf_ = DeviceArray(ctx, 2 * ctx->key_modulus_size() * ctx->poly_modulus_degree());
@@ -27,6 +38,50 @@ std::vector<uint64_t> PublicKey::to_host() const {
     std::vector<uint64_t> v(buf_.size());
     if (!v.empty()) buf_.download(v.data(), v.size());
     return v;
+}
+
+// ---- KeyGenerator (src/key_generator.cu:31-78, 136-256) ---------------------------------------------------------------------------------
+KeyGenerator::KeyGenerator(HeContextPointer context, RandomGenerator &prng) : context_(std::move(context)), prng_(&prng) {
+    sk_ = SecretKey::uninitialised(context_);
+    check(b2_generate_secret_key(context_->raw(), prng_->raw(), sk_.data(), context_->stream), "[KeyGenerator::KeyGenerator]");
+}
+KeyGenerator::KeyGenerator(HeContextPointer context, RandomGenerator &prng, const SecretKey &secret_key) : context_(std::move(context)), prng_(&prng) {
+    if (secret_key.empty()) throw std::invalid_argument("[KeyGenerator::KeyGenerator] Secret key is empty.");
+    sk_ = secret_key.clone();
+}
+void KeyGenerator::one_kswitch_key(const uint64_t *new_key, KSwitchKeys &dest, size_t index) {
+    const size_t K = context_->key_modulus_size(), n = context_->poly_modulus_degree();
+    if (K < 2) throw std::logic_error("[KeyGenerator::generate_one_kswitch_key] Keyswitching is not enabled.");
+    DeviceArray key(context_, (K - 1) * 2 * K * n);
+    check(b2_generate_kswitch_key(context_->raw(), sk_.data(), new_key, prng_->raw(), key.data(), context_->stream), "[KeyGenerator::generate_one_kswitch_key]");
+    dest.adopt_key(index, std::move(key), K - 1);
+}
+RelinKeys KeyGenerator::create_relin_keys() {
+    const size_t w = context_->key_modulus_size() * context_->poly_modulus_degree();
+    DeviceArray powers(context_, 2 * w);
+    check(b2_secret_key_powers(context_->raw(), sk_.data(), 2, powers.data(), context_->stream), "[KeyGenerator::create_relin_keys]");
+    RelinKeys rk(context_);
+    one_kswitch_key(powers.data() + w, rk, RelinKeys::get_index(2));
+    check(b2_stream_sync(context_->raw(), context_->stream), "[KeyGenerator::create_relin_keys]");      // `powers` is freed on return
+    return rk;
+}
+GaloisKeys KeyGenerator::create_galois_keys(const std::vector<size_t> &galois_elements) {
+    const size_t K = context_->key_modulus_size(), n = context_->poly_modulus_degree();
+    GaloisKeys gk(context_);
+    DeviceArray rotated(context_, K * n);
+    for (size_t e : galois_elements) {
+        if (e % 2 == 0 || e >= 2 * n) throw std::invalid_argument("[KeyGenerator::generate_galois_keys] Galois element is not valid.");
+        if (gk.has_key(e)) continue;
+        check(b2_galois(context_->raw(), sk_.data(), e, rotated.data(), 1, K, 0, 1, context_->stream), "[KeyGenerator::generate_galois_keys]");
+        one_kswitch_key(rotated.data(), gk, GaloisKeys::get_index(e));
+    }
+    check(b2_stream_sync(context_->raw(), context_->stream), "[KeyGenerator::generate_galois_keys]");
+    return gk;
+}
+GaloisKeys KeyGenerator::create_automorphism_keys() {
+    std::vector<size_t> elts;
+    for (size_t e = 2; e <= context_->poly_modulus_degree(); e <<= 1) elts.push_back(e + 1);
+    return create_galois_keys(elts);
 }
 
 // ---- Encryptor (src/encryptor.cu:12-118, 247-338) ---------------------------------------------------------------------------------

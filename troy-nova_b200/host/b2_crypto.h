@@ -33,6 +33,10 @@ class SecretKey {
 public:
     SecretKey() = default;
     static SecretKey from_host(const HeContextPointer &ctx, const uint64_t *words);
+    static SecretKey uninitialised(const HeContextPointer &ctx);
+    SecretKey clone() const;
+    uint64_t *data() { return buf_.data(); }
+    std::vector<uint64_t> to_host() const;
     const uint64_t *data() const { return buf_.data(); }
     const HeContextPointer &context() const { return ctx_; }
     bool empty() const { return buf_.size() == 0; }
@@ -52,6 +56,26 @@ public:
 private:
     HeContextPointer ctx_;
     DeviceArray buf_;
+};
+
+// src/key_generator.h: every key is drawn from the generator passed in, in call order, exactly as the reference's KeyGenerator draws from the context's
+// generator — same seed and call order => the reference's keys word for word (tests/test_keygen_gpu.py)
+class KeyGenerator {
+public:
+    // samples a fresh secret key (NTT(ternary)), or adopts an existing one
+    KeyGenerator(HeContextPointer context, RandomGenerator &prng);
+    KeyGenerator(HeContextPointer context, RandomGenerator &prng, const SecretKey &secret_key);
+    const SecretKey &secret_key() const { return sk_; }
+    PublicKey create_public_key() { return PublicKey::create(context_, sk_, *prng_); }
+    RelinKeys create_relin_keys();                                               // the key for s^2 at RelinKeys::get_index(2)
+    GaloisKeys create_galois_keys(const std::vector<size_t> &galois_elements);
+    GaloisKeys create_automorphism_keys();                                       // 2^k + 1, k = 1 .. log N: what pack_lwe_ciphertexts needs
+
+private:
+    void one_kswitch_key(const uint64_t *new_key, KSwitchKeys &dest, size_t index);
+    HeContextPointer context_;
+    RandomGenerator *prng_;
+    SecretKey sk_;
 };
 
 // src/encryptor.h.  `prng` is the context's generator of the reference (HeContext::random_generator()): it supplies the noise and, when no

@@ -141,6 +141,21 @@ void KSwitchKeys::set_key(size_t index, const uint64_t *words, size_t digits) {
     digits_[index] = digits;
 }
 
+void KSwitchKeys::adopt_key(size_t index, DeviceArray &&storage, size_t digits) {
+    if (!ctx_) throw std::invalid_argument("[KSwitchKeys::adopt_key] no context.");
+    if (index >= keys_.size()) { keys_.resize(index + 1, nullptr); digits_.resize(index + 1, 0); storage_.resize(index + 1); }
+    if (keys_[index]) { b2_kswitch_key_destroy(keys_[index]); keys_[index] = nullptr; }
+    storage_[index] = std::move(storage);
+    check(b2_kswitch_key_create_contiguous(ctx_->raw(), storage_[index].data(), digits, &keys_[index]), "[KSwitchKeys::adopt_key]");
+    digits_[index] = digits;
+}
+std::vector<uint64_t> KSwitchKeys::key_to_host(size_t index) const {
+    if (!has_index(index)) throw std::invalid_argument("[KSwitchKeys::key_to_host] key not present.");
+    std::vector<uint64_t> v(storage_[index].size());
+    storage_[index].download(v.data(), v.size());
+    return v;
+}
+
 std::vector<int> naf(int value) {
     std::vector<int> res;
     const bool negative = value < 0;

@@ -196,6 +196,9 @@ public:
     KSwitchKeys &operator=(const KSwitchKeys &) = delete;
     // words: [digits][2][K][N] (host memory), uploaded and kept resident
     void set_key(size_t index, const uint64_t *words, size_t digits);
+    // the same from a device array that already holds [digits][2][K][N] (KeyGenerator)
+    void adopt_key(size_t index, DeviceArray &&storage, size_t digits);
+    std::vector<uint64_t> key_to_host(size_t index) const;
     bool has_index(size_t index) const { return index < keys_.size() && keys_[index] != nullptr; }
     const b2_kswitch_key *key(size_t index) const { return has_index(index) ? keys_[index] : nullptr; }
     size_t digits(size_t index) const { return index < digits_.size() ? digits_[index] : 0; }

@@ -145,6 +145,21 @@ int main(int argc, char **argv) {
                 cprobe([&] { ev.pack_rlwe_ciphertexts_new({&a, &b}, none, 0, n, n / 2, false); });          // key missing
                 cprobe([&] { ev.pack_rlwe_ciphertexts_new({&a, &b, &r}, gk, 0, n, n / 2, false); });        // more ciphertexts than slots
             }
+            {                                                                           // 38-41: KeyGenerator from a seed: secret, public, relinearisation, Galois(3) keys
+                RandomGenerator kprng(0x5eed);
+                KeyGenerator kg(ctx, kprng);
+                { const std::vector<uint64_t> v = kg.secret_key().to_host(); out.insert(out.end(), v.begin(), v.end()); }
+                { const std::vector<uint64_t> v = kg.create_public_key().to_host(); out.insert(out.end(), v.begin(), v.end()); }
+                RelinKeys krk = kg.create_relin_keys();
+                { const std::vector<uint64_t> v = krk.key_to_host(RelinKeys::get_index(2)); out.insert(out.end(), v.begin(), v.end()); }
+                GaloisKeys kgk = kg.create_galois_keys({3, 3});
+                { const std::vector<uint64_t> v = kgk.key_to_host(GaloisKeys::get_index(3)); out.insert(out.end(), v.begin(), v.end()); }
+                // and they work: a fresh encryption under the generated public key decrypts to the message under the generated secret key
+                Encryptor kenc(ctx, 99);
+                kenc.set_public_key(kg.create_public_key());
+                Decryptor kdec(ctx, kg.secret_key());
+                emit_plain(kdec.decrypt_new(kenc.encrypt_asymmetric_new(msg)));
+            }
             cprobe([&] { Plaintext d; dec.decrypt(z, d); });                             // contains a seed
             cprobe([&] { Ciphertext t2 = c1.clone(); t2.is_ntt_form() = !t2.is_ntt_form(); Plaintext d; dec.decrypt(t2, d); });   // wrong form for the scheme
         }
