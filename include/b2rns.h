@@ -245,6 +245,8 @@ b2_status b2_generate_kswitch_key(b2_ctx *ctx, const uint64_t *sk, const uint64_
 b2_status b2_bfv_scale_up(b2_ctx *ctx, const uint64_t *plain, size_t plain_count, size_t nl, const uint64_t *from, int subtract, uint64_t *dest, void *stream);
 /* scaling_variant::centralize (src/utils/scaling_variant.cu:326-357): plain modulo t -> centred residues modulo q_j, out [nl][N] */
 b2_status b2_centralize(b2_ctx *ctx, const uint64_t *plain, size_t plain_count, size_t nl, uint64_t *out, void *stream);
+/* the same on (scalar * m mod t): BGV Evaluator::add_plain / sub_plain multiply by the ciphertext's correction factor first (src/evaluator_translate_plain.cu:79-82) */
+b2_status b2_centralize_scaled(b2_ctx *ctx, const uint64_t *plain, size_t plain_count, size_t nl, uint64_t scalar, uint64_t *out, void *stream);
 /* Encryptor::encrypt_internal (src/encryptor.cu:247-338): BFV / BGV plain = plain_count words modulo t (nl = first level);
  * CKKS plain = [nl][N] NTT form.  key = pk (asymmetric != 0) or sk. */
 b2_status b2_encrypt(b2_ctx *ctx, const uint64_t *plain, size_t plain_count, const uint64_t *key, int asymmetric, size_t nl, b2_prng *u_prng, b2_prng *e_prng,

@@ -404,6 +404,24 @@ class Oracle:
         o = np.zeros(nl * self.n, dtype=np.uint64)
         self.L.ro_centralize(self.h, _p(plain), plain.size, nl, _p(o)); return o
 
+    def plain_op(self, op, ct, nl, plain, correction_factor=1):
+        """Evaluator::multiply_plain (op 0) / add_plain (1) / sub_plain (2) with a plaintext modulo t on a ciphertext in the scheme's default form
+        (src/evaluator_multiply_plain.cu:13-68, src/evaluator_translate_plain.cu:95-170)"""
+        n, w = self.n, nl * self.n
+        ct = np.ascontiguousarray(ct, dtype=np.uint64)
+        plain = np.ascontiguousarray(plain, dtype=np.uint64)
+        if op == 0:
+            m = self.ntt_fwd(self.centralize(plain, nl), 1, nl)
+            if self.scheme == BFV:
+                return self.ntt_inv(self.dyadic_broadcast(self.ntt_fwd(ct, 2, nl), m, 2, nl), 2, nl)
+            return self.dyadic_broadcast(ct, m, 2, nl)
+        f = self.sub if op == 2 else self.add
+        if self.scheme == BFV:
+            return np.concatenate([self.bfv_scale_up(plain, nl, ct[:w], op == 2), ct[w:]])
+        scaled = plain if correction_factor == 1 else np.array([(int(v) * correction_factor) % self.t for v in plain], dtype=np.uint64)
+        m = self.ntt_fwd(self.centralize(scaled, nl), 1, nl)
+        return np.concatenate([f(ct[:w], m, 1, nl), ct[w:]])
+
     def encrypt(self, plain, key, asymmetric, nl, u_st, e_st=None):
         plain = np.ascontiguousarray(plain, dtype=np.uint64)
         ct = np.zeros(2 * nl * self.n, dtype=np.uint64)
@@ -479,6 +497,7 @@ def reflib():
         R.rs_pack_rlwes.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, u64p]
         R.rs_extract_lwe.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_size_t, C.c_int, u64p, u64p]
         R.rs_pack_lwes.argtypes = [C.c_void_p, u64p, u64p, C.c_size_t, C.c_size_t, C.c_int, u64p]
+        R.rs_plain_op.argtypes = [C.c_void_p, C.c_int, u64p, C.c_size_t, u64p, C.c_size_t, C.c_uint64, u64p]
         R.rs_time_op.restype = C.c_double
         R.rs_time_op.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int]
         _ref = R
@@ -599,6 +618,12 @@ class Reference:
         c0 = np.ascontiguousarray(np.concatenate([l[0] for l in lwes]), dtype=np.uint64); c1 = np.ascontiguousarray(np.concatenate([l[1] for l in lwes]), dtype=np.uint64)
         o = np.zeros(2 * nl * self.n, dtype=np.uint64)
         self._chk(self.R.rs_pack_lwes(self.h, _p(c0), _p(c1), len(lwes), nl, int(apply_field_trace), _p(o))); return o
+
+    def plain_op(self, op, ct, nl, plain, correction_factor=1):
+        """op 0 multiply_plain, 1 add_plain, 2 sub_plain with a plaintext modulo t; ct [2][nl][N] in the scheme's default form"""
+        plain = np.ascontiguousarray(plain, dtype=np.uint64)
+        o = np.zeros(2 * nl * self.n, dtype=np.uint64)
+        self._chk(self.R.rs_plain_op(self.h, op, _p(np.ascontiguousarray(ct, dtype=np.uint64)), nl, _p(plain), plain.size, correction_factor, _p(o))); return o
 
     def decrypt_raw(self, a, pc, nl, correction_factor=1):
         o = np.zeros((nl if self.scheme == 2 else 1) * self.n, dtype=np.uint64)

@@ -380,6 +380,22 @@ int rs_pack_lwes(void *hh, const uint64_t *c0s, const uint64_t *c1s, size_t coun
     })
 }
 
+/* ---- Evaluator::multiply_plain / add_plain / sub_plain with a plaintext modulo t (no parms_id), on a raw ciphertext [2][nl][N] in the scheme's
+ * default form (src/evaluator_multiply_plain.cu:13-68,309-328, src/evaluator_translate_plain.cu:95-170); op 0 multiply, 1 add, 2 sub ---- */
+int rs_plain_op(void *hh, int op, const uint64_t *ct, size_t nl, const uint64_t *plain, size_t plain_count, uint64_t correction_factor, uint64_t *out) {
+    RefShim *h = (RefShim *)hh;
+    RS_TRY({
+        Ciphertext c = make_ct(h, ct, 2, nl, default_ntt_form(h));
+        c.correction_factor() = correction_factor;
+        Plaintext p; p.resize(plain_count);
+        std::memcpy(p.data().raw_pointer(), plain, plain_count * 8);
+        if (h->device) p.to_device_inplace();
+        Ciphertext r = op == 0 ? h->eval->multiply_plain_new(c, p) : op == 1 ? h->eval->add_plain_new(c, p) : h->eval->sub_plain_new(c, p);
+        if (h->device) cudaDeviceSynchronize();
+        export_ct(r, out);
+    })
+}
+
 /* ---- timing helper: seconds per op, averaged over iters, data resident where the context is ----
  * op: 0 ntt_fwd(pc*nc limbs, componentwise key tables base 0) 1 ntt_inv 2 multiply 3 relinearize
  *     4 rotate(1) 5 rescale/modswitch_to_next 6 square 7 encrypt_zero_asymmetric (level nl) 8 decrypt (2 polynomials, level nl)

@@ -83,10 +83,11 @@ def test_host_mirror_script(po, scheme, tmp_path):
     want += [("encrypt_asymmetric", c1), ("encrypt_symmetric", c2), ("encrypt_zero_symmetric (saved seed, last level)", z), ("saved seed", np.array([zseed], dtype=np.uint64)),
              ("decrypt", o.decrypt(c1, 2, L, skp)), ("decrypt of a product", o.decrypt(prod, 3, L, skp)),
              ("decrypt_batched[0]", o.decrypt(c2, 2, L, skp)), ("decrypt_batched[1]", o.decrypt(c1, 2, L, skp))]
-    if scheme == 1:
-        want += [("add_plain", np.concatenate([o.bfv_scale_up(msg, L, c1[:w]), c1[w:]])), ("sub_plain", np.concatenate([o.bfv_scale_up(msg, L, c1[:w], True), c1[w:]]))]
-    elif scheme == 2:
-        want += [("add_plain", np.concatenate([o.add(c1[:w], msg, 1, L), c1[w:]])), ("sub_plain", np.concatenate([o.sub(c1[:w], msg, 1, L), c1[w:]]))]
+    if scheme == 2:
+        want += [("add_plain", np.concatenate([o.add(c1[:w], msg, 1, L), c1[w:]])), ("sub_plain", np.concatenate([o.sub(c1[:w], msg, 1, L), c1[w:]])),
+                 ("multiply_plain (message)", o.dyadic_broadcast(c1, msg, 2, L))]
+    else:
+        want += [("add_plain", o.plain_op(1, c1, L, msg)), ("sub_plain", o.plain_op(2, c1, L, msg)), ("multiply_plain (message modulo t)", o.plain_op(0, c1, L, msg))]
     want += [("pack_rlwe_ciphertexts_new", o.pack_rlwes([a, b, r], is_ntt, L, 0, n, n // 4, {3: gkeys[3], 5: gkeys[5]}, False))]
     coeff = (lambda c: c) if not is_ntt else (lambda c: o.ntt_inv(c.copy(), 2, L))
     l0, l7, l9 = o.extract_lwe(coeff(a), 0, L), o.extract_lwe(coeff(b), 7, L), o.extract_lwe(coeff(r), 9, L)

@@ -301,6 +301,25 @@ def test_live_reference_keygen(po, scheme, bits):
     assert np.array_equal(relin, r.relin_key()) and np.array_equal(g3, r.galois_key(3)) and np.array_equal(gc, r.galois_key(2 * n - 1))
 
 
+@pytest.mark.parametrize("scheme,bits", [(1, [40, 40, 50, 55]), (3, [40, 45, 50, 55]), (1, [60, 60, 60])])
+def test_live_reference_plaintext_ops(po, scheme, bits):
+    """multiply_plain / add_plain / sub_plain with a plaintext modulo t (centralize, BFV scale-up, the BGV correction factor):
+    oracle compositions == the unmodified reference (src/evaluator_multiply_plain.cu:13-68, src/evaluator_translate_plain.cu:95-170)"""
+    if not po.ref_available():
+        pytest.skip("oracle/_ref not built")
+    n = 512
+    r = po.Reference(scheme, n, bits, t_bits=20)
+    o = po.Oracle(9, r.moduli, r.t, scheme)
+    rng = np.random.default_rng(scheme)
+    for nl in (len(bits) - 1, 1):
+        ct = o.random_poly(rng, 2, nl)
+        for cnt in (n, n // 2 + 1):
+            plain = rng.integers(0, r.t, size=cnt, dtype=np.uint64)
+            for op in (0, 1, 2):
+                for cf in ((1, 7) if scheme == po.BGV and op else (1,)):
+                    assert np.array_equal(r.plain_op(op, ct, nl, plain, cf), o.plain_op(op, ct, nl, plain, cf)), (nl, cnt, op, cf)
+
+
 @pytest.mark.parametrize("scheme,bits", [(1, [40, 40, 50]), (2, [40, 40, 50]), (3, [40, 45, 55])])
 def test_live_reference_packing_and_lwe(po, scheme, bits):
     """oracle pack_rlwes / extract_lwe / pack_lwes == the unmodified reference's Evaluator::pack_rlwe_ciphertexts_new, extract_lwe_new and

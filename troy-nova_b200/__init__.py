@@ -97,6 +97,7 @@ _SIGS.update({
     "b2_encrypt_zero_symmetric": (C.c_int, [vp, vp, C.c_size_t, C.c_int, C.c_int, vp, vp, vp, u64p, vp]),
     "b2_bfv_scale_up": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, vp, C.c_int, vp, vp]),
     "b2_centralize": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, vp, vp]),
+    "b2_centralize_scaled": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, C.c_uint64, vp, vp]),
     "b2_encrypt": (C.c_int, [vp, vp, C.c_size_t, vp, C.c_int, C.c_size_t, vp, vp, vp, vp]),
     "b2_pack_layer": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint64, vp, vp]),
     "b2_pack_rlwes": (C.c_int, [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.c_size_t, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, u64p, C.POINTER(vp), C.c_size_t,
@@ -407,8 +408,12 @@ class Context:
     def bfv_scale_up(self, plain, plain_count, nl, dest, frm=None, subtract=False, stream=None):
         _chk(self.L.b2_bfv_scale_up(self.h, _dptr(plain), plain_count, nl, None if frm is None else _dptr(frm), int(subtract), _dptr(dest), self._stream(stream))); return dest
 
-    def centralize(self, plain, plain_count, nl, out, stream=None):
-        _chk(self.L.b2_centralize(self.h, _dptr(plain), plain_count, nl, _dptr(out), self._stream(stream))); return out
+    def centralize(self, plain, plain_count, nl, out, scalar=1, stream=None):
+        if scalar == 1:
+            _chk(self.L.b2_centralize(self.h, _dptr(plain), plain_count, nl, _dptr(out), self._stream(stream)))
+        else:
+            _chk(self.L.b2_centralize_scaled(self.h, _dptr(plain), plain_count, nl, scalar, _dptr(out), self._stream(stream)))
+        return out
 
     def encrypt(self, plain, plain_count, key, asymmetric, nl, ct, u_prng, e_prng=None, stream=None):
         e_prng = u_prng if e_prng is None else e_prng

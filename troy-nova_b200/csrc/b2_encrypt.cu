@@ -239,14 +239,17 @@ __global__ void __launch_bounds__(256) scale_up_kernel(const u64 *__restrict__ p
     dest[idx] = subtract ? submod(base, s, Q.p) : addmod(base, s, Q.p);
 }
 // centralize: out[j][x] = m_x (m_x < (t+1)/2) or m_x + q - t, modulo q_j; zero beyond plain_count     (scaling_variant.cu:326-357)
+// scalar != 1: the message is first multiplied by it modulo t (BGV add_plain: the ciphertext's correction factor, evaluator_translate_plain.cu:79-82)
 __global__ void __launch_bounds__(256) centralize_kernel(const u64 *__restrict__ plain, u32 plain_count, u64 *__restrict__ out, const ModInfo *__restrict__ mods,
-                                                         u64 t, u32 nl, u32 n) {
+                                                         u64 t, u32 nl, u32 n, u64 scalar = 1, u64 t_r0 = 0, u64 t_r1 = 0) {
     const u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (u64)nl * n) return;
     const u32 j = (u32)(idx / n), x = (u32)(idx % n);
     if (x >= plain_count) { out[idx] = 0; return; }
     const ModInfo &Q = mods[j];
-    const u64 m = plain[x], mq = barrett64(m, Q.p, Q.ratio);
+    u64 m = plain[x];
+    if (scalar != 1) m = mulmod(m, scalar, t, t_r0, t_r1);
+    const u64 mq = barrett64(m, Q.p, Q.ratio);
     out[idx] = m >= ((t + 1) >> 1) ? submod(mq, barrett64(t, Q.p, Q.ratio), Q.p) : mq;
 }
 
@@ -490,6 +493,21 @@ b2_status b2_centralize(b2_ctx *ctx, const uint64_t *plain, size_t plain_count, 
     cudaStream_t stream = (cudaStream_t)stream_;
     const u64 total = (u64)nl * ctx->n;
     centralize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>((const u64 *)plain, (u32)plain_count, (u64 *)out, ctx->d_mods, ctx->t, (u32)nl, (u32)ctx->n);
+    count_launches(1);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
+// centralize of (scalar * m mod t): BGV Evaluator::add_plain / sub_plain multiply the message by the ciphertext's correction factor first
+// (src/evaluator_translate_plain.cu:79-82, utils::multiply_scalar modulo t)
+b2_status b2_centralize_scaled(b2_ctx *ctx, const uint64_t *plain, size_t plain_count, size_t nl, uint64_t scalar, uint64_t *out, void *stream_) {
+    B2_REQUIRE(ctx && plain && out, "null argument");
+    B2_REQUIRE(ctx->t > 1 && nl >= 1 && nl <= ctx->K && plain_count <= ctx->n, "centralize needs a plain modulus, 1 <= nl <= K and at most N coefficients");
+    B2_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const u64 total = (u64)nl * ctx->n;
+    centralize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>((const u64 *)plain, (u32)plain_count, (u64 *)out, ctx->d_mods, ctx->t, (u32)nl, (u32)ctx->n,
+                                                                          scalar % ctx->t, ctx->t_r0, ctx->t_r1);
     count_launches(1);
     B2_CUDA(cudaGetLastError());
     return B2_OK;

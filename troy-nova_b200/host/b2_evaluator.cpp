@@ -625,12 +625,40 @@ Ciphertext Evaluator::pack_lwe_ciphertexts_new(const std::vector<const LWECipher
     return out;
 }
 
+// bfv_centralize / transform_plain_to_ntt (src/evaluator_transform_ntt.cu:35-129)
+Plaintext Evaluator::centralize(const Plaintext &p, size_t nl, uint64_t scalar) const {
+    if (p.empty() || !p.is_mod_t()) throw std::invalid_argument("[Evaluator::bfv_centralize] Plaintext must be modulo t (no parms_id).");
+    if (context_->plain_modulus() < 2) throw std::invalid_argument("[Evaluator::bfv_centralize] The context has no plain modulus.");
+    Plaintext r = Plaintext::rns(context_, nl, false);
+    check(b2_centralize_scaled(context_->raw(), p.data(), p.coeff_count(), nl, scalar, r.data(), context_->stream), "[Evaluator::bfv_centralize]");
+    return r;
+}
+Plaintext Evaluator::transform_plain_to_ntt(const Plaintext &p, size_t nl) const {
+    Plaintext c = centralize(p, nl);
+    Plaintext r = Plaintext::rns(context_, nl, true);
+    check(b2_ntt_forward(context_->raw(), c.data(), r.data(), 1, 1, nl, B2_TABLES_COMPONENTWISE, 0, 0, context_->stream), "[Evaluator::transform_plain_to_ntt]");
+    check(b2_stream_sync(context_->raw(), context_->stream), "[Evaluator::transform_plain_to_ntt]");      // the temporary is freed on return
+    return r;
+}
+
 // Evaluator::translate_plain (src/evaluator_translate_plain.cu:95-170)
 void Evaluator::translate_plain(const Ciphertext &e, const Plaintext &p, Ciphertext &d, bool subtract) const {
     check_ct("[Evaluator::translate_plain]", e);
     if (e.contains_seed()) throw std::invalid_argument("[Evaluator::translate_plain] Ciphertext contains a seed; expand it first.");
     const SchemeType scheme = context_->scheme();
-    if (scheme == SchemeType::BGV) throw std::logic_error("[Evaluator::translate_plain] BGV add_plain is not mirrored (needs the scalar product modulo t).");
+    if (scheme == SchemeType::BGV) {          // plain * correction_factor mod t -> centralize -> NTT -> c_0 +/- it     (evaluator_translate_plain.cu:79-88)
+        if (!e.is_ntt_form()) throw std::invalid_argument("[Evaluator::translate_plain] Ciphertext is not in NTT form.");
+        if (p.is_ntt_form() || !p.is_mod_t()) throw std::invalid_argument("[Evaluator::translate_plain] Plaintext is in NTT form.");
+        const size_t L = e.coeff_modulus_size();
+        Plaintext lifted = centralize(p, L, e.correction_factor());
+        b2_ctx *c = context_->raw();
+        check(b2_ntt_forward(c, lifted.data(), lifted.data(), 1, 1, L, B2_TABLES_COMPONENTWISE, 0, 0, context_->stream), "[Evaluator::translate_plain]");
+        Ciphertext r = e.clone();
+        check((subtract ? b2_sub : b2_add)(c, r.poly(0), lifted.data(), r.poly(0), 1, L, 0, context_->stream), "[Evaluator::translate_plain]");
+        check(b2_stream_sync(c, context_->stream), "[Evaluator::translate_plain]");
+        d = std::move(r);
+        return;
+    }
     if (e.is_ntt_form() != p.is_ntt_form()) throw std::invalid_argument("[Evaluator::translate_plain] Plaintext and ciphertext are not in the same NTT form.");
     if (scheme == SchemeType::BFV && p.is_mod_t() && e.is_ntt_form()) throw std::invalid_argument("[Evaluator::translate_plain] When plain is mod t, encrypted must not be in NTT form.");
     if (scheme == SchemeType::CKKS) {
@@ -652,6 +680,12 @@ void Evaluator::translate_plain(const Ciphertext &e, const Plaintext &p, Ciphert
 // NTT(ct), NTT(pt), dyadic product, INTT (multiply_plain_normal, :13-68, after its centralize step).
 void Evaluator::multiply_plain(const Ciphertext &e, const Plaintext &p, Ciphertext &d) const {
     check_ct("[Evaluator::multiply_plain]", e);
+    if (p.is_mod_t()) {      // a message modulo t: centralize it to the ciphertext's level first (multiply_plain_normal, evaluator_multiply_plain.cu:13-68)
+        Plaintext lifted = centralize(p, e.coeff_modulus_size());
+        multiply_plain(e, lifted, d);
+        check(b2_stream_sync(context_->raw(), context_->stream), "[Evaluator::multiply_plain]");
+        return;
+    }
     if (p.coeff_modulus_size() != e.coeff_modulus_size()) throw std::invalid_argument("[Evaluator::multiply_plain_ntt] Plaintext parms_id mismatch.");
     const size_t pc = e.polynomial_count(), L = e.coeff_modulus_size();
     b2_ctx *c = context_->raw();

@@ -322,6 +322,10 @@ public:
     void add_plain_inplace(Ciphertext &encrypted, const Plaintext &plain) const { Ciphertext d; translate_plain(encrypted, plain, d, false); encrypted = std::move(d); }
     void sub_plain_inplace(Ciphertext &encrypted, const Plaintext &plain) const { Ciphertext d; translate_plain(encrypted, plain, d, true); encrypted = std::move(d); }
 
+    // ---- plaintext lifts (src/evaluator_transform_ntt.cu:35-129): a mod-t plaintext -> the RNS plaintext of a level (centralize), in NTT form
+    Plaintext transform_plain_to_ntt(const Plaintext &plain, size_t coeff_modulus_size) const;
+    Plaintext centralize(const Plaintext &plain, size_t coeff_modulus_size, uint64_t scalar = 1) const;
+
     // ---- ct x pt (src/evaluator_multiply_plain.cu:13-383): multiply_plain in all four form combinations, NTT-form batched / accumulate forms
     void multiply_plain(const Ciphertext &encrypted, const Plaintext &plain, Ciphertext &destination) const;
     void multiply_plain_inplace(Ciphertext &encrypted, const Plaintext &plain) const { Ciphertext d; multiply_plain(encrypted, plain, d); encrypted = std::move(d); }

@@ -129,10 +129,10 @@ int main(int argc, char **argv) {
                 dec.decrypt_batched({&c2, &c1}, {&p0, &p1});
                 emit_plain(p0); emit_plain(p1);
             }
-            if (scheme != SchemeType::BGV) {                                            // 32, 33: add_plain / sub_plain
-                Ciphertext ap, sp;
-                ev.add_plain(c1, msg, ap); ev.sub_plain(c1, msg, sp);
-                emit(ap); emit(sp);
+            {                                                                           // 32-34: add_plain / sub_plain / multiply_plain with the message
+                Ciphertext ap, sp, mp2;                                                 //        (BFV / BGV: modulo t -> scale-up resp. centralize + NTT; CKKS: RNS)
+                ev.add_plain(c1, msg, ap); ev.sub_plain(c1, msg, sp); ev.multiply_plain(c1, msg, mp2);
+                emit(ap); emit(sp); emit(mp2);
             }
             {                                                                           // 34: RLWE packing of three ciphertexts (two layers, no trace): keys 3 and 5
                 Ciphertext packed = ev.pack_rlwe_ciphertexts_new({&a, &b, &r}, gk, 0, n, n / 4, false);
