@@ -52,13 +52,15 @@ struct ModUpLoad {
     u32 decomp, K, n;
     u32 g0;          // output modulus of group 0 (limb-sharded calls transform a sub-range of the output moduli)
     u32 f64_path;    // 1 iff FP64-pipe moduli really run the FP64 back end in this launch (N >= 4096); the tiny-N kernel is integer-only
+    u32 special_first = 0;   // 1: group 0 is the special prime (output modulus `decomp`) and group g > 0 is output modulus g - 1: the slow
+                             // integer-pipe limbs of every digit are claimed first, so the queue does not end on one
     __device__ __forceinline__ const u64 *src(int, int c, u64) const {
         const u32 b = (u32)c / decomp, j = (u32)c - b * decomp;
         return tc.p[b] + (u64)j * n;
     }
     struct Prep { u64 m, ratio; bool reduce; };
     __device__ __forceinline__ Prep prep(int g, int c) const {
-        const u32 i = (u32)g + g0;
+        const u32 i = special_first ? ((u32)g == 0 ? decomp : (u32)g - 1) : (u32)g + g0;
         const u32 ki = i == decomp ? K - 1 : i;
         const u32 j = (u32)c % decomp;
         const ModInfo &Mi = mods[ki];
@@ -326,11 +328,16 @@ static b2_status keyswitch_chunk(b2_ctx *ctx, const uint64_t *const *targets, ui
     for (size_t i0 = 0; i0 < R && !fused; i0 += blk) {
         const size_t cnt = std::min(blk, R - i0);
         std::vector<LimbGroup> groups;
+        // one block covering every output modulus: the special prime's group goes first (its place in `temp` stays row `decomp`)
+        static const bool sp_first_env = [] { const char *e = getenv("B2_KS_SPECIAL_FIRST"); return !(e && e[0] == '0'); }();
+        const bool sp_first = sp_first_env && i0 == 0 && cnt == R;
+        if (sp_first) groups.push_back(LimbGroup{(u32)(K - 1), (u32)(nb * decomp), (u64)(decomp * nb * decomp * n), (u64)n});
         for (size_t il = 0; il < cnt; il++) {
             const size_t i = i0 + il;
+            if (sp_first && i == decomp) continue;
             groups.push_back(LimbGroup{(u32)(i == decomp ? K - 1 : i), (u32)(nb * decomp), (u64)(il * nb * decomp * n), (u64)n});
         }
-        ModUpLoad ld{coef, ctx->d_mods, (u32)decomp, (u32)K, (u32)n, (u32)i0, ctx->logn > 11 ? 1u : 0u};
+        ModUpLoad ld{coef, ctx->d_mods, (u32)decomp, (u32)K, (u32)n, (u32)i0, ctx->logn > 11 ? 1u : 0u, sp_first ? 1u : 0u};
         st = run_ntt_dir<true>(ctx, sc, groups, temp, ld, PlainStore{temp}, stream);
         if (st != B2_OK) return st;
         if (i0 == 0) mark();

@@ -35,6 +35,10 @@ b2_status ntt_launch(b2_ctx *ctx, bool forward, const uint64_t *in, uint64_t *ou
             groups.push_back(LimbGroup{table, (u32)(batch * pcount), (u64)(j * n), (u64)(ncomp * n)});
         }
     }
+    // the work queue is in group order within every batch item: the slow integer-pipe moduli go first so that the queue does not end on one
+    // (the groups carry their own offsets, so their order is free)
+    static const bool int_first = [] { const char *e = getenv("B2_NTT_INT_FIRST"); return !(e && e[0] == '0'); }();
+    if (int_first) std::stable_partition(groups.begin(), groups.end(), [&](const LimbGroup &g) { return !ctx->h_mods[g.table].use_f64; });
     Scratch sc(ctx, stream);
     // throughput regime at N = 2^16: the FP64-pipe moduli take the TMA kernel (b2_ntt5.cuh); few-limb calls stay on the
     // cluster kernel (latency regime)
