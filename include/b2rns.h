@@ -232,6 +232,11 @@ b2_status b2_encrypt_zero_asymmetric(b2_ctx *ctx, const uint64_t *pk, size_t nl,
  * receives the seed of a's generator, which the reference stores in the ciphertext when save_seed != 0. */
 b2_status b2_encrypt_zero_symmetric(b2_ctx *ctx, const uint64_t *sk, size_t nl, int is_ntt_form, int save_seed, b2_prng *c1_prng, b2_prng *e_prng, uint64_t *ct,
                                     uint64_t *seed_out, void *stream);
+/* BatchEncoder (src/batch_encoder.cu:14-60,169-227,407-460): SIMD slots <-> the plaintext polynomial modulo t.  The context's plain modulus must be a
+ * batching prime (= 1 mod 2N); the tables of the negacyclic transform modulo t and the slot map are built by the first call.
+ * encode: values DEVICE [count <= N] -> plain DEVICE [N] (coefficient form, modulo t); decode: plain [plain_count <= N] -> values [N]. */
+b2_status b2_batch_encode(b2_ctx *ctx, const uint64_t *values, size_t count, uint64_t *plain, void *stream);
+b2_status b2_batch_decode(b2_ctx *ctx, const uint64_t *plain, size_t plain_count, uint64_t *values, void *stream);
 /* KeyGenerator (src/key_generator.cu): with the generator in the state of the reference's context generator the keys equal the reference's.
  *   secret key (:31-58)                sk [K][N] = NTT(ternary sample)
  *   public key (:60-78)                = b2_encrypt_zero_symmetric(sk, K, ntt = 1, save_seed = 0) at the key level

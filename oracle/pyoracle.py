@@ -339,6 +339,33 @@ class Oracle:
                 deg >>= 1
         return ret
 
+    # ---- BatchEncoder (src/batch_encoder.cu:14-60,169-227,407-460): slot i <-> coefficient index_map[i] of the NTT-form polynomial modulo t
+    def _batching(self):
+        if not hasattr(self, "_bt"):
+            n, logn = self.n, self.log_n
+            row, m, pos = n >> 1, n << 1, 1
+            mp = np.zeros(n, dtype=np.int64)
+            rev = lambda v: int(format(v, "0%db" % logn)[::-1], 2)
+            for i in range(row):
+                mp[i] = rev((pos - 1) >> 1); mp[i + row] = rev((m - pos - 1) >> 1)
+                pos = (pos * 3) & (m - 1)
+            self._bt = (mp, Oracle(logn, np.array([self.t], dtype=np.uint64), 0, BFV))      # negacyclic NTT tables modulo t (minimal primitive root, as plain_ntt_tables)
+        return self._bt
+
+    def batch_encode(self, values):
+        mp, ot = self._batching()
+        a = np.zeros(self.n, dtype=np.uint64)
+        v = np.ascontiguousarray(values, dtype=np.uint64)
+        a[mp[:v.size]] = v
+        return ot.ntt_inv(a, 1, 1)
+
+    def batch_decode(self, plain):
+        mp, ot = self._batching()
+        a = np.zeros(self.n, dtype=np.uint64)
+        p = np.ascontiguousarray(plain, dtype=np.uint64)
+        a[:p.size] = p
+        return ot.ntt_fwd(a, 1, 1)[mp]
+
     # ---- LWE (src/evaluator_lwes.cu:51-94, src/lwe_ciphertext.cu:12-140, pack_lwe_ciphertexts_new :201-229)
     def extract_lwe(self, ct, term, nl):
         """coefficient-form ct [2][nl][N] -> (c0 [nl], c1 [nl][N])"""
@@ -498,6 +525,8 @@ def reflib():
         R.rs_extract_lwe.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_size_t, C.c_int, u64p, u64p]
         R.rs_pack_lwes.argtypes = [C.c_void_p, u64p, u64p, C.c_size_t, C.c_size_t, C.c_int, u64p]
         R.rs_plain_op.argtypes = [C.c_void_p, C.c_int, u64p, C.c_size_t, u64p, C.c_size_t, C.c_uint64, u64p]
+        R.rs_batch_encode.argtypes = [C.c_void_p, u64p, C.c_size_t, u64p]
+        R.rs_batch_decode.argtypes = [C.c_void_p, u64p, C.c_size_t, u64p]
         R.rs_time_op.restype = C.c_double
         R.rs_time_op.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int]
         _ref = R
@@ -624,6 +653,14 @@ class Reference:
         plain = np.ascontiguousarray(plain, dtype=np.uint64)
         o = np.zeros(2 * nl * self.n, dtype=np.uint64)
         self._chk(self.R.rs_plain_op(self.h, op, _p(np.ascontiguousarray(ct, dtype=np.uint64)), nl, _p(plain), plain.size, correction_factor, _p(o))); return o
+
+    def batch_encode(self, values):
+        values = np.ascontiguousarray(values, dtype=np.uint64); o = np.zeros(self.n, dtype=np.uint64)
+        self._chk(self.R.rs_batch_encode(self.h, _p(values), values.size, _p(o))); return o
+
+    def batch_decode(self, plain):
+        plain = np.ascontiguousarray(plain, dtype=np.uint64); o = np.zeros(self.n, dtype=np.uint64)
+        self._chk(self.R.rs_batch_decode(self.h, _p(plain), plain.size, _p(o))); return o
 
     def decrypt_raw(self, a, pc, nl, correction_factor=1):
         o = np.zeros((nl if self.scheme == 2 else 1) * self.n, dtype=np.uint64)

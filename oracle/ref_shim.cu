@@ -396,6 +396,29 @@ int rs_plain_op(void *hh, int op, const uint64_t *ct, size_t nl, const uint64_t 
     })
 }
 
+/* ---- BatchEncoder::encode / decode (src/batch_encoder.cu:169-227,407-460), host contexts only (the reference builds the encoder from a host context) ---- */
+int rs_batch_encode(void *hh, const uint64_t *values, size_t count, uint64_t *out) {
+    RefShim *h = (RefShim *)hh;
+    RS_TRY({
+        if (h->device) throw std::invalid_argument("batch encoder shim: host context only");
+        BatchEncoder be(h->ctx);
+        std::vector<uint64_t> v(values, values + count);
+        Plaintext p = be.encode_new(v);
+        std::memcpy(out, p.data().raw_pointer(), h->n * 8);
+    })
+}
+int rs_batch_decode(void *hh, const uint64_t *plain, size_t count, uint64_t *out) {
+    RefShim *h = (RefShim *)hh;
+    RS_TRY({
+        if (h->device) throw std::invalid_argument("batch encoder shim: host context only");
+        BatchEncoder be(h->ctx);
+        Plaintext p; p.resize(count);
+        std::memcpy(p.data().raw_pointer(), plain, count * 8);
+        std::vector<uint64_t> v = be.decode_new(p);
+        std::memcpy(out, v.data(), h->n * 8);
+    })
+}
+
 /* ---- timing helper: seconds per op, averaged over iters, data resident where the context is ----
  * op: 0 ntt_fwd(pc*nc limbs, componentwise key tables base 0) 1 ntt_inv 2 multiply 3 relinearize
  *     4 rotate(1) 5 rescale/modswitch_to_next 6 square 7 encrypt_zero_asymmetric (level nl) 8 decrypt (2 polynomials, level nl)

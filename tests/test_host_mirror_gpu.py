@@ -102,6 +102,9 @@ def test_host_mirror_script(po, scheme, tmp_path):
     kct = o.encrypt(msg, kpk2, True, L, o.prng_state(99))
     want += [("KeyGenerator secret key", ksk), ("public key", kpk), ("relinearisation key", krk), ("Galois key", kgk),
              ("decrypt(encrypt(m)) under generated keys", o.decrypt(kct, 2, L, o.secret_key_powers(ksk, 1)))]
+    if scheme != 2:
+        slots = msg[:n // 2 + 1]
+        want += [("BatchEncoder::encode", o.batch_encode(slots)), ("BatchEncoder::decode", np.concatenate([slots, np.zeros(n - slots.size, dtype=np.uint64)]))]
     pos = 0
     for name, exp in want:
         got = out[pos:pos + exp.size]; pos += exp.size

@@ -320,6 +320,23 @@ def test_live_reference_plaintext_ops(po, scheme, bits):
                     assert np.array_equal(r.plain_op(op, ct, nl, plain, cf), o.plain_op(op, ct, nl, plain, cf)), (nl, cnt, op, cf)
 
 
+@pytest.mark.parametrize("scheme,log_n", [(1, 10), (3, 8), (1, 13)])
+def test_live_reference_batch_encoder(po, scheme, log_n):
+    """BatchEncoder::encode / decode (src/batch_encoder.cu:14-60,169-227,407-460): oracle slot map + transform modulo t == the unmodified reference"""
+    if not po.ref_available():
+        pytest.skip("oracle/_ref not built")
+    n = 1 << log_n
+    r = po.Reference(scheme, n, [40, 40, 50], t_bits=20)
+    o = po.Oracle(log_n, r.moduli, r.t, scheme)
+    rng = np.random.default_rng(n)
+    for cnt in (n, n // 2 + 1, 1):
+        v = rng.integers(0, r.t, size=cnt, dtype=np.uint64)
+        e = r.batch_encode(v)
+        assert np.array_equal(e, o.batch_encode(v)) and np.array_equal(r.batch_decode(e), o.batch_decode(e)) and np.array_equal(o.batch_decode(e)[:cnt], v)
+    p = rng.integers(0, r.t, size=n // 3, dtype=np.uint64)
+    assert np.array_equal(r.batch_decode(p), o.batch_decode(p))
+
+
 @pytest.mark.parametrize("scheme,bits", [(1, [40, 40, 50]), (2, [40, 40, 50]), (3, [40, 45, 55])])
 def test_live_reference_packing_and_lwe(po, scheme, bits):
     """oracle pack_rlwes / extract_lwe / pack_lwes == the unmodified reference's Evaluator::pack_rlwe_ciphertexts_new, extract_lwe_new and

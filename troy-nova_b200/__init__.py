@@ -105,6 +105,8 @@ _SIGS.update({
     "b2_extract_lwe": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, vp, vp, vp]),
     "b2_assemble_lwes": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.c_size_t, C.c_size_t, vp]),
     "b2_pack_lwes": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t), C.c_size_t, C.c_size_t, u64p, C.POINTER(vp), C.c_size_t, C.c_int, C.c_int, C.POINTER(vp), vp]),
+    "b2_batch_encode": (C.c_int, [vp, vp, C.c_size_t, vp, vp]),
+    "b2_batch_decode": (C.c_int, [vp, vp, C.c_size_t, vp, vp]),
     "b2_generate_secret_key": (C.c_int, [vp, vp, vp, vp]),
     "b2_generate_kswitch_key": (C.c_int, [vp, vp, vp, vp, vp, vp]),
     "b2_secret_key_powers": (C.c_int, [vp, vp, C.c_size_t, vp, vp]),
@@ -397,6 +399,12 @@ class Context:
         seed = C.c_uint64(0)
         _chk(self.L.b2_encrypt_zero_symmetric(self.h, _dptr(sk), nl, int(is_ntt), int(save_seed), C.byref(c1_prng), C.byref(e_prng), _dptr(ct), C.byref(seed), self._stream(stream)))
         return int(seed.value)
+
+    def batch_encode(self, values, count, plain, stream=None):
+        _chk(self.L.b2_batch_encode(self.h, _dptr(values), count, _dptr(plain), self._stream(stream))); return plain
+
+    def batch_decode(self, plain, plain_count, values, stream=None):
+        _chk(self.L.b2_batch_decode(self.h, _dptr(plain), plain_count, _dptr(values), self._stream(stream))); return values
 
     def generate_secret_key(self, g, sk, stream=None):
         _chk(self.L.b2_generate_secret_key(self.h, C.byref(g), _dptr(sk), self._stream(stream))); return sk

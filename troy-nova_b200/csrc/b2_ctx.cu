@@ -167,6 +167,6 @@ extern "C" b2_status b2_ctx_create(int device, const b2_params *prm, b2_ctx **ou
 extern "C" void b2_ctx_destroy(b2_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaFree(c->d_tw); cudaFree(c->d_itw); cudaFree(c->d_twd); cudaFree(c->d_itwd); cudaFree(c->d_n5); cudaFree(c->d_mods); b2::behz_release(c); b2::decrypt_release(c); if (c->mempool) cudaMemPoolDestroy(c->mempool); cudaFree(c->d_inv); cudaFree(c->d_inv_mod_t); b2::scratch_release_all(c);
+    cudaFree(c->d_tw); cudaFree(c->d_itw); cudaFree(c->d_twd); cudaFree(c->d_itwd); cudaFree(c->d_n5); cudaFree(c->d_mods); b2::behz_release(c); b2::decrypt_release(c); if (c->mempool) cudaMemPoolDestroy(c->mempool); if (c->plain_ctx) b2_ctx_destroy(c->plain_ctx); cudaFree(c->d_slot_map); cudaFree(c->d_inv); cudaFree(c->d_inv_mod_t); b2::scratch_release_all(c);
     delete c;
 }

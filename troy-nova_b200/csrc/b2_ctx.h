@@ -43,6 +43,9 @@ struct b2_ctx {
     // stream-ordered arena of the multi-launch entry points (b2_pack_rlwes): a private pool with an unbounded release threshold, so that the
     // memory stays mapped between calls (the device's default pool hands it back to the OS at every synchronisation)
     cudaMemPool_t mempool = nullptr;
+    // BatchEncoder: a one-modulus context over the plain modulus t (its negacyclic NTT tables) and the slot -> coefficient index map, built lazily
+    b2_ctx *plain_ctx = nullptr;
+    uint32_t *d_slot_map = nullptr;
 };
 
 // Mutable state of one (stream, host thread).  `mu` is held by an entry point for the whole time it enqueues its launches,

@@ -259,6 +259,48 @@ __global__ void __launch_bounds__(256) kskey_add_kernel(u64 *__restrict__ c0_lim
     if (x < n) c0_limb[x] = addmod(c0_limb[x], shoup(new_key_limb[x], factor, p), p);
 }
 
+// BatchEncoder (src/batch_encoder.cu:14-60,106-130,345-365): slot i lives at coefficient index_map[i] of the NTT-form polynomial modulo t
+__global__ void __launch_bounds__(256) batch_scatter_kernel(const u64 *__restrict__ values, u32 count, const u32 *__restrict__ map, u64 *__restrict__ out, u32 n, u64 t, u64 t_ratio) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[map[i]] = i < count ? barrett64(values[i], t, t_ratio) : 0;
+}
+__global__ void __launch_bounds__(256) batch_gather_kernel(const u64 *__restrict__ in, const u32 *__restrict__ map, u64 *__restrict__ out, u32 n) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[map[i]];
+}
+__global__ void __launch_bounds__(256) pad_copy_kernel(const u64 *__restrict__ in, u32 count, u64 *__restrict__ out, u32 n) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = i < count ? in[i] : 0;
+}
+static b2_status ensure_batching(b2_ctx *ctx) {
+    std::lock_guard<std::mutex> guard(ctx->mu);
+    if (ctx->plain_ctx) return B2_OK;
+    const size_t n = ctx->n;
+    const uint64_t t = ctx->t;
+    B2_REQUIRE(t > 1 && host::is_prime(t) && (t - 1) % (2 * n) == 0, "The parameters does not support vector batching.");      // batch_encoder.cu:191-193
+    b2_params prm;
+    prm.log_n = ctx->logn; prm.n_moduli = 1; prm.moduli = &t; prm.plain_modulus = 0; prm.scheme = B2_SCHEME_BFV;
+    b2_ctx *pc = nullptr;
+    b2_status st = b2_ctx_create(ctx->device, &prm, &pc);
+    if (st != B2_OK) return st;
+    // matrix_reps_index_map (batch_encoder.cu:46-58): rows of N/2 slots, positions generated by 3^i mod 2N
+    std::vector<uint32_t> map(n);
+    const size_t row = n >> 1, m = n << 1;
+    size_t pos = 1;
+    for (size_t i = 0; i < row; i++) {
+        map[i] = host::bitrev((uint32_t)((pos - 1) >> 1), ctx->logn);
+        map[i + row] = host::bitrev((uint32_t)((m - pos - 1) >> 1), ctx->logn);
+        pos = (pos * 3) & (m - 1);
+    }
+    uint32_t *d = nullptr;
+    cudaError_t e = cudaMalloc(&d, n * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(d, map.data(), n * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(d); b2_ctx_destroy(pc); return cuda_fail(e, "cudaMalloc(slot map)"); }
+    ctx->d_slot_map = d;
+    ctx->plain_ctx = pc;
+    return B2_OK;
+}
+
 static uint64_t q_div_t_mod(const std::vector<uint64_t> &q, size_t nl, uint64_t t, uint64_t m) {     // floor(prod q / t) mod m
     std::vector<uint64_t> limbs{1};
     for (size_t i = 0; i < nl; i++) {
@@ -429,6 +471,51 @@ b2_status b2_encrypt_zero_symmetric(b2_ctx *ctx, const uint64_t *sk, size_t nl, 
     // ONE inverse transform over 2 nl limbs of the sample A: groups [0, nl) = sk o A -> c0 = -(. + scale e), groups [nl, 2 nl) = A -> c1
     for (size_t j = 0; j < nl; j++) g.push_back(LimbGroup{(u32)j, 1u, (u64)((nl + j) * n), 0});
     return run_ntt_dir<false>(ctx, sc.s, g, mid, SkMulLoad{A, (const u64 *)sk, ctx->d_mods, (u32)nl, (u32)n}, SymCoeffStore{c0, E, ctx->d_mods, (u32)nl, (u32)n, escale}, stream);
+}
+
+// BatchEncoder::encode_slice (src/batch_encoder.cu:169-227): values DEVICE [count <= N] -> plain DEVICE [N] modulo t (coefficient form): the values are
+// placed at their slots' positions of the NTT-form polynomial (zero beyond count) and the inverse negacyclic transform modulo t is applied; two launches.
+// (values are reduced modulo t on the way in; the reference expects them reduced already)
+b2_status b2_batch_encode(b2_ctx *ctx, const uint64_t *values, size_t count, uint64_t *plain, void *stream_) {
+    B2_REQUIRE(ctx && (values || count == 0) && plain, "null argument");
+    B2_REQUIRE(count <= ctx->n, "Values has size larger than the number of slots.");
+    B2_REQUIRE(values != plain, "out of place only");
+    b2_status st = ensure_batching(ctx);
+    if (st != B2_OK) return st;
+    B2_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t n = ctx->n;
+    batch_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((const u64 *)values, (u32)count, ctx->d_slot_map, (u64 *)plain, (u32)n, ctx->t, ctx->t_ratio);
+    count_launches(1);
+    B2_CUDA(cudaGetLastError());
+    return b2_ntt_inverse(ctx->plain_ctx, plain, plain, 1, 1, 1, B2_TABLES_COMPONENTWISE, 0, 0, stream_);
+}
+
+// BatchEncoder::decode_slice (src/batch_encoder.cu:407-460): plain DEVICE [plain_count <= N] modulo t, coefficient form -> values DEVICE [N]; three launches
+b2_status b2_batch_decode(b2_ctx *ctx, const uint64_t *plain, size_t plain_count, uint64_t *values, void *stream_) {
+    B2_REQUIRE(ctx && plain && values, "null argument");
+    B2_REQUIRE(plain != values, "out of place only");
+    b2_status st = ensure_batching(ctx);
+    if (st != B2_OK) return st;
+    B2_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t n = ctx->n;
+    u64 *tmp;
+    {
+        Scratch sc(ctx, stream);
+        st = ensure_stage(sc.s, stream, n * 8);          // the staging buffer: the transform below takes the plain context's own scratch
+        if (st != B2_OK) return st;
+        tmp = (u64 *)sc->stage;
+        pad_copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((const u64 *)plain, (u32)std::min(plain_count, n), tmp, (u32)n);
+        count_launches(1);
+        B2_CUDA(cudaGetLastError());
+    }
+    st = b2_ntt_forward(ctx->plain_ctx, (const uint64_t *)tmp, (uint64_t *)tmp, 1, 1, 1, B2_TABLES_COMPONENTWISE, 0, 0, stream_);
+    if (st != B2_OK) return st;
+    batch_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(tmp, ctx->d_slot_map, (u64 *)values, (u32)n);
+    count_launches(1);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
 }
 
 // KeyGenerator::KeyGenerator (src/key_generator.cu:31-58): sk [K][N] = NTT(ternary sample), two launches

@@ -40,6 +40,44 @@ std::vector<uint64_t> PublicKey::to_host() const {
     return v;
 }
 
+// ---- BatchEncoder (src/batch_encoder.cu) ----------------------------------------------------------------------------------------------------
+BatchEncoder::BatchEncoder(HeContextPointer context) : context_(std::move(context)) {
+    if (context_->scheme() != SchemeType::BFV && context_->scheme() != SchemeType::BGV) throw std::invalid_argument("[BatchEncoder::BatchEncoder] Unsupported scheme.");
+}
+void BatchEncoder::encode(const std::vector<uint64_t> &values, Plaintext &destination) const {
+    const size_t n = slot_count();
+    if (values.size() > n) throw std::invalid_argument("[BatchEncoder::encode_slice] Values has size larger than the number of slots.");
+    DeviceArray v(context_, (values.size() + 2) & ~(size_t)1);
+    if (!values.empty()) v.upload(values.data(), values.size());
+    Plaintext p = Plaintext::mod_t(context_, n);
+    const b2_status st = b2_batch_encode(context_->raw(), v.data(), values.size(), p.data(), context_->stream);
+    if (st == B2_ERR_INVALID_ARG) throw std::logic_error(std::string("[BatchEncoder::encode_slice] ") + b2_last_error());      // "does not support vector batching"
+    check(st, "[BatchEncoder::encode_slice]");
+    check(b2_stream_sync(context_->raw(), context_->stream), "[BatchEncoder::encode_slice]");
+    destination = std::move(p);
+}
+std::vector<uint64_t> BatchEncoder::decode_new(const Plaintext &plain) const {
+    if (plain.empty() || !plain.is_mod_t()) throw std::invalid_argument("[BatchEncoder::decode] Plaintext must be modulo t (no parms_id).");
+    if (plain.is_ntt_form()) throw std::invalid_argument("[BatchEncoder::decode] Plaintext is in NTT form.");
+    const size_t n = slot_count();
+    DeviceArray out(context_, n);
+    const b2_status st = b2_batch_decode(context_->raw(), plain.data(), plain.coeff_count(), out.data(), context_->stream);
+    if (st == B2_ERR_INVALID_ARG) throw std::logic_error(std::string("[BatchEncoder::encode] ") + b2_last_error());
+    check(st, "[BatchEncoder::decode]");
+    std::vector<uint64_t> v(n);
+    out.download(v.data(), n);
+    return v;
+}
+Plaintext BatchEncoder::encode_polynomial_new(const std::vector<uint64_t> &values) const {
+    if (values.size() > slot_count()) throw std::invalid_argument("[BatchEncoder::encode_polynomial_slice] Values has size larger than the number of slots.");
+    if (values.empty()) throw std::invalid_argument("[BatchEncoder::encode_polynomial_slice] Values is empty.");
+    std::vector<uint64_t> r(values);
+    const uint64_t t = context_->plain_modulus();
+    if (t < 2) throw std::invalid_argument("[BatchEncoder::encode_polynomial_slice] The context has no plain modulus.");
+    for (uint64_t &w : r) w %= t;
+    return Plaintext::from_host_mod_t(context_, r.data(), r.size());
+}
+
 // ---- KeyGenerator (src/key_generator.cu:31-78, 136-256) ---------------------------------------------------------------------------------
 KeyGenerator::KeyGenerator(HeContextPointer context, RandomGenerator &prng) : context_(std::move(context)), prng_(&prng) {
     sk_ = SecretKey::uninitialised(context_);

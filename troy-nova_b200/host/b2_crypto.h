@@ -58,6 +58,20 @@ private:
     DeviceArray buf_;
 };
 
+// src/batch_encoder.h (BFV / BGV with a batching plain modulus): SIMD slots <-> the plaintext polynomial modulo t
+class BatchEncoder {
+public:
+    explicit BatchEncoder(HeContextPointer context);
+    size_t slot_count() const { return context_->poly_modulus_degree(); }
+    void encode(const std::vector<uint64_t> &values, Plaintext &destination) const;
+    Plaintext encode_new(const std::vector<uint64_t> &values) const { Plaintext p; encode(values, p); return p; }
+    std::vector<uint64_t> decode_new(const Plaintext &plain) const;
+    // encode_polynomial (src/batch_encoder.cu:296-343): the values ARE the coefficients (reduced modulo t)
+    Plaintext encode_polynomial_new(const std::vector<uint64_t> &values) const;
+private:
+    HeContextPointer context_;
+};
+
 // src/key_generator.h: every key is drawn from the generator passed in, in call order, exactly as the reference's KeyGenerator draws from the context's
 // generator — same seed and call order => the reference's keys word for word (tests/test_keygen_gpu.py)
 class KeyGenerator {

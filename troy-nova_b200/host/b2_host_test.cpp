@@ -160,6 +160,14 @@ int main(int argc, char **argv) {
                 Decryptor kdec(ctx, kg.secret_key());
                 emit_plain(kdec.decrypt_new(kenc.encrypt_asymmetric_new(msg)));
             }
+            if (!ckks) {                                                                // BatchEncoder: encode the message words as slots, decode them back
+                BatchEncoder be(ctx);
+                const std::vector<uint64_t> slots(msg_words, msg_words + n / 2 + 1);
+                Plaintext ep = be.encode_new(slots);
+                emit_plain(ep);
+                const std::vector<uint64_t> back = be.decode_new(ep);
+                out.insert(out.end(), back.begin(), back.end());
+            }
             cprobe([&] { Plaintext d; dec.decrypt(z, d); });                             // contains a seed
             cprobe([&] { Ciphertext t2 = c1.clone(); t2.is_ntt_form() = !t2.is_ntt_form(); Plaintext d; dec.decrypt(t2, d); });   // wrong form for the scheme
         }
