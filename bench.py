@@ -288,6 +288,33 @@ def bench_c5_pack(b2, torch, timed, local, world):
     return r
 
 
+def bench_c1_quickstart(b2, torch, timed, local, world):
+    """BASELINE config 1 (the reference's quickstart, which it runs in host memory): BFV N=8192, q={40,40}+special 40, t 20 bits — BatchEncoder encode x2,
+    asymmetric encrypt x2, BEHZ multiply, relinearize, decrypt, decode, natively on the GPU with keys generated from a seed."""
+    log_n, n = 13, 1 << 13
+    moduli = b2.coeff_modulus_create(n, [40, 40, 40]); K = len(moduli); L = K - 1
+    ctx = b2.Context(log_n, moduli, 1032193, b2.BFV, device=local)
+    z = lambda w: torch.zeros(w, dtype=torch.int64, device="cuda")
+    g = b2.Prng(0x123, 0)
+    sk, pk, skp, rk = z(K * n), z(2 * K * n), z(2 * K * n), z(L * 2 * K * n)
+    ctx.generate_secret_key(g, sk); ctx.encrypt_zero_symmetric(sk, K, True, pk, g); ctx.secret_key_powers(sk, 2, skp)
+    ctx.generate_kswitch_key(sk, skp[K * n:], g, rk)
+    kh = ctx.kswitch_key(rk.view(L, 2, K, n))
+    x = torch.randint(0, 1032193, (n,), dtype=torch.int64, device="cuda"); y = torch.randint(0, 1032193, (n,), dtype=torch.int64, device="cuda")
+    px, py, cx, cy, prod, dec, out = z(n), z(n), z(2 * L * n), z(2 * L * n), z(3 * L * n), z(n), z(n)
+
+    def pipeline():
+        ctx.batch_encode(x, n, px); ctx.batch_encode(y, n, py)
+        ctx.encrypt(px, n, pk, True, L, cx, g); ctx.encrypt(py, n, pk, True, L, cy, g)
+        ctx.bfv_multiply(cx, cy, prod, L)
+        ctx.keyswitch(prod[2 * L * n:], L, False, kh, prod[:2 * L * n], b2.ASSIGN_ADD_INPLACE)
+        ctx.decrypt([prod[:2 * L * n]], [dec], 2, L, skp)
+        ctx.batch_decode(dec, n, out)
+    t = timed(pipeline, 10)
+    ok = bool(torch.equal(out, (x * y) % 1032193))
+    return {"pipeline_us": t * 1e6, "pipelines_per_s": world / t, "decoded_equals_slotwise_product": ok}
+
+
 def bench_c4(b2, torch, timed, local, world):
     """BASELINE config 4: BGV N=32768, q={60,40x7}+special 60: multiply + relinearize, then the mod-switch chain to the last level."""
     log_n, n = 15, 1 << 15
@@ -562,6 +589,7 @@ def main():
         extra["c2_bfv_n16384_batch256"] = bench_c2(b2, torch, timed, local, world)
         extra["c4_bgv_n32768"] = bench_c4(b2, torch, timed, local, world)
         extra["c5_bfv_n8192_packing"] = bench_c5_pack(b2, torch, timed, local, world)
+        extra["c1_bfv_n8192_quickstart"] = bench_c1_quickstart(b2, torch, timed, local, world)
         if world > 1:
             # ONE relinearize cut over all GPUs by RNS limb: all-gather of the coefficient-form target and
             # broadcast of the special limb over NCCL, everything else local to the modulus owner
