@@ -431,7 +431,8 @@ def main():
     tr = measured_traffic()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": tr["bytes_per_launch"] if tr else None, "traffic_source": tr["source"] if tr else None,
-                "kernel": "b2_ntt_forward over 420 limbs = ntt5_kernel (TMA, 380 FP64-pipe limbs) + ntt_persistent_kernel (40 integer-pipe limbs)",
+                "kernel": "b2_ntt_forward over 420 limbs = ONE launch of ntt_persistent_kernel<8,true,3,PlainLoad,PlainStore> (the operand mixes 380 FP64-pipe and 40 integer-pipe limbs; "
+                          "mixed launches take the cp.async queue kernel, all-FP64 launches the TMA kernel ntt5_kernel: csrc/b2_ntt5_launch.cuh run_ntt_split)",
                 "algorithmic_bytes_per_call": limbs * n * 16, "call_ms": fwd_s * 1e3, "peak_source": peak_src}
 
     # ---- end to end through the host-buffer C ABI (pinned host memory, H2D + D2H inside the timed region)
