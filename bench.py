@@ -537,8 +537,8 @@ def main():
             s = max_over_ranks(time.perf_counter() - t0)
             for nm in ("relinearize", "rotate"):
                 ksblocks[nm]["e2e"] = {"value": world * k / s, "unit": "ops/s", "h2d_bytes_per_step": 3 * L * n * 8, "d2h_bytes_per_step": 2 * L * n * 8,
-                                       "note": "b2_keyswitch_host: target + destination from pinned host memory, key resident, result back to the host; "
-                                               "measured on relinearize (rotate moves the same bytes)"}
+                                       "note": "b2_keyswitch_host: target + destination from pinned host memory, key resident, result back to the host (the destination's old contents "
+                                               "are uploaded on a copy stream under the keyswitch and added by one launch); measured on relinearize (rotate uploads one polynomial less)"}
             del h3, hd
         except Exception as ex:
             for nm in ("relinearize", "rotate"):

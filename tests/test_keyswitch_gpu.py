@@ -31,6 +31,10 @@ def test_keyswitch_all_assign_modes(b2, po, scheme, log_n, bits):
             d = to_dev(dest0)
             ctx.keyswitch(to_dev(target), decomp, is_ntt, kh, d, assign)
             assert np.array_equal(to_np(d), want), f"{SCHEMES[scheme]} decomp={decomp} assign={assign}"
+            # the host-buffer entry point (target and destination in host memory; the destination's old contents travel under the keyswitch)
+            hd = dest0.copy()
+            ctx.keyswitch_host(np.ascontiguousarray(target), decomp, is_ntt, kh, hd, assign)
+            assert np.array_equal(hd, want), f"{SCHEMES[scheme]} host buffers decomp={decomp} assign={assign}"
 
 
 def test_keyswitch_bfv_both_forms(b2, po):
