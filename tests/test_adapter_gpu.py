@@ -24,10 +24,10 @@ def _run(filt, adapter="1", timeout=900):
     m = re.search(r"\[  PASSED  \] (\d+) tests", out)
     stats = re.search(r"\[b2_adapter\] ntt (\d+) \(\+(\d+) batched\)\s+keyswitch (\d+) \(\+(\d+) batched\)\s+dyadic (\d+)\s+modswitch (\d+)\s+galois (\d+)\s+bfv_multiply (\d+) \| "
                       r"device calls left to the reference (\d+)", out)
-    extra = re.search(r"\[b2_adapter §8f\] samplers (\d+)\s+decrypt (\d+)\s+pack (\d+)", out)
+    extra = re.search(r"\[b2_adapter §8f\] samplers (\d+)\s+decrypt (\d+)\s+pack (\d+)\s+elementwise (\d+)", out)
     st = [int(x) for x in stats.groups()] if stats else None
     if st is not None:
-        st += [int(x) for x in extra.groups()] if extra else [0, 0, 0]      # 9 samplers, 10 decrypt, 11 pack
+        st += [int(x) for x in extra.groups()] if extra else [0, 0, 0, 0]      # 9 samplers, 10 decrypt, 11 pack, 12 element-wise (E1)
     return p.returncode, int(m.group(1)) if m else 0, st, out
 
 
@@ -45,8 +45,8 @@ def test_adapter_library_passes_host_tests_untouched():
 @needs_bin
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,filt,need", [
-    # (suite, gtest filter, indices of adapter counters that must be non-zero: 0 ntt 2 keyswitch 3 keyswitch_batched 4 dyadic 5 modswitch 6 galois 7 bfv_multiply 9 samplers 10 decrypt 11 pack)
-    ("evaluator", "EvaluatorTest.Device*", [0, 2, 4, 5, 6, 7]),
+    # (suite, gtest filter, indices of adapter counters that must be non-zero: 0 ntt 2 keyswitch 3 keyswitch_batched 4 dyadic 5 modswitch 6 galois 7 bfv_multiply 9 samplers 10 decrypt 11 pack 12 element-wise)
+    ("evaluator", "EvaluatorTest.Device*", [0, 2, 4, 5, 6, 7, 12]),
     ("evaluator_batched", "EvaluatorBatchTest.Device*", [0, 1, 3, 4]),
     ("encryptor_decryptor_keygen", "EncryptorTest.Device*:EncryptorBatchTest.Device*:SpecialPrimeForEncryptionTest.Device*", [0, 9, 10]),
     # (RandomGeneratorTest.Device* samples modulo 12345 / 23456 / 56789 — not an NTT-friendly chain, so those calls stay with the reference by
