@@ -51,7 +51,7 @@ struct ModDownLoad {      // NTT-form path: the transform's input IS the term
 };
 // batches are passed to the kernels BY VALUE as small pointer tables (no per-call device upload of pointer arrays,
 // cf. the reference's construct_batch, src/utils/box_batch.h:222-247); larger batches are processed in chunks
-constexpr int KS_MAXB = 64;
+constexpr int KS_MAXB = 128;
 struct PtrTab { const u64 *p[KS_MAXB]; };
 struct PtrTabW { u64 *p[KS_MAXB]; };
 
